@@ -1,0 +1,424 @@
+// api.cu -- C ABI of libb2deflate.so (include/b2deflate.h): the host runtime around the sm_100a kernels.
+//
+// This is the layer the reference's stream classes would call through Panama FFM:
+//   InflaterInputStream.read  -> decomp/Open.read (Open.java:83-110)                 => b2d_inflate_batch
+//   DeflaterOutputStream.writeBuffer -> Strategy.decide / Decision.compressTo
+//                                    (DeflaterOutputStream.java:119-137)              => b2d_deflate_chunks
+//   java.util.zip.CRC32 at GzipOutputStream.java:57 / GzipInputStream.java:72          => b2d_crc32*
+// It owns one CUDA stream per direction of the copy pipeline, a grow-only device scratch pool and the
+// staging logic (H2D -> kernels -> D2H, sliced so copies overlap compute).  There is no CPU codec in this
+// library: without a usable sm_100 device every entry point returns B2D_ERR_NO_DEVICE.
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+#include <algorithm>
+#include "kernels.h"
+
+using namespace b2d;
+
+namespace {
+
+struct DevBuf {
+	void *p = nullptr;
+	size_t cap = 0;
+};
+
+struct Ctx {
+	bool ready = false;
+	int device = -1;
+	int sm_count = 0;
+	cudaStream_t st[3] = {nullptr, nullptr, nullptr};    // round-robin pipeline streams
+	cudaEvent_t ev[8] = {};
+	DevBuf in, out, meta, scratch, crc;
+	void *pinned_meta = nullptr;
+	size_t pinned_meta_cap = 0;
+	char last_error[256] = "";
+};
+
+Ctx g;
+std::mutex g_mu;
+
+int fail_cuda(cudaError_t e, const char *where) {
+	snprintf(g.last_error, sizeof g.last_error, "%s: %s", where, cudaGetErrorString(e));
+	cudaGetLastError();
+	return e == cudaErrorMemoryAllocation ? B2D_ERR_OUT_OF_MEMORY : B2D_ERR_CUDA;
+}
+#define CK(call)                                                     \
+	do {                                                             \
+		cudaError_t e_ = (call);                                     \
+		if (e_ != cudaSuccess) return fail_cuda(e_, #call);          \
+	} while (0)
+
+int ensure(DevBuf &b, size_t bytes) {
+	bytes = (bytes + 255) & ~(size_t)255;
+	if (bytes <= b.cap) return 0;
+	if (b.p) { cudaFree(b.p); b.p = nullptr; b.cap = 0; }
+	size_t want = bytes + bytes / 8;
+	cudaError_t e = cudaMalloc(&b.p, want);
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		want = bytes;
+		e = cudaMalloc(&b.p, want);
+	}
+	if (e != cudaSuccess) { b.p = nullptr; return fail_cuda(e, "cudaMalloc"); }
+	b.cap = want;
+	return 0;
+}
+
+int ensure_pinned_meta(size_t bytes) {
+	if (bytes <= g.pinned_meta_cap) return 0;
+	if (g.pinned_meta) cudaFreeHost(g.pinned_meta);
+	g.pinned_meta = nullptr;
+	g.pinned_meta_cap = 0;
+	CK(cudaMallocHost(&g.pinned_meta, bytes * 2));
+	g.pinned_meta_cap = bytes * 2;
+	return 0;
+}
+
+void release_all() {
+	for (DevBuf *b : {&g.in, &g.out, &g.meta, &g.scratch, &g.crc}) {
+		if (b->p) cudaFree(b->p);
+		b->p = nullptr;
+		b->cap = 0;
+	}
+	if (g.pinned_meta) cudaFreeHost(g.pinned_meta);
+	g.pinned_meta = nullptr;
+	g.pinned_meta_cap = 0;
+	for (auto &s : g.st) { if (s) cudaStreamDestroy(s); s = nullptr; }
+	for (auto &e : g.ev) { if (e) cudaEventDestroy(e); e = nullptr; }
+	g.ready = false;
+	g.device = -1;
+}
+
+int normalise_opts(const b2d_deflate_opts *o, uint64_t in_len, DeflateParams &p) {
+	b2d_deflate_opts d;
+	memset(&d, 0, sizeof d);
+	d.lazy = -1;
+	if (o) d = *o;
+	p.framing = d.framing;
+	if (p.framing != B2D_FRAMING_CHUNKED && p.framing != B2D_FRAMING_REFERENCE) return B2D_ERR_BAD_ARGUMENT;
+	p.block_bytes = d.block_bytes ? d.block_bytes : (1u << 16);
+	if (p.block_bytes < 4096 || p.block_bytes > (1u << 20)) return B2D_ERR_BAD_ARGUMENT;
+	if (p.framing == B2D_FRAMING_REFERENCE) {
+		// one unit: chunk = the whole input rounded up to whole blocks (must fit 32 bits)
+		uint64_t nb = std::max<uint64_t>(1, (in_len + p.block_bytes - 1) / p.block_bytes);
+		uint64_t cb = nb * p.block_bytes;
+		if (cb > 0xFFFF0000ull) return B2D_ERR_BAD_ARGUMENT;
+		p.chunk_bytes = (uint32_t)cb;
+	} else {
+		p.chunk_bytes = d.chunk_bytes ? d.chunk_bytes : (1u << 20);
+		if (p.chunk_bytes % p.block_bytes != 0) return B2D_ERR_BAD_ARGUMENT;
+	}
+	p.mode = d.mode;
+	if (p.mode < B2D_MODE_AUTO || p.mode > B2D_MODE_DYNAMIC) return B2D_ERR_BAD_ARGUMENT;
+	p.search = d.search;
+	if (p.search < B2D_SEARCH_DEFAULT || p.search > B2D_SEARCH_FULL) return B2D_ERR_BAD_ARGUMENT;
+	p.depth = d.chain_depth > 0 ? d.chain_depth : 8;
+	p.lazy = d.lazy < 0 ? 1 : (d.lazy ? 1 : 0);
+	if (p.search != B2D_SEARCH_DEFAULT) p.lazy = d.lazy > 0 ? 1 : 0;     // the reference strategies are greedy
+	p.is_last = d.is_last ? 1 : 0;
+	return 0;
+}
+
+// ---- device-pointer cores (caller holds g_mu) ----
+
+int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
+                       const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc,
+                       int32_t *d_status, uint32_t flags, cudaStream_t st) {
+	if (n == 0) return B2D_OK;
+	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st));
+	if ((flags & B2D_INFLATE_CRC32) && d_crc) CK(launch_crc32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
+	return B2D_OK;
+}
+
+int deflate_dev_locked(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out, uint64_t out_cap,
+                       uint64_t *d_total, uint64_t *d_chunk_len, uint32_t *d_chunk_crc, cudaStream_t st) {
+	size_t sb = deflate_scratch_bytes(in_len, p);
+	int r = ensure(g.scratch, sb);
+	if (r) return r;
+	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, g.scratch.p, g.scratch.cap, st));
+	if (d_chunk_crc) {
+		uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
+		CK(launch_crc32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
+	}
+	return B2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+#define B2D_API __attribute__((visibility("default")))
+
+B2D_API int b2d_init(int device) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g.ready && g.device == device) return B2D_OK;
+	if (g.ready) release_all();
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess || count == 0 || device < 0 || device >= count) {
+		snprintf(g.last_error, sizeof g.last_error, "no usable CUDA device %d (%s)", device,
+		         e == cudaSuccess ? "out of range" : cudaGetErrorString(e));
+		cudaGetLastError();
+		return B2D_ERR_NO_DEVICE;
+	}
+	cudaDeviceProp prop;
+	CK(cudaGetDeviceProperties(&prop, device));
+	if (prop.major != 10) {
+		snprintf(g.last_error, sizeof g.last_error, "device %d is sm_%d%d; libb2deflate is built for sm_100a only",
+		         device, prop.major, prop.minor);
+		return B2D_ERR_NO_DEVICE;
+	}
+	CK(cudaSetDevice(device));
+	for (auto &s : g.st) CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+	for (auto &ev : g.ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+	g.device = device;
+	g.sm_count = prop.multiProcessorCount;
+	g.ready = true;
+	return B2D_OK;
+}
+
+B2D_API void b2d_shutdown(void) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (g.ready) {
+		cudaSetDevice(g.device);
+		cudaDeviceSynchronize();
+		release_all();
+	}
+}
+
+B2D_API const char *b2d_strerror(int status) {
+	switch (status) {
+	case B2D_OK: return "OK";
+	case B2D_UNEXPECTED_END_OF_STREAM: return "Unexpected end of stream";
+	case B2D_RESERVED_BLOCK_TYPE: return "Reserved block type";
+	case B2D_UNCOMPRESSED_BLOCK_LENGTH_MISMATCH: return "len/nlen mismatch in uncompressed block";
+	case B2D_HUFFMAN_CODE_UNDER_FULL: return "This canonical code produces an under-full Huffman code tree";
+	case B2D_HUFFMAN_CODE_OVER_FULL: return "This canonical code produces an over-full Huffman code tree";
+	case B2D_NO_PREVIOUS_CODE_LENGTH_TO_COPY: return "No code length value to copy";
+	case B2D_CODE_LENGTH_CODE_OVER_FULL: return "Run exceeds number of codes";
+	case B2D_END_OF_BLOCK_CODE_ZERO_LENGTH: return "End-of-block symbol has zero code length";
+	case B2D_RESERVED_LENGTH_SYMBOL: return "Reserved run length symbol";
+	case B2D_RESERVED_DISTANCE_SYMBOL: return "Reserved distance symbol";
+	case B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE: return "Length symbol encountered with empty distance code";
+	case B2D_COPY_FROM_BEFORE_DICTIONARY_START: return "Attempting to copy from before start of dictionary";
+	case B2D_HEADER_CHECKSUM_MISMATCH: return "Header CRC-16 mismatch";
+	case B2D_UNSUPPORTED_COMPRESSION_METHOD: return "Unsupported compression method";
+	case B2D_DECOMPRESSED_CHECKSUM_MISMATCH: return "Decompression CRC-32 mismatch";
+	case B2D_DECOMPRESSED_SIZE_MISMATCH: return "Decompressed size mismatch";
+	case B2D_GZIP_INVALID_MAGIC_NUMBER: return "Invalid GZIP magic number";
+	case B2D_GZIP_RESERVED_FLAGS_SET: return "Reserved flags are set";
+	case B2D_GZIP_UNSUPPORTED_OPERATING_SYSTEM: return "Unsupported operating system value";
+	case B2D_ERR_OUTPUT_OVERFLOW: return "Output capacity exceeded";
+	case B2D_ERR_BAD_ARGUMENT: return "Bad argument";
+	case B2D_ERR_NO_DEVICE: return "No usable sm_100 GPU (b2d_init not called or failed); there is no CPU fallback";
+	case B2D_ERR_CUDA: return "CUDA runtime failure";
+	case B2D_ERR_OUT_OF_MEMORY: return "Out of device memory";
+	default: return "Unknown status";
+	}
+}
+
+B2D_API const char *b2d_last_error(void) { return g.last_error; }
+
+B2D_API int b2d_device_sm_count(void) { return g.ready ? g.sm_count : 0; }
+
+B2D_API void *b2d_alloc_pinned(size_t bytes) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return nullptr;
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+	return p;
+}
+
+B2D_API void b2d_free_pinned(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+// ---------------------------------------------------------------- inflate
+
+B2D_API int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
+                                  const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
+                                  uint32_t *d_crc32, int32_t *d_status, uint32_t flags, void *stream) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if (n && (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_in_consumed || !d_status))
+		return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & B2D_INFLATE_CRC32) && !d_crc32 && n) return B2D_ERR_BAD_ARGUMENT;
+	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	return inflate_dev_locked(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_crc32, d_status, flags, st);
+}
+
+// Host entry: the batch is cut into slices of members; slice k's H2D, kernels and D2H run on stream k % 3, so
+// the copy engines and the SMs overlap (PCIe is the end-to-end bound; pinned buffers from b2d_alloc_pinned make
+// the copies asynchronous).
+B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint8_t *out,
+                              const uint64_t *out_off, uint64_t *out_len, uint64_t *in_consumed, uint32_t *crc32,
+                              int32_t *status, uint32_t flags) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if (n == 0) return B2D_OK;
+	if (!in_off || !out_off || !out_len || !in_consumed || !status) return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & B2D_INFLATE_CRC32) && !crc32) return B2D_ERR_BAD_ARGUMENT;
+	for (uint32_t i = 0; i < n; i++)
+		if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) return B2D_ERR_BAD_ARGUMENT;
+	const uint64_t in0 = in_off[0], in_total = in_off[n] - in0;
+	const uint64_t out0 = out_off[0], out_total = out_off[n] - out0;
+	if ((in_total && !in) || (out_total && !out)) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	int r;
+	if ((r = ensure(g.in, in_total + 64))) return r;
+	if ((r = ensure(g.out, out_total + 64))) return r;
+	// meta layout (device): in_off[n+1] out_off[n+1] out_len[n] consumed[n] crc[n] status[n]
+	const size_t m_off_in = 0, m_off_out = (size_t)(n + 1) * 8, m_len = m_off_out + (size_t)(n + 1) * 8,
+	             m_cons = m_len + (size_t)n * 8, m_crc = m_cons + (size_t)n * 8, m_stat = m_crc + (size_t)n * 4,
+	             m_total = m_stat + (size_t)n * 4;
+	if ((r = ensure(g.meta, m_total))) return r;
+	if ((r = ensure_pinned_meta(m_total))) return r;
+	uint8_t *hm = (uint8_t *)g.pinned_meta, *dm = (uint8_t *)g.meta.p;
+	uint64_t *h_in_off = (uint64_t *)(hm + m_off_in), *h_out_off = (uint64_t *)(hm + m_off_out);
+	for (uint32_t i = 0; i <= n; i++) { h_in_off[i] = in_off[i] - in0; h_out_off[i] = out_off[i] - out0; }
+	uint8_t *d_in = (uint8_t *)g.in.p, *d_out = (uint8_t *)g.out.p;
+	CK(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, g.st[0]));
+	CK(cudaEventRecord(g.ev[0], g.st[0]));
+	// slices: ~16 MiB of output each, at least 1 member, at most 64 slices
+	uint32_t n_slices = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, out_total >> 24));
+	n_slices = std::min(n_slices, n);
+	uint32_t per = (n + n_slices - 1) / n_slices;
+	int k = 0;
+	for (uint32_t a = 0; a < n; a += per, k++) {
+		uint32_t b = std::min(n, a + per);
+		cudaStream_t st = g.st[k % 3];
+		if (k > 0 && k < 3) CK(cudaStreamWaitEvent(st, g.ev[0], 0));
+		uint64_t ia = h_in_off[a], ib = h_in_off[b], oa = h_out_off[a], ob = h_out_off[b];
+		// (a kernel may read the aligned words around its slice while a neighbour's copy lands in them; those bytes
+		// are shifted out / masked by the bit reader, so the race is benign)
+		if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
+		r = inflate_dev_locked(d_in, (const uint64_t *)(dm + m_off_in) + a, b - a, d_out,
+		                       (const uint64_t *)(dm + m_off_out) + a, (uint64_t *)(dm + m_len) + a,
+		                       (uint64_t *)(dm + m_cons) + a, (uint32_t *)(dm + m_crc) + a,
+		                       (int32_t *)(dm + m_stat) + a, flags, st);
+		if (r) return r;
+		if (ob > oa) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
+	}
+	for (int s = 1; s < 3 && s < k; s++) {
+		CK(cudaEventRecord(g.ev[s], g.st[s]));
+		CK(cudaStreamWaitEvent(g.st[0], g.ev[s], 0));
+	}
+	CK(cudaMemcpyAsync(hm + m_len, dm + m_len, m_total - m_len, cudaMemcpyDeviceToHost, g.st[0]));
+	CK(cudaStreamSynchronize(g.st[0]));
+	memcpy(out_len, hm + m_len, (size_t)n * 8);
+	memcpy(in_consumed, hm + m_cons, (size_t)n * 8);
+	if (crc32 && (flags & B2D_INFLATE_CRC32)) memcpy(crc32, hm + m_crc, (size_t)n * 4);
+	memcpy(status, hm + m_stat, (size_t)n * 4);
+	return B2D_OK;
+}
+
+// ---------------------------------------------------------------- deflate
+
+B2D_API uint64_t b2d_deflate_bound(uint64_t in_len, uint32_t chunk_bytes) {
+	return deflate_bound_bytes(in_len, chunk_bytes ? chunk_bytes : (1u << 20), 1u << 16);
+}
+
+B2D_API int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *d_out,
+                                   uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
+                                   uint32_t *d_chunk_crc32, void *stream) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	DeflateParams p;
+	int r = normalise_opts(opts, in_len, p);
+	if (r) return r;
+	if ((in_len && !d_in) || !d_out || !d_out_len_total) return B2D_ERR_BAD_ARGUMENT;
+	if (out_cap < deflate_bound_bytes(in_len, p.chunk_bytes, p.block_bytes)) return B2D_ERR_OUTPUT_OVERFLOW;
+	CK(cudaSetDevice(g.device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	return deflate_dev_locked(d_in, in_len, p, d_out, out_cap, d_out_len_total, d_chunk_out_len, d_chunk_crc32, st);
+}
+
+B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *out,
+                                   uint64_t out_cap, uint32_t *crc32_inout, uint64_t *chunk_out_len) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	DeflateParams p;
+	int r = normalise_opts(opts, in_len, p);
+	if (r) return r;
+	if ((in_len && !in) || !out) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	const uint64_t bound = deflate_bound_bytes(in_len, p.chunk_bytes, p.block_bytes);
+	const uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
+	if ((r = ensure(g.in, in_len + 64))) return r;
+	if ((r = ensure(g.out, bound + 64))) return r;
+	const size_t m_total_off = 0, m_clen = 8, m_ccrc = m_clen + (size_t)(n_chunks + 1) * 8,
+	             m_total = m_ccrc + (size_t)(n_chunks + 1) * 4;
+	if ((r = ensure(g.meta, m_total))) return r;
+	if ((r = ensure_pinned_meta(m_total))) return r;
+	uint8_t *dm = (uint8_t *)g.meta.p, *hm = (uint8_t *)g.pinned_meta;
+	cudaStream_t st = g.st[0];
+	if (in_len) CK(cudaMemcpyAsync(g.in.p, in, in_len, cudaMemcpyHostToDevice, st));
+	r = deflate_dev_locked((const uint8_t *)g.in.p, in_len, p, (uint8_t *)g.out.p, bound, (uint64_t *)(dm + m_total_off),
+	                       (uint64_t *)(dm + m_clen), crc32_inout ? (uint32_t *)(dm + m_ccrc) : nullptr, st);
+	if (r) return r;
+	CK(cudaMemcpyAsync(hm, dm, m_total, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t total = *(uint64_t *)(hm + m_total_off);
+	if (total > out_cap) return B2D_ERR_OUTPUT_OVERFLOW;
+	if (total) CK(cudaMemcpyAsync(out, g.out.p, total, cudaMemcpyDeviceToHost, st));
+	const uint64_t *cl = (const uint64_t *)(hm + m_clen);
+	if (chunk_out_len) {
+		if (p.framing == B2D_FRAMING_REFERENCE) chunk_out_len[0] = total;
+		else memcpy(chunk_out_len, cl, (size_t)n_chunks * 8);
+	}
+	if (crc32_inout) {
+		const uint32_t *cc = (const uint32_t *)(hm + m_ccrc);
+		uint32_t crc = *crc32_inout;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			uint64_t len = std::min<uint64_t>(p.chunk_bytes, in_len - (uint64_t)c * p.chunk_bytes);
+			crc = host_crc32_combine(crc, cc[c], len);
+		}
+		*crc32_inout = crc;
+	}
+	CK(cudaStreamSynchronize(st));
+	return (int64_t)total;
+}
+
+// ---------------------------------------------------------------- CRC-32
+
+B2D_API uint32_t b2d_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b) {
+	return host_crc32_combine(crc_a, crc_b, len_b);
+}
+
+B2D_API int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_out, void *stream) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if ((len && !d_data) || !d_crc_out) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	const uint64_t piece = 1u << 20;
+	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
+	int r = ensure(g.crc, (size_t)(n_pieces + 1) * 4);
+	if (r) return r;
+	CK(launch_crc32_pieces(d_data, len, piece, n_pieces, (uint32_t *)g.crc.p, st));
+	CK(launch_crc32_fold(( const uint32_t *)g.crc.p, n_pieces, piece, len, d_crc_out, st));
+	return B2D_OK;
+}
+
+B2D_API uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready || len == 0 || !data) return crc;     // no device: unchanged (callers check b2d_init's result)
+	if (cudaSetDevice(g.device) != cudaSuccess) return crc;
+	if (ensure(g.in, len + 64)) return crc;
+	const uint64_t piece = 1u << 20;
+	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
+	if (ensure(g.crc, (size_t)(n_pieces + 1) * 4)) return crc;
+	if (ensure_pinned_meta(8)) return crc;
+	cudaStream_t st = g.st[0];
+	uint32_t *d_res = (uint32_t *)g.crc.p + n_pieces;
+	if (cudaMemcpyAsync(g.in.p, data, len, cudaMemcpyHostToDevice, st) != cudaSuccess) return crc;
+	if (launch_crc32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st) != cudaSuccess) return crc;
+	if (launch_crc32_fold((const uint32_t *)g.crc.p, n_pieces, piece, len, d_res, st) != cudaSuccess) return crc;
+	if (cudaMemcpyAsync(g.pinned_meta, d_res, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return crc;
+	if (cudaStreamSynchronize(st) != cudaSuccess) return crc;
+	return host_crc32_combine(crc, *(uint32_t *)g.pinned_meta, len);
+}
+
+}  // extern "C"

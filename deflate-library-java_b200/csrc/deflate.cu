@@ -1,0 +1,861 @@
+// deflate.cu -- chunked DEFLATE encoder for sm_100a.
+//
+// Replaces the encode path of the reference (paths relative to src/io/nayuki/deflate/):
+//   comp/Lz77Huffman.java:68-130   greedy brute-force match loop   -> chains_kernel + match_kernel + parse_kernel
+//   comp/Lz77Huffman.java:66-67,89,109,125,132  histograms          -> parse_kernel (shared-memory atomics)
+//   comp/Lz77Huffman.java:143-265,309-335,372-391  package-merge, code-length RLE, header, canonical codes
+//                                                                   -> huffman_kernel (one warp per block)
+//   comp/Uncompressed.java:19-48, comp/MultiStrategy.java:31-57     -> layout_kernel (cost rule per start bit)
+//   comp/Lz77Huffman.java:267-285 + DeflaterOutputStream.java:141-171 bit emission -> emit_kernel
+//   DeflaterOutputStream.java:119-137 framing                       -> independent chunks joined by empty stored blocks
+//
+// Pipeline (all on one stream, no host round trips):
+//   chains : one warp per block re-inserts the preceding 32 KiB and links every position to the previous
+//            position with the same 15-bit hash (u16 distance per input byte)
+//   match  : one CTA per 32 KiB tile; the 64 KiB window and its links are staged in shared memory with 128-bit
+//            loads; one thread per position walks the chain (depth-limited) -> (len, dist) per position
+//   parse  : one warp per block walks the positions (greedy or lazy), writes tokens and lit/len + distance
+//            histograms
+//   huffman: one warp per block: exact package-merge (limit 15 / 7), code-length RLE, header bits, block costs
+//   layout : one thread per chunk picks stored / fixed / dynamic per block and assigns bit offsets;
+//            scan_kernel turns chunk sizes into byte offsets
+//   emit   : one CTA per block: prefix sum of code lengths, bits OR-ed into a shared staging tile, coalesced out
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b2d {
+
+constexpr int HASH_BITS = 15;
+constexpr u32 WINDOW = 32768;
+constexpr int MAX_MATCH = 258;
+constexpr u32 TILE = 32768;                 // positions per match CTA
+constexpr int MATCH_THREADS = 1024;
+constexpr u32 MATCH_DATA_WORDS = (WINDOW + TILE + 272) / 4;
+constexpr size_t MATCH_SMEM = MATCH_DATA_WORDS * 4 + (size_t)(WINDOW + TILE) * 2;
+constexpr int HDR_WORDS = 144;
+
+__constant__ u8 CL_ORDER_D[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};   // Lz77Huffman.java:368-369
+
+// match / token entry: [31:24] literal byte at the position, [23:15] length (0 = literal), [14:0] distance - 1
+__device__ __forceinline__ u32 tok_len(u32 e) { return (e >> 15) & 0x1FF; }
+__device__ __forceinline__ u32 tok_dist(u32 e) { return (e & 0x7FFF) + 1; }
+
+struct BlockRec {
+	u32 hist_ll[288];
+	u32 hist_d[32];
+	u32 code_ll[288];       // bit-reversed code << 4 | length  (Lz77Huffman.codeLengthsToCodes, :372-391)
+	u32 code_d[32];
+	u32 hdr[HDR_WORDS];     // dynamic header after the 3 block-header bits, LSB-first
+	u32 hdr_bits;
+	u32 n_tokens;           // without the end-of-block symbol
+	u32 cost_fixed;         // whole block in bits, fixed code    (3 + symbols + extra bits)
+	u32 cost_dyn;           // whole block in bits, dynamic code  (3 + header + symbols + extra bits)
+	u32 mode;               // set by layout: 1 stored, 2 fixed, 3 dynamic
+	u32 bfinal;
+	u64 out_bit;            // bit offset of the block inside its chunk's output
+};
+
+// ---------------------------------------------------------------- helpers
+__device__ __forceinline__ u32 load4_global(const u8 *in, u64 p, u64 n_words) {   // unaligned LE 4-byte read
+	const u32 *w = (const u32 *)in;
+	u64 i = p >> 2;
+	u32 a = i < n_words ? __ldg(w + i) : 0u;
+	u32 b = i + 1 < n_words ? __ldg(w + i + 1) : 0u;
+	return __funnelshift_r(a, b, (u32)(p & 3) * 8);
+}
+__device__ __forceinline__ u32 hash4(u32 v, int hb) {
+	if (hb == 3) v &= 0xFFFFFFu;
+	return (v * 2654435761u) >> (32 - HASH_BITS);
+}
+__device__ __forceinline__ int len_symbol(int len, int &ne, int &extra) {          // Lz77Huffman.java:93-107
+	int r = len - 3;
+	if (len < 11) { ne = 0; extra = 0; return r + 257; }
+	if (len == 258) { ne = 0; extra = 0; return 285; }
+	ne = 29 - __clz(r);
+	extra = r & ((1 << ne) - 1);
+	return (ne << 2) + (r >> ne) + 257;
+}
+__device__ __forceinline__ int dist_symbol(int dist, int &ne, int &extra) {        // Lz77Huffman.java:113-123
+	int d = dist - 1;
+	if (dist < 5) { ne = 0; extra = 0; return d; }
+	ne = 30 - __clz(d);
+	extra = d & ((1 << ne) - 1);
+	return (ne << 1) + (d >> ne);
+}
+__device__ __forceinline__ int ll_extra_bits(int sym) { return (sym >= 265 && sym < 285) ? (sym - 261) >> 2 : 0; }
+__device__ __forceinline__ int d_extra_bits(int sym) { return sym >= 4 ? (sym >> 1) - 1 : 0; }
+__device__ __forceinline__ int fixed_ll_len(int sym) { return sym < 144 ? 8 : sym < 256 ? 9 : sym < 280 ? 7 : 8; }
+
+__device__ __forceinline__ u32 warp_sum(u32 v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
+	return v;
+}
+
+// ---------------------------------------------------------------- K1a: hash chains
+__global__ void __launch_bounds__(32)
+chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, int hb, u16 *__restrict__ prevdist) {
+	extern __shared__ __align__(16) u16 head[];      // 1 << HASH_BITS entries: low 16 bits of the chunk-relative position
+	const u32 lane = threadIdx.x;
+	const u64 bs = (u64)blockIdx.x * block_bytes;
+	const u64 be = min(n, bs + block_bytes);
+	const u64 cs = bs / chunk_bytes * chunk_bytes;
+	const u64 ce = min(n, cs + chunk_bytes);
+	const u64 ws = (bs - cs > WINDOW) ? bs - WINDOW : cs;       // re-insert up to 32 KiB before the block
+	const u64 n_words = (n + 3) >> 2;
+	for (u32 i = lane; i < (2u << HASH_BITS) / 16; i += 32) ((uint4 *)head)[i] = make_uint4(0, 0, 0, 0);
+	__syncwarp();
+	const u32 ws_rel = (u32)(ws - cs);
+	for (u64 base = ws; base < be; base += 32) {
+		const u64 p = base + lane;
+		const bool valid = p < be && p + hb <= ce;
+		u32 v = valid ? load4_global(in, p, n_words) : 0u;
+		const u32 h = hash4(v, hb);
+		const u32 grp = __match_any_sync(FULL_MASK, valid ? h : (0x80000000u | lane));
+		const u32 lower = grp & lanemask_lt();
+		const u32 prel = (u32)(p - cs);
+		u32 dist = 0;
+		if (valid) {
+			if (lower) dist = lane - (31 - __clz(lower));       // same hash earlier in this group of 32
+			else {
+				u32 d = (prel - head[h]) & 0xFFFFu;
+				if (d == 0) d = 65536;
+				if (d <= WINDOW && d <= prel - ws_rel) dist = d;
+			}
+		}
+		__syncwarp();
+		if (valid && (grp >> lane) == 1u) head[h] = (u16)prel;    // highest lane of the group
+		__syncwarp();
+		if (p >= bs && p < be) prevdist[p] = (u16)dist;
+	}
+}
+
+// ---------------------------------------------------------------- K1b: match search
+struct MatchParams {
+	int search, hb, depth, nice;
+};
+
+__device__ __forceinline__ u32 sm_load4(const u32 *W, u32 o) {
+	return __funnelshift_r(W[o >> 2], W[(o >> 2) + 1], (o & 3) * 8);
+}
+// number of equal bytes of a[0..] and b[0..], at most maxlen
+__device__ __forceinline__ int sm_match_len(const u32 *W, u32 a, u32 b, int maxlen) {
+	int len = 0;
+	while (len < maxlen) {
+		u32 x = sm_load4(W, a + len) ^ sm_load4(W, b + len);
+		if (x) { len += (__ffs(x) - 1) >> 3; break; }
+		len += 4;
+	}
+	return len < maxlen ? len : maxlen;
+}
+
+__global__ void __launch_bounds__(MATCH_THREADS, 1)
+match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, MatchParams mp,
+             const u16 *__restrict__ prevdist, u32 *__restrict__ match) {
+	extern __shared__ __align__(16) u32 msm[];
+	u32 *W = msm;                                     // window bytes as words, W[0] = byte win_start
+	u16 *P = (u16 *)(msm + MATCH_DATA_WORDS);         // links for [win_start, tile_end)
+	const u64 ts = (u64)blockIdx.x * TILE;
+	const u64 te = min(n, ts + TILE);
+	const u64 cs = ts / chunk_bytes * chunk_bytes;
+	const u64 ce = min(n, cs + chunk_bytes);
+	const u64 win = (ts - cs > WINDOW) ? ts - WINDOW : cs;
+	const u64 n16 = (n + 15) >> 4;
+	{   // stage data: 128-bit loads, zero past the end of input
+		const uint4 *src = (const uint4 *)in + (win >> 4);
+		const u64 first16 = win >> 4;
+		uint4 *dst = (uint4 *)W;
+		for (u32 i = threadIdx.x; i < MATCH_DATA_WORDS / 4; i += MATCH_THREADS)
+			dst[i] = (first16 + i < n16) ? __ldg(src + i) : make_uint4(0, 0, 0, 0);
+		if (mp.search == B2D_SEARCH_DEFAULT || mp.search == 3) {
+			const uint4 *ps = (const uint4 *)(prevdist + win);
+			uint4 *pd = (uint4 *)P;
+			const u32 cnt16 = (u32)((te - win + 7) >> 3);
+			const u64 p16_lim = (n + 7) >> 3;
+			for (u32 i = threadIdx.x; i < cnt16; i += MATCH_THREADS)
+				pd[i] = ((win >> 3) + i < p16_lim) ? __ldg(ps + i) : make_uint4(0, 0, 0, 0);
+		}
+	}
+	__syncthreads();
+	const u32 woff = (u32)(ts - win);                 // offset of the tile inside the window
+	for (u32 k = threadIdx.x; k < (u32)(te - ts); k += MATCH_THREADS) {
+		const u64 p = ts + k;
+		const u32 o = woff + k;
+		const u32 cur = sm_load4(W, o);
+		const u64 blk_end = min(ce, (p / block_bytes + 1) * block_bytes);
+		const int maxlen = (int)min((u64)MAX_MATCH, blk_end - p);   // runs stop at the block end (Lz77Huffman.java:75)
+		int best_len = 0, best_dist = 0;
+		if (mp.search == B2D_SEARCH_RLE) {
+			if (p > cs && maxlen >= 3) {                           // distance 1 only (RLE_*, Lz77Huffman.java:301-302)
+				int len = sm_match_len(W, o - 1, o, maxlen);
+				if (len >= 3) { best_len = len; best_dist = 1; }
+			}
+		} else if (mp.search != B2D_SEARCH_LITERAL && maxlen >= mp.hb && p + mp.hb <= ce) {
+			const u32 cmask = mp.hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
+			const u32 max_dist = (u32)min((u64)WINDOW, p - cs);
+			u32 d = P[o];
+			u32 dist = 0;
+			int depth = mp.depth;
+			best_len = mp.hb - 1;
+			while (d != 0 && depth-- > 0) {
+				dist += d;
+				if (dist > max_dist) break;
+				const u32 c = o - dist;
+				if (((sm_load4(W, c) ^ cur) & cmask) == 0) {
+					int len = mp.hb + sm_match_len(W, c + mp.hb, o + mp.hb, maxlen - mp.hb);
+					if (len > best_len) {                          // strict: ties keep the smaller distance (:80)
+						best_len = len;
+						best_dist = (int)dist;
+						if (len >= mp.nice || len >= maxlen) break;
+					}
+				}
+				d = P[c];
+			}
+			if (best_dist == 0) best_len = 0;
+		}
+		match[p] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
+	}
+}
+
+// ---------------------------------------------------------------- K2: parse + histograms
+constexpr int PARSE_WARPS = 4;
+
+__device__ __forceinline__ void hist_token(u32 *hist, u32 tok) {
+	int len = (int)tok_len(tok);
+	if (len == 0) { atomicAdd(&hist[tok >> 24], 1u); return; }
+	int ne, ex;
+	atomicAdd(&hist[len_symbol(len, ne, ex)], 1u);
+	atomicAdd(&hist[288 + dist_symbol((int)tok_dist(tok), ne, ex)], 1u);
+}
+
+__global__ void __launch_bounds__(PARSE_WARPS * 32)
+parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks, int lazy,
+             u32 *__restrict__ tokens, BlockRec *__restrict__ recs) {
+	__shared__ u32 hist_sm[PARSE_WARPS][320];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 g = blockIdx.x * PARSE_WARPS + warp;
+	if (g >= n_blocks) return;
+	u32 *hist = hist_sm[warp];
+	for (int i = lane; i < 320; i += 32) hist[i] = 0;
+	__syncwarp();
+	const u64 bs = (u64)g * block_bytes, be = min(n, bs + block_bytes);
+	u64 i = bs;
+	u64 base = bs & ~(u64)31;
+	u32 w0 = base + lane < n ? match[base + lane] : 0u;
+	u32 w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
+	u32 ntok = 0, my_tok = 0;
+	while (i < be) {
+		u32 o = (u32)(i - base);
+		if (o >= 64) {
+			base = i & ~(u64)31;
+			w0 = base + lane < n ? match[base + lane] : 0u;
+			w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
+			o = (u32)(i - base);
+		} else if (o >= 32) {
+			base += 32;
+			w0 = w1;
+			w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
+			o -= 32;
+		}
+		u32 e = __shfl_sync(FULL_MASK, w0, o);
+		u32 len = tok_len(e);
+		if (lazy && len) {                                 // defer when the next position matches longer
+			u32 e1 = __shfl_sync(FULL_MASK, o < 31 ? w0 : w1, (o + 1) & 31);
+			if (i + 1 < be && tok_len(e1) > len) len = 0;
+		}
+		u32 tok = len ? e : (e & 0xFF000000u);
+		if (lane == (ntok & 31)) my_tok = tok;
+		ntok++;
+		if ((ntok & 31) == 0) {
+			tokens[bs + ntok - 32 + lane] = my_tok;
+			hist_token(hist, my_tok);
+		}
+		i += len ? len : 1;
+	}
+	if (lane < (ntok & 31)) {
+		tokens[bs + (ntok & ~31u) + lane] = my_tok;
+		hist_token(hist, my_tok);
+	}
+	__syncwarp();
+	if (lane == 0) { hist[256] += 1; recs[g].n_tokens = ntok; }   // end-of-block (Lz77Huffman.java:131-132)
+	__syncwarp();
+	for (int k = lane; k < 288; k += 32) recs[g].hist_ll[k] = hist[k];
+	recs[g].hist_d[lane] = hist[288 + lane];
+}
+
+// ---------------------------------------------------------------- K3: Huffman construction
+constexpr int HUFF_WARPS = 2;
+
+struct HuffSmem {
+	u32 keys[512];
+	u32 leaf_w[288];
+	u32 pk_a[288];
+	u32 pk_b[288];
+	u32 merged[576];
+	u32 leafmask[15][18];
+	u32 hist[320];
+	u32 cnt[16];
+	u32 run[16];
+	u32 first[16];
+	u32 cl_hist[19];
+	u32 cl_code[19];
+	u32 level_leaves[15];
+	u32 hdr[HDR_WORDS];
+	u16 leaf_sym[288];
+	u8 lens[320];
+	u8 cl_len[19];
+	u8 cl_sym[320];
+	u8 cl_ext[320];
+};
+
+// calcHuffmanCodeLengths (Lz77Huffman.java:309-335): exact package-merge.  The reference's stable sort puts, among
+// equal weights, packages before leaves and leaves in symbol order; the merged order is rebuilt here from ranks
+// (leaf r sits after every package with weight <= its own; package j after every leaf with smaller weight).  A
+// leaf's code length is the number of levels in which it lies inside the selected prefix, which equals the
+// reference's countOccurrences over the first nLeaves-1 final packages.
+template <int SORT_N>
+__device__ void package_merge(HuffSmem *s, const u32 *hist, int n, int maxlen, u8 *out_lens, u32 lane) {
+	for (int i = lane; i < n; i += 32) out_lens[i] = 0;
+	int nl;
+	if (SORT_N == 32) {
+		u32 key = ((int)lane < n && hist[lane] > 0) ? (hist[lane] << 9 | lane) : 0xFFFFFFFFu;
+		u32 rank = 0;
+		for (int j = 0; j < 32; j++) rank += __shfl_sync(FULL_MASK, key, j) < key;
+		nl = __popc(__ballot_sync(FULL_MASK, key != 0xFFFFFFFFu));
+		if (key != 0xFFFFFFFFu) { s->leaf_w[rank] = key >> 9; s->leaf_sym[rank] = (u16)(key & 511); }
+	} else {
+		int cnt = 0;
+		for (int i = lane; i < 512; i += 32) {
+			u32 key = (i < n && hist[i] > 0) ? (hist[i] << 9 | (u32)i) : 0xFFFFFFFFu;
+			s->keys[i] = key;
+			cnt += key != 0xFFFFFFFFu;
+		}
+		nl = (int)warp_sum((u32)cnt);
+		__syncwarp();
+		for (int k = 2; k <= 512; k <<= 1) {           // bitonic sort, ascending
+			for (int j = k >> 1; j > 0; j >>= 1) {
+				for (int t = lane; t < 256; t += 32) {
+					int a = ((t & ~(j - 1)) << 1) | (t & (j - 1));
+					int b = a | j;
+					u32 x = s->keys[a], y = s->keys[b];
+					bool up = (a & k) == 0;
+					if ((x > y) == up) { s->keys[a] = y; s->keys[b] = x; }
+				}
+				__syncwarp();
+			}
+		}
+		for (int r = lane; r < nl; r += 32) { s->leaf_w[r] = s->keys[r] >> 9; s->leaf_sym[r] = (u16)(s->keys[r] & 511); }
+	}
+	__syncwarp();
+	if (nl < 2) return;                                // the reference would return all zeros too
+	for (int i = lane; i < 15 * 18; i += 32) (&s->leafmask[0][0])[i] = 0;
+	__syncwarp();
+	u32 *pk = s->pk_a, *pk_new = s->pk_b;
+	int npk = 0;
+	for (int lvl = 0; lvl < maxlen; lvl++) {
+		for (int r = lane; r < nl; r += 32) {          // leaves: after packages with weight <= own
+			u32 w = s->leaf_w[r];
+			int lo = 0, hi = npk;
+			while (lo < hi) { int mid = (lo + hi) >> 1; if (pk[mid] <= w) lo = mid + 1; else hi = mid; }
+			int pos = r + lo;
+			s->merged[pos] = w;
+			atomicOr(&s->leafmask[lvl][pos >> 5], 1u << (pos & 31));
+		}
+		for (int j = lane; j < npk; j += 32) {         // packages: after leaves with smaller weight
+			u32 w = pk[j];
+			int lo = 0, hi = nl;
+			while (lo < hi) { int mid = (lo + hi) >> 1; if (s->leaf_w[mid] < w) lo = mid + 1; else hi = mid; }
+			s->merged[j + lo] = w;
+		}
+		__syncwarp();
+		int nn = (npk + nl) >> 1;
+		for (int j = lane; j < nn; j += 32) pk_new[j] = s->merged[2 * j] + s->merged[2 * j + 1];
+		__syncwarp();
+		u32 *t = pk; pk = pk_new; pk_new = t;
+		npk = nn;
+	}
+	int m = 2 * (nl - 1);
+	for (int lvl = maxlen - 1; lvl >= 0; lvl--) {      // selected prefix per level, top down
+		u32 c = 0;
+		if (lane < 18) {
+			u32 w = s->leafmask[lvl][lane];
+			int lo = (int)lane * 32;
+			if (m >= lo + 32) c = __popc(w);
+			else if (m > lo) c = __popc(w & ((1u << (m - lo)) - 1));
+		}
+		c = warp_sum(c);
+		if (lane == 0) s->level_leaves[lvl] = c;
+		m = 2 * (m - (int)c);
+	}
+	__syncwarp();
+	for (int r = lane; r < nl; r += 32) {
+		int len = 0;
+		for (int lvl = 0; lvl < maxlen; lvl++) len += s->level_leaves[lvl] > (u32)r;
+		out_lens[s->leaf_sym[r]] = (u8)len;
+	}
+	__syncwarp();
+}
+
+// codeLengthsToCodes (Lz77Huffman.java:372-391): canonical, bit-reversed, packed code << 4 | len
+__device__ void assign_codes(HuffSmem *s, const u8 *lens, int n, u32 *codes, u32 lane) {
+	if (lane < 16) { s->cnt[lane] = 0; s->run[lane] = 0; }
+	__syncwarp();
+	for (int i = lane; i < n; i += 32) if (lens[i]) atomicAdd(&s->cnt[lens[i]], 1u);
+	__syncwarp();
+	if (lane == 0) {
+		u32 code = 0, prev = 0;
+		for (int l = 1; l <= 15; l++) { code = (code + prev) << 1; s->first[l] = code; prev = s->cnt[l]; }
+	}
+	__syncwarp();
+	for (int base = 0; base < n; base += 32) {
+		int i = base + (int)lane;
+		int l = i < n ? lens[i] : 0;
+		u32 grp = __match_any_sync(FULL_MASK, l);
+		u32 r = __popc(grp & lanemask_lt());
+		u32 start = s->run[l];
+		__syncwarp();
+		if (r == 0) s->run[l] = start + __popc(grp);
+		__syncwarp();
+		if (i < n) codes[i] = l ? ((__brev(s->first[l] + start + r) >> (32 - l)) << 4 | (u32)l) : 0u;
+	}
+	__syncwarp();
+}
+
+struct BitW { u32 *w; u32 pos; };
+__device__ __forceinline__ void bw_put(BitW &b, u32 v, int n) {      // single writer (lane 0), n <= 16
+	if (n == 0) return;
+	u32 i = b.pos >> 5, sh = b.pos & 31;
+	b.w[i] |= v << sh;
+	if (sh + n > 32) b.w[i + 1] |= v >> (32 - sh);
+	b.pos += n;
+}
+
+__global__ void __launch_bounds__(HUFF_WARPS * 32)
+huffman_kernel(BlockRec *__restrict__ recs, u32 n_blocks, u64 n, u32 block_bytes) {
+	__shared__ HuffSmem hs[HUFF_WARPS];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 g = blockIdx.x * HUFF_WARPS + warp;
+	if (g >= n_blocks) return;
+	HuffSmem *s = &hs[warp];
+	BlockRec *rec = &recs[g];
+	const u64 bs = (u64)g * block_bytes;
+	const u32 data_len = (u32)(min(n, bs + block_bytes) - min(n, bs));
+	for (int i = lane; i < 288; i += 32) s->hist[i] = rec->hist_ll[i];
+	s->hist[288 + lane] = rec->hist_d[lane];
+	__syncwarp();
+
+	// fixed-code cost (Lz77Huffman *_STATIC): 3 header bits + codes + extra bits
+	u32 fixed = 0, extra_bits = 0;
+	for (int i = lane; i < 286; i += 32) { fixed += s->hist[i] * fixed_ll_len(i); extra_bits += s->hist[i] * ll_extra_bits(i); }
+	if (lane < 30) { fixed += s->hist[288 + lane] * 5; extra_bits += s->hist[288 + lane] * d_extra_bits(lane); }
+	fixed = warp_sum(fixed);
+	extra_bits = warp_sum(extra_bits);
+
+	// histogram fix-ups (Lz77Huffman.java:145-181)
+	if (lane == 0 && data_len == 0) s->hist[0] += 1;                       // :146-147 dummy literal
+	__syncwarp();
+	int n_ll = 286;
+	{
+		u32 nz = 0;                                                        // highest used lit/len symbol
+		for (int i = lane; i < 286; i += 32) if (s->hist[i]) nz = i + 1;
+		for (int o = 16; o > 0; o >>= 1) nz = max(nz, __shfl_xor_sync(FULL_MASK, nz, o));
+		n_ll = max(257, (int)nz);                                          // :148-151
+	}
+	int n_d;
+	bool no_dist;
+	{
+		u32 used = __ballot_sync(FULL_MASK, lane < 30 && s->hist[288 + lane] > 0);
+		if (__popc(used) == 1) {                                           // :161-171 give a lone distance code a neighbour
+			int i = __ffs(used) - 1;
+			if (lane == 0) s->hist[288 + (i < 29 ? i + 1 : i - 1)] = 1;
+			used |= 1u << (i < 29 ? i + 1 : i - 1);
+		}
+		__syncwarp();
+		n_d = used ? 32 - __clz(used) : 1;                                 // :172-175
+		no_dist = used == 0;                                               // :177-179
+	}
+
+	package_merge<512>(s, s->hist, n_ll, 15, s->lens, lane);                // :153
+	if (no_dist) { if (lane == 0) s->lens[n_ll] = 0; }
+	else package_merge<32>(s, s->hist + 288, n_d, 15, s->lens + n_ll, lane);   // :181
+	__syncwarp();
+	const int total = n_ll + n_d;
+
+	// code-length RLE (Lz77Huffman.java:189-223), greedy and sequential by definition
+	int ncl = 0;
+	if (lane < 19) s->cl_hist[lane] = 0;
+	__syncwarp();
+	if (lane == 0) {
+		const u8 *lens = s->lens;
+		for (int i = 0; i < total;) {
+			int val = lens[i];
+			if (val == 0) {
+				int rl = 1;
+				for (; rl < 138 && i + rl < total && lens[i + rl] == 0; rl++);
+				if (rl < 3) { s->cl_sym[ncl] = 0; s->cl_ext[ncl] = 0; i++; }
+				else if (rl < 11) { s->cl_sym[ncl] = 17; s->cl_ext[ncl] = (u8)(rl - 3); i += rl; }
+				else { s->cl_sym[ncl] = 18; s->cl_ext[ncl] = (u8)(rl - 11); i += rl; }
+				ncl++;
+				continue;
+			}
+			if (i > 0) {
+				int rl = 0;
+				for (; rl < 6 && i + rl < total && lens[i + rl] == lens[i - 1]; rl++);
+				if (rl >= 3) { s->cl_sym[ncl] = 16; s->cl_ext[ncl] = (u8)(rl - 3); ncl++; i += rl; continue; }
+			}
+			s->cl_sym[ncl] = (u8)val; s->cl_ext[ncl] = 0; ncl++; i++;
+		}
+		for (int k = 0; k < ncl; k++) s->cl_hist[s->cl_sym[k]]++;
+	}
+	ncl = __shfl_sync(FULL_MASK, ncl, 0);
+	__syncwarp();
+	package_merge<32>(s, s->cl_hist, 19, 7, s->cl_len, lane);               // :228
+	assign_codes(s, s->cl_len, 19, s->cl_code, lane);                       // :243
+
+	// header bits (Lz77Huffman.java:230-258) and the dynamic block cost
+	for (int i = lane; i < HDR_WORDS; i += 32) s->hdr[i] = 0;
+	__syncwarp();
+	u32 hdr_bits = 0;
+	if (lane == 0) {
+		int ncll = 19;
+		for (; ncll > 4 && s->cl_len[CL_ORDER_D[ncll - 1]] == 0; ncll--);
+		BitW bw{s->hdr, 0};
+		bw_put(bw, (u32)(n_ll - 257), 5);
+		bw_put(bw, (u32)(n_d - 1), 5);
+		bw_put(bw, (u32)(ncll - 4), 4);
+		for (int i = 0; i < ncll; i++) bw_put(bw, s->cl_len[CL_ORDER_D[i]], 3);
+		for (int k = 0; k < ncl; k++) {
+			int sym = s->cl_sym[k];
+			u32 pair = s->cl_code[sym];
+			bw_put(bw, pair >> 4, (int)(pair & 15));
+			if (sym >= 16) bw_put(bw, s->cl_ext[k], sym == 16 ? 2 : sym == 17 ? 3 : 7);
+		}
+		hdr_bits = bw.pos;
+	}
+	hdr_bits = __shfl_sync(FULL_MASK, hdr_bits, 0);
+	__syncwarp();
+	u32 dyn = 0;                                       // emitted symbols only: the fix-up counts are not written
+	for (int i = lane; i < n_ll; i += 32) dyn += rec->hist_ll[i] * s->lens[i];
+	if ((int)lane < n_d && !no_dist) dyn += rec->hist_d[lane] * s->lens[n_ll + lane];
+	dyn = warp_sum(dyn);
+
+	// canonical codes for the emitter (:260-264)
+	assign_codes(s, s->lens, n_ll, rec->code_ll, lane);
+	if (!no_dist) assign_codes(s, s->lens + n_ll, n_d, rec->code_d, lane);
+	for (int i = lane; i < HDR_WORDS; i += 32) rec->hdr[i] = s->hdr[i];
+	if (lane == 0) {
+		rec->hdr_bits = hdr_bits;
+		rec->cost_fixed = 3 + fixed + extra_bits;
+		rec->cost_dyn = 3 + hdr_bits + dyn + extra_bits;
+	}
+}
+
+// ---------------------------------------------------------------- K3b: per-chunk layout, K3c: scan
+// Per block the cheapest of stored / fixed / dynamic for the block's actual start bit position, first listed
+// wins ties (MultiStrategy.java:35-44,54); stored cost per Uncompressed.java:23-25.
+__global__ void layout_kernel(BlockRec *__restrict__ recs, u32 n_blocks, u32 n_chunks, u64 n, u32 chunk_bytes,
+                              u32 block_bytes, int mode, int is_last, int ref_framing, u64 *__restrict__ chunk_len,
+                              u64 *__restrict__ chunk_tail) {
+	u32 c = blockIdx.x * blockDim.x + threadIdx.x;
+	if (c >= n_chunks) return;
+	const u32 bpc = chunk_bytes / block_bytes;
+	const u32 g0 = c * bpc;
+	const u32 g1 = min(n_blocks, g0 + bpc);
+	u64 bit = 0;
+	for (u32 g = g0; g < g1; g++) {
+		BlockRec *r = &recs[g];
+		const u64 bs = (u64)g * block_bytes;
+		const u64 dl = min(n, bs + block_bytes) - min(n, bs);
+		const int i = (int)(bit & 7);
+		const u64 nsb = max((u64)1, (dl + 65534) / 65535);
+		const u64 stored_cost = (u64)((long long)(dl * 8 + nsb * 40) + (((13 - i) % 8) - 5));
+		u64 best;
+		u32 m;
+		if (mode == B2D_MODE_STORED) { m = 1; best = stored_cost; }
+		else if (mode == B2D_MODE_FIXED) { m = 2; best = r->cost_fixed; }
+		else if (mode == B2D_MODE_DYNAMIC) { m = 3; best = r->cost_dyn; }
+		else {
+			m = 1; best = stored_cost;
+			if (r->cost_fixed < best) { m = 2; best = r->cost_fixed; }
+			if (r->cost_dyn < best) { m = 3; best = r->cost_dyn; }
+		}
+		r->mode = m;
+		r->out_bit = bit;
+		r->bfinal = (ref_framing && is_last && g + 1 == n_blocks) ? 1u : 0u;
+		bit += best;
+	}
+	chunk_tail[c] = bit;
+	if (!ref_framing) {
+		// empty stored block closes the chunk byte-aligned: 3 header bits, pad, 00 00 FF FF
+		bit += 3;
+		bit = (bit + 7) & ~(u64)7;
+		bit += 32;
+	} else {
+		bit = (bit + 7) & ~(u64)7;                   // BitOut.finish pads with zeros (DeflaterOutputStream.java:164-169)
+	}
+	chunk_len[c] = bit >> 3;
+}
+
+__global__ void __launch_bounds__(1024)
+scan_kernel(const u64 *__restrict__ chunk_len, u32 n_chunks, u64 *__restrict__ chunk_off, u64 *__restrict__ total_out,
+            u64 *__restrict__ user_chunk_len) {
+	__shared__ u64 warp_tot[32];
+	__shared__ u64 carry_sh;
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	if (threadIdx.x == 0) carry_sh = 0;
+	__syncthreads();
+	for (u32 base = 0; base < n_chunks; base += 1024) {
+		u32 i = base + threadIdx.x;
+		u64 v = i < n_chunks ? chunk_len[i] : 0;
+		if (user_chunk_len && i < n_chunks) user_chunk_len[i] = v;
+		u64 x = v;
+		for (int o = 1; o < 32; o <<= 1) { u64 y = __shfl_up_sync(FULL_MASK, x, o); if ((int)lane >= o) x += y; }
+		if (lane == 31) warp_tot[warp] = x;
+		__syncthreads();
+		u64 wsum = 0;
+		for (u32 w = 0; w < warp; w++) wsum += warp_tot[w];
+		u64 carry = carry_sh;
+		if (i < n_chunks) chunk_off[i] = carry + wsum + x - v;
+		__syncthreads();
+		if (threadIdx.x == 1023) carry_sh = carry + wsum + x;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { chunk_off[n_chunks] = carry_sh; *total_out = carry_sh; }
+}
+
+// ---------------------------------------------------------------- K4: bit emission
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_STAGE_WORDS = EMIT_THREADS * 48 / 32 + 4;
+
+__device__ __forceinline__ void or_bits_global(u32 *out_words, u64 bitpos, u64 v, int nbits) {
+	if (nbits == 0) return;
+	u64 wi = bitpos >> 5;
+	u32 sh = (u32)(bitpos & 31);
+	atomicOr(out_words + wi, (u32)(v << sh));
+	if (sh + nbits > 32) {
+		atomicOr(out_words + wi + 1, (u32)(v >> (32 - sh)));
+		if (sh + nbits > 64) atomicOr(out_words + wi + 2, (u32)(v >> (64 - sh)));
+	}
+}
+__device__ __forceinline__ void or_bits_shared(u32 *w, u32 bitpos, u64 v, int nbits) {
+	if (nbits == 0) return;
+	u32 wi = bitpos >> 5, sh = bitpos & 31;
+	atomicOr(w + wi, (u32)(v << sh));
+	if (sh + nbits > 32) {
+		atomicOr(w + wi + 1, (u32)(v >> (32 - sh)));
+		if (sh + nbits > 64) atomicOr(w + wi + 2, (u32)(v >> (64 - sh)));
+	}
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, u32 n_blocks, u32 n_chunks,
+            const BlockRec *__restrict__ recs, const u32 *__restrict__ tokens, const u64 *__restrict__ chunk_off,
+            const u64 *__restrict__ chunk_tail, int is_last, int ref_framing, u8 *out) {
+	__shared__ u32 code_ll[288];
+	__shared__ u32 code_d[32];
+	__shared__ u32 stage[EMIT_STAGE_WORDS];
+	__shared__ u32 warp_tot[EMIT_THREADS / 32];
+	const u32 g = blockIdx.x;
+	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+	const BlockRec *r = &recs[g];
+	const u32 c = g / (chunk_bytes / block_bytes);
+	const u64 bs = (u64)g * block_bytes;
+	const u64 dl = min(n, bs + block_bytes) - bs;
+	u32 *outw = (u32 *)out;
+	u64 bit = chunk_off[c] * 8 + r->out_bit;
+	const u32 mode = r->mode;
+
+	// the last block of a chunk also writes the chunk trailer: empty stored block, BFINAL only at the stream end
+	const bool chunk_tail_blk = (g + 1 == n_blocks) || ((g + 1) % (chunk_bytes / block_bytes) == 0);
+	if (chunk_tail_blk && !ref_framing && tid == 0) {
+		const u64 tb = chunk_off[c] * 8 + chunk_tail[c];
+		const bool fin = is_last && c + 1 == n_chunks;
+		if (fin) or_bits_global(outw, tb, 1u, 1);                          // BFINAL; BTYPE = 00 is already zero
+		or_bits_global(outw, ((tb + 3 + 7) & ~(u64)7) + 16, 0xFFFFu, 16);   // LEN = 0000, NLEN = FFFF
+	}
+
+	if (mode == 1) {                                   // stored (Uncompressed.java:35-45)
+		u64 pos = bs, end = bs + dl;
+		do {
+			u64 nb = min((u64)65535, end - pos);
+			bool fin = r->bfinal && nb == end - pos;
+			if (tid == 0) or_bits_global(outw, bit, fin ? 1u : 0u, 3);
+			bit = (bit + 3 + 7) & ~(u64)7;
+			if (tid == 0) or_bits_global(outw, bit, (u32)nb | ((u32)nb ^ 0xFFFFu) << 16, 32);
+			bit += 32;
+			// payload: whole 32-bit words with plain stores; the (up to 3) bytes before the first and after the last
+			// whole word share their word with neighbouring blocks' bits, so they are OR-ed in atomically
+			const u64 B = bit >> 3;
+			const u8 *src = in + pos;
+			const u32 head = (u32)min((u64)((4 - (B & 3)) & 3), nb);
+			const u64 nw = (nb - head) >> 2;
+			const u32 tail = (u32)(nb - head - (nw << 2));
+			if (tid < head) atomicOr(outw + (B >> 2), (u32)src[tid] << (((B & 3) + tid) * 8));
+			u32 *dw = outw + ((B + head) >> 2);
+			const u8 *s4 = src + head;
+			if ((((uintptr_t)s4) & 3) == 0) {
+				const u32 *sw = (const u32 *)s4;
+				for (u64 k = tid; k < nw; k += EMIT_THREADS) dw[k] = __ldg(sw + k);
+			} else {
+				const u32 *sw = (const u32 *)((uintptr_t)s4 & ~(uintptr_t)3);
+				const u32 sh = (u32)((uintptr_t)s4 & 3) * 8;
+				for (u64 k = tid; k < nw; k += EMIT_THREADS) dw[k] = __funnelshift_r(__ldg(sw + k), __ldg(sw + k + 1), sh);
+			}
+			if (tid < tail) atomicOr(dw + nw, (u32)s4[(nw << 2) + tid] << (tid * 8));
+			bit += nb * 8;
+			pos += nb;
+		} while (pos < end);
+		return;
+	}
+
+	for (int i = tid; i < 288; i += EMIT_THREADS) code_ll[i] = mode == 3 ? r->code_ll[i]
+		: ((__brev((u32)(i < 144 ? 0x30 + i : i < 256 ? 0x190 + i - 144 : i < 280 ? i - 256 : 0xC0 + i - 280)) >> (32 - fixed_ll_len(i))) << 4 | (u32)fixed_ll_len(i));
+	if (tid < 32) code_d[tid] = mode == 3 ? r->code_d[tid] : ((__brev(tid) >> 27) << 4 | 5u);
+	for (int i = tid; i < EMIT_STAGE_WORDS; i += EMIT_THREADS) stage[i] = 0;
+	if (tid == 0) or_bits_global(outw, bit, (r->bfinal ? 1u : 0u) | (mode == 3 ? 2u : 1u) << 1, 3);
+	bit += 3;
+	if (mode == 3) {                                   // dynamic header
+		const u32 hb = r->hdr_bits;
+		for (u32 w = tid; w * 32 < hb; w += EMIT_THREADS) {
+			int nb = (int)min(32u, hb - w * 32);
+			or_bits_global(outw, bit + (u64)w * 32, r->hdr[w], nb);
+		}
+		bit += hb;
+	}
+	__syncthreads();
+
+	const u32 ntok = r->n_tokens + 1;                  // + end-of-block
+	const u32 *tk = tokens + bs;
+	for (u32 base = 0; base < ntok; base += EMIT_THREADS) {
+		const u32 t = base + tid;
+		u64 bits = 0;
+		int nb = 0;
+		if (t < ntok) {
+			if (t + 1 == ntok) { u32 p = code_ll[256]; bits = p >> 4; nb = p & 15; }
+			else {
+				u32 e = tk[t];
+				int len = (int)tok_len(e);
+				if (len == 0) { u32 p = code_ll[e >> 24]; bits = p >> 4; nb = p & 15; }
+				else {
+					int ne, ex;
+					int sym = len_symbol(len, ne, ex);
+					u32 p = code_ll[sym];
+					bits = p >> 4; nb = p & 15;
+					bits |= (u64)ex << nb; nb += ne;
+					int dsym = dist_symbol((int)tok_dist(e), ne, ex);
+					u32 q = code_d[dsym];
+					bits |= (u64)(q >> 4) << nb; nb += q & 15;
+					bits |= (u64)ex << nb; nb += ne;
+				}
+			}
+		}
+		// exclusive prefix sum of nb over the CTA
+		u32 x = (u32)nb;
+		for (int o = 1; o < 32; o <<= 1) { u32 y = __shfl_up_sync(FULL_MASK, x, o); if ((int)lane >= o) x += y; }
+		if (lane == 31) warp_tot[warp] = x;
+		__syncthreads();
+		u32 woff = 0, tile_bits = 0;
+		for (int w = 0; w < EMIT_THREADS / 32; w++) { u32 v = warp_tot[w]; if (w < (int)warp) woff += v; tile_bits += v; }
+		const u32 sh0 = (u32)(bit & 31);
+		or_bits_shared(stage, sh0 + woff + x - (u32)nb, bits, nb);
+		__syncthreads();
+		const u32 nwords = (sh0 + tile_bits + 31) >> 5;
+		u32 *dstw = outw + (bit >> 5);
+		for (u32 w = tid; w < nwords; w += EMIT_THREADS) {
+			u32 v = stage[w];
+			stage[w] = 0;
+			if (w == 0 || w + 1 == nwords) { if (v) atomicOr(dstw + w, v); }    // words shared with neighbours
+			else dstw[w] = v;
+		}
+		bit += tile_bits;
+		__syncthreads();
+	}
+}
+
+// ---------------------------------------------------------------- host side
+// Worst case over all modes: a block never costs more than 9 bits per byte (the fixed code is always available to
+// the optimiser; a flat 9-bit code bounds the length-limited dynamic code) plus 3 header bits and < 384 bytes of
+// dynamic header; stored pieces add 5 bytes per 65535; every chunk adds its 5-byte marker plus padding.
+uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t block_bytes) {
+	(void)block_bytes;                                    // sized for the smallest accepted block (4 KiB)
+	uint64_t n_blocks = in_len / 4096 + 1;
+	uint64_t n_chunks = (in_len + chunk_bytes - 1) / chunk_bytes + 1;
+	return in_len + in_len / 8 + n_blocks * 384 + n_chunks * 16 + 1024;
+}
+size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p) {
+	u64 n_blocks = (in_len + p.block_bytes - 1) / p.block_bytes;
+	u64 n_chunks = (in_len + p.chunk_bytes - 1) / p.chunk_bytes;
+	size_t s = 0;
+	s += ((in_len * 2 + 255) & ~(u64)255) + 256;          // prevdist u16
+	s += ((in_len * 4 + 255) & ~(u64)255) + 256;          // match u32
+	s += ((in_len * 4 + 255) & ~(u64)255) + 256;          // tokens u32
+	s += ((n_blocks * sizeof(BlockRec) + 255) & ~(u64)255) + 256;
+	s += ((n_chunks + 2) * 8 + 255) & ~(u64)255;          // chunk_len
+	s += ((n_chunks + 2) * 8 + 255) & ~(u64)255;          // chunk_off
+	s += ((n_chunks + 2) * 8 + 255) & ~(u64)255;          // chunk_tail
+	return s + sizeof(BlockRec) + 2048;
+}
+
+static bool g_attr_set = false;
+
+cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams &p, uint8_t *d_out,
+                           uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+	cudaError_t e;
+	if (!g_attr_set) {
+		e = cudaFuncSetAttribute(chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << HASH_BITS);
+		if (e != cudaSuccess) return e;
+		e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM);
+		if (e != cudaSuccess) return e;
+		g_attr_set = true;
+	}
+	const int ref_framing = p.framing == 1;
+	const int is_last = p.is_last;
+	u32 n_blocks = (u32)((n + p.block_bytes - 1) / p.block_bytes);
+	u32 n_chunks = (u32)((n + p.chunk_bytes - 1) / p.chunk_bytes);
+	if (ref_framing && n == 0) { n_blocks = 1; n_chunks = 1; }   // the reference writes one (empty) final block
+	// carve scratch
+	u8 *sp = (u8 *)d_scratch;
+	auto carve = [&](size_t bytes) { u8 *r = sp; sp += (bytes + 255) & ~(size_t)255; return r; };
+	u16 *prevdist = (u16 *)carve(n * 2 + 256);
+	u32 *match = (u32 *)carve(n * 4 + 256);
+	u32 *tokens = (u32 *)carve(n * 4 + 256);
+	BlockRec *recs = (BlockRec *)carve((size_t)n_blocks * sizeof(BlockRec) + 256);
+	u64 *chunk_len = (u64 *)carve((size_t)(n_chunks + 2) * 8);
+	u64 *chunk_off = (u64 *)carve((size_t)(n_chunks + 2) * 8);
+	u64 *chunk_tail = (u64 *)carve((size_t)(n_chunks + 2) * 8);
+	if ((size_t)(sp - (u8 *)d_scratch) > scratch_bytes) return cudaErrorInvalidValue;
+
+	e = cudaMemsetAsync(d_out, 0, out_cap, st);
+	if (e != cudaSuccess) return e;
+	if (n_blocks == 0) {
+		// empty input: only the closing empty stored block (if this call ends the stream)
+		static const u8 fin[5] = {0x01, 0x00, 0x00, 0xFF, 0xFF};
+		u64 len = is_last ? 5 : 0;
+		if (is_last) { e = cudaMemcpyAsync(d_out, fin, 5, cudaMemcpyHostToDevice, st); if (e != cudaSuccess) return e; }
+		return cudaMemcpyAsync(d_out_len_total, &len, 8, cudaMemcpyHostToDevice, st);
+	}
+	const bool need_search = p.mode != B2D_MODE_STORED;
+	MatchParams mp;
+	mp.search = p.search;
+	mp.hb = p.search == 3 ? 3 : 4;
+	mp.depth = p.search == 3 ? 0x7FFFFFFF : p.depth;
+	mp.nice = MAX_MATCH;
+	if (need_search) {
+		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3))
+			chains_kernel<<<n_blocks, 32, 2 << HASH_BITS, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, mp.hb, prevdist);
+		const u32 n_tiles = (u32)((n + TILE - 1) / TILE);
+		if (n_tiles) match_kernel<<<n_tiles, MATCH_THREADS, MATCH_SMEM, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, mp, prevdist, match);
+		parse_kernel<<<(n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st>>>(
+			match, n, p.block_bytes, n_blocks, p.lazy, tokens, recs);
+		huffman_kernel<<<(n_blocks + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_blocks, n, p.block_bytes);
+	}
+	layout_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(recs, n_blocks, n_chunks, n, p.chunk_bytes, p.block_bytes,
+	                                                     p.mode, is_last, ref_framing, chunk_len, chunk_tail);
+	scan_kernel<<<1, 1024, 0, st>>>(chunk_len, n_chunks, chunk_off, d_out_len_total, d_chunk_out_len);
+	emit_kernel<<<n_blocks, EMIT_THREADS, 0, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, n_blocks, n_chunks, recs,
+	                                               tokens, chunk_off, chunk_tail, is_last, ref_framing, d_out);
+	return cudaGetLastError();
+}
+
+}  // namespace b2d

@@ -1,0 +1,39 @@
+// kernels.h -- internal launch interface between the C-ABI host runtime (api.cu) and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/b2deflate.h"
+
+namespace b2d {
+
+// inflate.cu
+cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
+                           const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
+                           int *d_status, uint32_t flags, cudaStream_t st);
+
+// crc32.cu
+// CRC-32 of n_seg independent segments: segment i = data[off[i], off[i] + len[i])  (len from d_len, u64)
+cudaError_t launch_crc32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
+                                  uint32_t n_seg, uint32_t *d_crc, cudaStream_t st);
+// CRC-32 of fixed-size pieces of one buffer: piece i = data[i*piece, min((i+1)*piece, total))
+cudaError_t launch_crc32_pieces(const uint8_t *d_data, uint64_t total, uint64_t piece, uint32_t n_pieces,
+                                uint32_t *d_crc, cudaStream_t st);
+// folds n_pieces piece CRCs (pieces of `piece` bytes, the last one shorter: total bytes) into one CRC on the device
+cudaError_t launch_crc32_fold(const uint32_t *d_piece_crc, uint32_t n_pieces, uint64_t piece, uint64_t total,
+                              uint32_t *d_crc_out, cudaStream_t st);
+uint32_t host_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+uint32_t host_crc32_bytes(uint32_t crc, const uint8_t *p, size_t n);   // tiny inputs only (gzip headers)
+
+// deflate.cu
+struct DeflateParams {
+	uint32_t chunk_bytes, block_bytes;
+	int mode, search, depth, lazy, is_last;
+	int framing;      // 0 = chunks closed by empty stored blocks; 1 = reference framing (one chunk, BFINAL on the last block)
+};
+uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t block_bytes);
+size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p);
+cudaError_t launch_deflate(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out,
+                           uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+
+}  // namespace b2d

@@ -1,0 +1,177 @@
+/*
+ * b2deflate.h -- C ABI of libb2deflate.so, the B200 (sm_100a) DEFLATE codec.
+ *
+ * This is the drop-in boundary for the hot path of nayuki/DEFLATE-library-Java (paths below are
+ * relative to the reference's src/io/nayuki/deflate/).  Each entry point names the reference
+ * interface it replaces; INTEGRATION.md shows the Panama FFM (java.lang.foreign) binding a
+ * maintainer of the reference would add.  Plain pointers and sizes only -- no CUDA or torch types.
+ *
+ * Conventions
+ *   - One process drives one GPU (b2d_init(device)); calls are blocking and serialised by an
+ *     internal mutex, so they may arrive from any thread (the reference classes are not thread-safe
+ *     and spawn no threads; FFM downcalls may come from any JVM thread).
+ *   - Host entry points take HOST pointers and include the host<->device copies.  The *_dev entry
+ *     points take DEVICE pointers (e.g. torch tensor data_ptr()) and run on the given CUDA stream
+ *     (a cudaStream_t passed as void*, NULL = the library's own stream) without synchronising it.
+ *   - There is no CPU fallback: every call fails with B2D_ERR_NO_DEVICE if no sm_100 GPU is usable.
+ *   - Format errors are per-member status codes: 0 = OK, otherwise 1 + Reason.ordinal() of the
+ *     reference's DataFormatException.Reason (DataFormatException.java:61-83).  The Java wrapper
+ *     re-throws `new DataFormatException(Reason.values()[status - 1], b2d_strerror(status))`.
+ */
+#ifndef B2DEFLATE_H
+#define B2DEFLATE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- status codes ---- */
+enum {
+	B2D_OK = 0,
+	/* 1 + DataFormatException.Reason.ordinal()  (DataFormatException.java:61-83) */
+	B2D_UNEXPECTED_END_OF_STREAM = 1,
+	B2D_RESERVED_BLOCK_TYPE = 2,
+	B2D_UNCOMPRESSED_BLOCK_LENGTH_MISMATCH = 3,
+	B2D_HUFFMAN_CODE_UNDER_FULL = 4,
+	B2D_HUFFMAN_CODE_OVER_FULL = 5,
+	B2D_NO_PREVIOUS_CODE_LENGTH_TO_COPY = 6,
+	B2D_CODE_LENGTH_CODE_OVER_FULL = 7,
+	B2D_END_OF_BLOCK_CODE_ZERO_LENGTH = 8,
+	B2D_RESERVED_LENGTH_SYMBOL = 9,
+	B2D_RESERVED_DISTANCE_SYMBOL = 10,
+	B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE = 11,
+	B2D_COPY_FROM_BEFORE_DICTIONARY_START = 12,
+	B2D_HEADER_CHECKSUM_MISMATCH = 13,
+	B2D_UNSUPPORTED_COMPRESSION_METHOD = 14,
+	B2D_DECOMPRESSED_CHECKSUM_MISMATCH = 15,
+	B2D_DECOMPRESSED_SIZE_MISMATCH = 16,
+	B2D_GZIP_INVALID_MAGIC_NUMBER = 17,
+	B2D_GZIP_RESERVED_FLAGS_SET = 18,
+	B2D_GZIP_UNSUPPORTED_OPERATING_SYSTEM = 19,
+	/* not reference Reasons (the reference's streams are unbounded / have no device) */
+	B2D_ERR_OUTPUT_OVERFLOW = -1,   /* a member needs more output than its out_off[] slot holds */
+	B2D_ERR_BAD_ARGUMENT = -2,      /* maps to IllegalArgumentException / NullPointerException */
+	B2D_ERR_NO_DEVICE = -3,         /* no usable sm_100 GPU / b2d_init not called */
+	B2D_ERR_CUDA = -4,              /* CUDA runtime failure; see b2d_last_error() */
+	B2D_ERR_OUT_OF_MEMORY = -5
+};
+
+/* ---- lifetime ---- */
+
+/* Binds the process to GPU `device` (CUDA ordinal), creates the stream and scratch pools.
+ * Idempotent for the same device.  Reference objects "only use memory and no OS resources"
+ * (InflaterInputStream.java:22-23), so nothing below requires per-stream teardown. */
+int b2d_init(int device);
+void b2d_shutdown(void);
+const char *b2d_strerror(int status);        /* message strings of Open.java / GzipInputStream.java */
+const char *b2d_last_error(void);            /* last CUDA error text for B2D_ERR_CUDA */
+int b2d_device_sm_count(void);
+
+/* Pinned staging memory the Java side wraps as a MemorySegment (ownership: caller frees). */
+void *b2d_alloc_pinned(size_t bytes);
+void b2d_free_pinned(void *p);
+
+/* ---- decompression: replaces decomp/Open.java (Open.read :83-110) behind
+ *      InflaterInputStream.read (InflaterInputStream.java:147-164) ---- */
+
+#define B2D_INFLATE_CRC32        1u   /* also compute CRC-32 of every member's output (GzipInputStream.java:72) */
+#define B2D_INFLATE_CHUNK_INDEXED 2u  /* unit = chunk of a b2d_deflate_chunks stream: ends at BFINAL *or* exactly
+                                         at the end of its byte range on a block boundary */
+
+/* Decodes n independent raw-DEFLATE members.  Member i occupies in[in_off[i], in_off[i+1]) and is
+ * written to out[out_off[i], out_off[i+1]) (the slot size is its capacity).
+ *   out_len[i]     bytes produced (on failure: bytes produced before the failing symbol)
+ *   in_consumed[i] ceil(bits consumed / 8): the end-exactly position of Open.finish (Open.java:113-124)
+ *   crc32[i]       CRC-32 of the member's output if B2D_INFLATE_CRC32 (may be NULL otherwise)
+ *   status[i]      0 or 1 + Reason.ordinal(); a bad member does not disturb the others
+ * Returns B2D_OK if the batch ran (inspect status[]), or a negative B2D_ERR_*. */
+int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n,
+                      uint8_t *out, const uint64_t *out_off,
+                      uint64_t *out_len, uint64_t *in_consumed, uint32_t *crc32, int32_t *status,
+                      uint32_t flags);
+
+/* Same with device pointers.  `in` must be readable up to the next 4-byte boundary past in_off[n]. */
+int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n,
+                          uint8_t *d_out, const uint64_t *d_out_off,
+                          uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc32, int32_t *d_status,
+                          uint32_t flags, void *stream);
+
+/* ---- compression: replaces comp/Lz77Huffman.java (decide/compressTo :42-288), comp/Uncompressed.java,
+ *      comp/MultiStrategy.java behind DeflaterOutputStream.writeBuffer (DeflaterOutputStream.java:119-137) ---- */
+
+enum {
+	B2D_MODE_AUTO = 0,      /* per block the cheapest of stored / fixed / dynamic (MultiStrategy.java:35-44 rule) */
+	B2D_MODE_STORED = 1,    /* comp/Uncompressed.java */
+	B2D_MODE_FIXED = 2,     /* Lz77Huffman *_STATIC  (Lz77Huffman.java:298,301,304) */
+	B2D_MODE_DYNAMIC = 3    /* Lz77Huffman *_DYNAMIC (Lz77Huffman.java:299,302,305) */
+};
+
+/* Match search of the Lz77Huffman record (Lz77Huffman.java:20-25): which back-references are tried. */
+enum {
+	B2D_SEARCH_DEFAULT = 0, /* hash chains, depth-limited, lazy parse (ratio >= FULL_DYNAMIC on text/mixed data) */
+	B2D_SEARCH_LITERAL = 1, /* no matches            = LITERAL_*  (0,0,0,0) */
+	B2D_SEARCH_RLE = 2,     /* distance 1 only, greedy = RLE_*    (3,258,1,1), the DeflaterOutputStream default */
+	B2D_SEARCH_FULL = 3     /* exhaustive chains, 3-byte minimum, greedy = FULL_* (3,258,1,32768): finds exactly
+	                           the matches of the brute-force scan Lz77Huffman.java:71-84 (slow; parity/ratio bar) */
+};
+
+/* Stream framing. */
+enum {
+	B2D_FRAMING_CHUNKED = 0,   /* independent chunks, each closed by an empty stored block (sync-flush marker) */
+	B2D_FRAMING_REFERENCE = 1  /* exactly what DeflaterOutputStream emits (DeflaterOutputStream.java:119-137): history
+	                              carried across blocks, no markers, BFINAL on the last (possibly empty) block when
+	                              is_last, zero padding to a byte.  chunk_bytes is ignored; the input is ONE unit, so
+	                              only block-level parallelism remains.  With search RLE/FULL/LITERAL and lazy = 0 the
+	                              output is byte-identical to the reference strategy of the same name. */
+};
+
+typedef struct b2d_deflate_opts {
+	uint32_t chunk_bytes;   /* independent unit, history reset at its start; 0 = 1 MiB */
+	uint32_t block_bytes;   /* one DEFLATE block per this many input bytes (dataLookaheadLimit,
+	                           DeflaterOutputStream.java:50-52); 0 = 64 KiB; must divide chunk_bytes */
+	int32_t mode;           /* B2D_MODE_* */
+	int32_t search;         /* B2D_SEARCH_* */
+	int32_t chain_depth;    /* candidates examined per position; 0 = default (8) */
+	int32_t lazy;           /* -1 = default (on), 0 = greedy, 1 = lazy */
+	int32_t is_last;        /* 1: the stream ends after this call (final block emitted) */
+	int32_t framing;        /* B2D_FRAMING_* */
+} b2d_deflate_opts;
+
+/* Worst-case output size of b2d_deflate_chunks for in_len bytes (any mode, any framing). */
+uint64_t b2d_deflate_bound(uint64_t in_len, uint32_t chunk_bytes);
+
+/* Compresses in[0,in_len) as ceil(in_len / chunk_bytes) independent chunks.  The output is raw DEFLATE,
+ * byte-aligned: every chunk ends with an empty stored block (bits 0|00, zero pad, 00 00 FF FF -- the
+ * Z_SYNC_FLUSH marker), whose BFINAL bit is set only on the last chunk when opts->is_last.  The
+ * concatenation of all calls' outputs is ONE valid DEFLATE stream for the reference's sequential
+ * decoder (Open.java:83-110, stored path :232-241) and for zlib.
+ *   crc32_inout    running CRC-32 of the uncompressed data (GzipOutputStream.java:57), updated; may be NULL
+ *   chunk_out_len  per-chunk compressed byte counts (the chunk index), ceil(in_len/chunk_bytes) entries; may be NULL
+ * Returns bytes written, or a negative B2D_ERR_*. */
+int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d_deflate_opts *opts,
+                           uint8_t *out, uint64_t out_cap, uint32_t *crc32_inout, uint64_t *chunk_out_len);
+
+/* Same with device pointers (d_in 16-byte aligned, d_out 4-byte aligned; d_out need not be cleared, the call
+ * clears it).  *d_out_len_total (device, 8 bytes) receives the byte count; d_chunk_out_len / d_chunk_crc32
+ * receive the per-chunk compressed sizes and per-chunk CRC-32s of the input (either may be NULL). */
+int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b2d_deflate_opts *opts,
+                           uint8_t *d_out, uint64_t out_cap, uint64_t *d_out_len_total,
+                           uint64_t *d_chunk_out_len, uint32_t *d_chunk_crc32, void *stream);
+
+/* ---- CRC-32: replaces java.util.zip.CRC32 at GzipOutputStream.java:25,57 / GzipInputStream.java:32,72 ---- */
+uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len);            /* host pointer, computed on the GPU */
+int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_out, void *stream);   /* crc of d_data[0,len), init 0 */
+uint32_t b2d_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);     /* crc(A||B) from crc(A), crc(B), |B| */
+
+/* ---- synthetic corpora (host; SURVEY.md Appendix D -- the reference ships no data) ---- */
+void b2d_corpus_random(uint64_t seed, uint8_t *out, size_t n);
+void b2d_corpus_text(uint64_t seed, uint8_t *out, size_t n);
+void b2d_corpus_mixed(uint64_t seed, uint8_t *out, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
