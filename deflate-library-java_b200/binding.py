@@ -1,0 +1,213 @@
+"""ctypes binding of libb2deflate.so (include/b2deflate.h) -- the harness-side twin of the Panama FFM binding
+shown in INTEGRATION.md.  Every function here is a thin call through the C ABI; there is no CPU codec in this
+package: if the library or a B200 is missing, calls raise (they never fall back).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libb2deflate.so")
+
+# 1 + DataFormatException.Reason.ordinal() (DataFormatException.java:61-83)
+REASONS = [
+    "UNEXPECTED_END_OF_STREAM", "RESERVED_BLOCK_TYPE", "UNCOMPRESSED_BLOCK_LENGTH_MISMATCH",
+    "HUFFMAN_CODE_UNDER_FULL", "HUFFMAN_CODE_OVER_FULL", "NO_PREVIOUS_CODE_LENGTH_TO_COPY",
+    "CODE_LENGTH_CODE_OVER_FULL", "END_OF_BLOCK_CODE_ZERO_LENGTH", "RESERVED_LENGTH_SYMBOL",
+    "RESERVED_DISTANCE_SYMBOL", "LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE",
+    "COPY_FROM_BEFORE_DICTIONARY_START", "HEADER_CHECKSUM_MISMATCH", "UNSUPPORTED_COMPRESSION_METHOD",
+    "DECOMPRESSED_CHECKSUM_MISMATCH", "DECOMPRESSED_SIZE_MISMATCH", "GZIP_INVALID_MAGIC_NUMBER",
+    "GZIP_RESERVED_FLAGS_SET", "GZIP_UNSUPPORTED_OPERATING_SYSTEM",
+]
+ERR_OUTPUT_OVERFLOW, ERR_BAD_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
+INFLATE_CRC32, INFLATE_CHUNK_INDEXED = 1, 2
+MODE_AUTO, MODE_STORED, MODE_FIXED, MODE_DYNAMIC = 0, 1, 2, 3
+SEARCH_DEFAULT, SEARCH_LITERAL, SEARCH_RLE, SEARCH_FULL = 0, 1, 2, 3
+FRAMING_CHUNKED, FRAMING_REFERENCE = 0, 1
+
+EXPORTS = [
+    "b2d_init", "b2d_shutdown", "b2d_strerror", "b2d_last_error", "b2d_device_sm_count", "b2d_alloc_pinned",
+    "b2d_free_pinned", "b2d_inflate_batch", "b2d_inflate_batch_dev", "b2d_deflate_bound", "b2d_deflate_chunks",
+    "b2d_deflate_chunks_dev", "b2d_crc32", "b2d_crc32_dev", "b2d_crc32_combine", "b2d_corpus_random",
+    "b2d_corpus_text", "b2d_corpus_mixed",
+]
+
+
+def status_name(st):
+    if st == 0:
+        return "OK"
+    if 1 <= st <= len(REASONS):
+        return REASONS[st - 1]
+    return {-1: "ERR_OUTPUT_OVERFLOW", -2: "ERR_BAD_ARGUMENT", -3: "ERR_NO_DEVICE", -4: "ERR_CUDA",
+            -5: "ERR_OUT_OF_MEMORY"}.get(st, f"UNKNOWN({st})")
+
+
+class B2dError(RuntimeError):
+    def __init__(self, code, what=""):
+        self.code = code
+        super().__init__(f"{what}: {status_name(code)} ({code})")
+
+
+class DeflateOpts(ctypes.Structure):
+    _fields_ = [("chunk_bytes", ctypes.c_uint32), ("block_bytes", ctypes.c_uint32), ("mode", ctypes.c_int32),
+                ("search", ctypes.c_int32), ("chain_depth", ctypes.c_int32), ("lazy", ctypes.c_int32),
+                ("is_last", ctypes.c_int32), ("framing", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def lib():
+    """Loads libb2deflate.so.  Raises if it has not been built (python deflate-library-java_b200/build.py)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise ImportError(f"{SO_PATH} is missing: build it with `python deflate-library-java_b200/build.py` "
+                          "(there is no CPU fallback)")
+    L = ctypes.CDLL(SO_PATH)
+    vp, u32, u64, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int
+    L.b2d_init.restype = i32
+    L.b2d_init.argtypes = [i32]
+    L.b2d_shutdown.restype = None
+    L.b2d_strerror.restype = ctypes.c_char_p
+    L.b2d_strerror.argtypes = [i32]
+    L.b2d_last_error.restype = ctypes.c_char_p
+    L.b2d_device_sm_count.restype = i32
+    L.b2d_alloc_pinned.restype = vp
+    L.b2d_alloc_pinned.argtypes = [ctypes.c_size_t]
+    L.b2d_free_pinned.restype = None
+    L.b2d_free_pinned.argtypes = [vp]
+    L.b2d_inflate_batch.restype = i32
+    L.b2d_inflate_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32]
+    L.b2d_inflate_batch_dev.restype = i32
+    L.b2d_inflate_batch_dev.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.b2d_deflate_bound.restype = u64
+    L.b2d_deflate_bound.argtypes = [u64, u32]
+    L.b2d_deflate_chunks.restype = ctypes.c_int64
+    L.b2d_deflate_chunks.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp]
+    L.b2d_deflate_chunks_dev.restype = i32
+    L.b2d_deflate_chunks_dev.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp, vp, vp]
+    L.b2d_crc32.restype = u32
+    L.b2d_crc32.argtypes = [u32, vp, u64]
+    L.b2d_crc32_dev.restype = i32
+    L.b2d_crc32_dev.argtypes = [vp, u64, vp, vp]
+    L.b2d_crc32_combine.restype = u32
+    L.b2d_crc32_combine.argtypes = [u32, u32, u64]
+    for name in ("b2d_corpus_random", "b2d_corpus_text", "b2d_corpus_mixed"):
+        f = getattr(L, name)
+        f.restype = None
+        f.argtypes = [u64, vp, ctypes.c_size_t]
+    _lib = L
+    return L
+
+
+def _check(code, what):
+    if code < 0:
+        detail = lib().b2d_last_error().decode() if code == ERR_CUDA else ""
+        raise B2dError(code, what + (f" [{detail}]" if detail else ""))
+    return code
+
+
+def init(device=0):
+    _check(lib().b2d_init(device), "b2d_init")
+
+
+def shutdown():
+    lib().b2d_shutdown()
+
+
+def strerror(st):
+    return lib().b2d_strerror(st).decode()
+
+
+def _u8(a):
+    a = np.frombuffer(a, dtype=np.uint8) if isinstance(a, (bytes, bytearray, memoryview)) else a
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def _ptr(a):
+    return a.ctypes.data if a is not None and a.size else (a.ctypes.data if a is not None else None)
+
+
+def make_opts(chunk_bytes=0, block_bytes=0, mode=MODE_AUTO, search=SEARCH_DEFAULT, chain_depth=0, lazy=-1, is_last=1,
+              framing=FRAMING_CHUNKED):
+    return DeflateOpts(chunk_bytes, block_bytes, mode, search, chain_depth, lazy, is_last, framing)
+
+
+# ---- corpora (host) ----
+def corpus(kind, seed, n):
+    out = np.empty(n, dtype=np.uint8)
+    getattr(lib(), "b2d_corpus_" + kind)(seed, out.ctypes.data, n)
+    return out
+
+
+# ---- host-pointer entry points ----
+def inflate_batch(members, out_caps, flags=0):
+    """members: list of bytes-like raw-DEFLATE members; out_caps: int or list of output capacities.
+    -> (outputs list[bytes], out_len, in_consumed, crc32, status) with numpy arrays for the last four."""
+    n = len(members)
+    if isinstance(out_caps, int):
+        out_caps = [out_caps] * n
+    in_off = np.zeros(n + 1, dtype=np.uint64)
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    for i, m in enumerate(members):
+        in_off[i + 1] = in_off[i] + np.uint64(len(m))
+        out_off[i + 1] = out_off[i] + np.uint64(out_caps[i])
+    blob = np.frombuffer(b"".join(bytes(m) for m in members), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    out, out_len, in_consumed, crc, status = inflate_batch_raw(blob, in_off, out_off, flags)
+    outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_len[i])]) for i in range(n)]
+    return outs, out_len, in_consumed, crc, status
+
+
+def inflate_batch_raw(blob, in_off, out_off, flags=0, out=None):
+    """Contiguous form: blob (u8), in_off/out_off (u64[n+1]).  -> (out u8, out_len, in_consumed, crc32, status)."""
+    blob = _u8(blob)
+    n = len(in_off) - 1
+    in_off = np.ascontiguousarray(in_off, dtype=np.uint64)
+    out_off = np.ascontiguousarray(out_off, dtype=np.uint64)
+    total = int(out_off[n]) if n >= 0 else 0
+    if out is None:
+        out = np.zeros(max(total, 1), dtype=np.uint8)
+    out_len = np.zeros(max(n, 1), dtype=np.uint64)
+    in_consumed = np.zeros(max(n, 1), dtype=np.uint64)
+    crc = np.zeros(max(n, 1), dtype=np.uint32)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    r = lib().b2d_inflate_batch(blob.ctypes.data if blob.size else None, in_off.ctypes.data, n, out.ctypes.data,
+                                out_off.ctypes.data, out_len.ctypes.data, in_consumed.ctypes.data,
+                                crc.ctypes.data, status.ctypes.data, flags)
+    _check(r, "b2d_inflate_batch")
+    return out, out_len[:n], in_consumed[:n], crc[:n], status[:n]
+
+
+def deflate_bound(n, chunk_bytes=0):
+    return int(lib().b2d_deflate_bound(n, chunk_bytes))
+
+
+def deflate_chunks(data, opts=None, crc=None, want_index=False):
+    """-> compressed bytes (np.uint8 array) [, crc32, chunk_out_len]."""
+    data = _u8(data)
+    opts = opts if opts is not None else make_opts()
+    cap = deflate_bound(data.size, opts.chunk_bytes)
+    out = np.empty(cap, dtype=np.uint8)
+    cb = opts.chunk_bytes or (1 << 20)
+    n_chunks = max(1, (data.size + cb - 1) // cb)
+    idx = np.zeros(n_chunks, dtype=np.uint64)
+    c = ctypes.c_uint32(crc if crc is not None else 0)
+    r = lib().b2d_deflate_chunks(data.ctypes.data if data.size else None, data.size, ctypes.byref(opts),
+                                 out.ctypes.data, cap, ctypes.byref(c), idx.ctypes.data)
+    _check(int(r), "b2d_deflate_chunks")
+    res = out[:int(r)]
+    if want_index or crc is not None:
+        return res, c.value, idx
+    return res
+
+
+def crc32(data, crc=0):
+    data = _u8(data)
+    return int(lib().b2d_crc32(crc, data.ctypes.data if data.size else None, data.size))
+
+
+def crc32_combine(a, b, len_b):
+    return int(lib().b2d_crc32_combine(a, b, len_b))

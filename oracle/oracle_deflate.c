@@ -181,6 +181,16 @@ static void chains_insert_upto(Chains *c, size_t upto) {   /* insert positions p
 	if (c->inserted < upto && c->inserted + 2 >= c->n) c->inserted = upto;
 }
 
+/* undo insertions back to `mark` (LIFO), so a pricing pass leaves the chains as it found them */
+static void chains_rollback(Chains *c, size_t mark) {
+	while (c->inserted > mark) {
+		size_t p = --c->inserted;
+		if (p + 2 >= c->n) continue;
+		uint32_t key = (uint32_t)c->data[p] | (uint32_t)c->data[p + 1] << 8 | (uint32_t)c->data[p + 2] << 16;
+		c->head[key] = c->prev[p];
+	}
+}
+
 /* One Lz77Huffman block (Lz77Huffman.java:55-286).  b = whole input, [start,end) = this block,
  * off = start - historyLen. */
 static void lz77_block(const Lz77Params *p, const uint8_t *b, size_t off, size_t start, size_t end,
@@ -423,7 +433,9 @@ size_t oracle_deflate(const uint8_t *in, size_t n, const int *strategies, int n_
 					BitOut cnt;
 					memset(&cnt, 0, sizeof cnt);
 					cnt.counting = 1;
+					size_t mark = chp ? chp->inserted : 0;
 					lz77_block(&PRESETS[strategies[k]], in, off, start, end, chp, search, &cnt, 0);
+					if (chp) chains_rollback(chp, mark);
 					cost = (int64_t)cnt.count;
 				}
 				if (cost < best) { best = cost; chosen = strategies[k]; }      /* strict '<': first listed wins ties */

@@ -1,0 +1,141 @@
+"""CPU: the oracle encoder.  The reference has no golden compressed bytes (DeflaterOutputStreamTest.java:24-115 only
+round-trips, default strategy), so these mirror its five round-trip tests with fixed seeds, extend them to every
+preset, and pin the survey's independent cross-check bytes."""
+import random
+import zlib
+
+import pytest
+
+from util import zlib_inflate_raw
+
+STRATS = list(range(7))
+
+
+def _roundtrip(oracle, data, strategies, **kw):
+    comp = oracle.deflate(data, strategies, **kw)
+    st, out, consumed = oracle.inflate(comp, out_cap=len(data) + 8)
+    assert st == 0 and out == bytes(data) and consumed == len(comp)
+    assert zlib_inflate_raw(comp)[0] == bytes(data)
+    return comp
+
+
+def test_empty(oracle):                                # DeflaterOutputStreamTest.java:24-29
+    for s in STRATS:
+        _roundtrip(oracle, b"", (s,))
+
+
+def test_short_random(oracle):                         # :32-44
+    rng = random.Random(32)
+    for _ in range(300):
+        _roundtrip(oracle, rng.randbytes(rng.randrange(100)), (oracle.RLE_DYNAMIC,))
+
+
+def test_byte_runs(oracle):                            # :67-86
+    rng = random.Random(67)
+    data = b"".join(bytes([rng.randrange(256)]) * rng.randrange(1, 1001) for _ in range(1000))
+    for s in STRATS:
+        _roundtrip(oracle, data, (s,))
+
+
+def test_long_random_multiblock(oracle):               # :89-115 (lengths up to 1 MB cross the 64 KiB block size)
+    rng = random.Random(89)
+    for _ in range(6):
+        n = rng.randrange(1000000)
+        data = bytes(rng.choices(range(256), weights=[1 + 40 * (i < 8) for i in range(256)], k=n))
+        _roundtrip(oracle, data, (oracle.RLE_DYNAMIC,))
+        _roundtrip(oracle, data[:200000], (oracle.FULL_DYNAMIC,))
+
+
+def test_history_crosses_blocks(oracle):
+    rng = random.Random(5)
+    seg = rng.randbytes(20000)
+    data = seg * 9                                      # repeats at distance 20000 across 64 KiB block boundaries
+    full = _roundtrip(oracle, data, (oracle.FULL_DYNAMIC,))
+    assert len(full) < len(data) // 4
+    nohist = _roundtrip(oracle, data, (oracle.FULL_DYNAMIC,), lookahead=16384, history=0)
+    assert len(nohist) > len(data) * 0.9
+
+
+def test_brute_force_equals_hash_chains(oracle):
+    rng = random.Random(11)
+    words = [rng.randbytes(rng.randrange(1, 8)) for _ in range(64)]
+    data = b"".join(rng.choice(words) for _ in range(3000))
+    for s in (oracle.FULL_STATIC, oracle.FULL_DYNAMIC, oracle.RLE_DYNAMIC):
+        assert oracle.deflate(data, (s,), brute_force=True) == oracle.deflate(data, (s,), brute_force=False)
+
+
+def test_multistrategy_never_worse(oracle):
+    rng = random.Random(13)
+    for data in (rng.randbytes(70000), bytes(70000), b"abcabcabd" * 5000, b"x"):
+        multi = _roundtrip(oracle, data, (oracle.UNCOMPRESSED, oracle.FULL_STATIC, oracle.FULL_DYNAMIC))
+        for s in (oracle.UNCOMPRESSED, oracle.FULL_STATIC, oracle.FULL_DYNAMIC):
+            assert len(multi) <= len(oracle.deflate(data, (s,)))
+
+
+APPENDIX_F = [
+    (b"", "LITERAL_STATIC", "0300"),
+    (b"", "FULL_DYNAMIC", "05c0810800000000a0fda92f"),
+    (b"A", "RLE_STATIC", "730400"),
+    (b"A", "RLE_DYNAMIC", "05c081080000000020b6fda54e"),
+    (b"abc" * 1000, "FULL_STATIC", "4b4c4a1e45a368148da251348a46d1281a45a368140d720400"),
+    (b"abc" * 1000, "FULL_DYNAMIC", "edc3411100000c02a0ac9bfd3b58c30777701f0000605c01"),
+    (bytes(1000), "RLE_STATIC", "631805a360140c7b0000"),
+    (bytes(1000), "FULL_DYNAMIC", "edc1010d000000c220fba7b6c7070cc83b"),
+    (b"a" * 10 + b"b" * 10, "LITERAL_STATIC", "4b4c4c4c4c4c4c4c4c4c4c4a4a4a4a4a4a4a4a4a0200"),
+    (b"a" * 10 + b"b" * 10, "FULL_STATIC", "4b848324380000"),
+    (b"a" * 10 + b"b" * 10, "LITERAL_DYNAMIC", "05c0810c0000008030d6ee0fd1aaaa0a8001"),
+    (b"a" * 10 + b"b" * 10, "RLE_DYNAMIC", "3dc13101000000c2a0acda3fc43e609c00"),
+]
+APPENDIX_F_CRC = [
+    (b"abc" * 1000, "RLE_DYNAMIC", 763, 0xF664BED9),
+    (bytes(1000), "LITERAL_DYNAMIC", 137, 0xC375BE96),
+    (bytes(range(256)), "FULL_STATIC", 272, 0x8557FBB7),
+    (bytes(range(256)), "FULL_DYNAMIC", 280, 0xFF540EEC),
+]
+
+
+@pytest.mark.parametrize("data,strat,hexout", APPENDIX_F)
+def test_cross_check_bytes(oracle, data, strat, hexout):
+    assert oracle.deflate(data, (getattr(oracle, strat),)).hex() == hexout
+
+
+@pytest.mark.parametrize("data,strat,n,crc", APPENDIX_F_CRC)
+def test_cross_check_crc(oracle, data, strat, n, crc):
+    comp = oracle.deflate(data, (getattr(oracle, strat),))
+    assert len(comp) == n and zlib.crc32(comp) == crc
+
+
+def test_package_merge_is_optimal_and_complete(oracle):
+    rng = random.Random(3)
+    for _ in range(200):
+        n = rng.randrange(2, 286)
+        hist = [rng.randrange(0, 1 << rng.randrange(1, 16)) if rng.random() < 0.7 else 0 for _ in range(n)]
+        if sum(h > 0 for h in hist) < 2:
+            continue
+        for limit in (15, 7) if sum(h > 0 for h in hist) <= 128 else (15,):
+            lens = oracle.package_merge(hist, limit)
+            assert all((l > 0) == (h > 0) for l, h in zip(lens, hist))
+            assert max(lens) <= limit
+            assert sum(2 ** (limit - l) for l in lens if l) == 2 ** limit     # complete code
+
+
+def test_crc32_and_gzip_container(oracle, tmp_path):
+    import gzip
+    import subprocess
+    assert oracle.crc32(b"123456789") == 0xCBF43926
+    rng = random.Random(17)
+    data = rng.randbytes(1000) + b"hello " * 30000
+    assert oracle.crc32(data) == zlib.crc32(data)
+    member = oracle.gzip_member(data, file_name="in.txt", mtime=1700000000)
+    assert gzip.decompress(member) == data                                      # Python's gzip (zlib)
+    st, out, consumed = oracle.gunzip(member, out_cap=len(data) + 8)
+    assert st == 0 and out == data and consumed == len(member)
+    p = tmp_path / "x.gz"
+    p.write_bytes(member)
+    assert subprocess.run(["gzip", "-t", str(p)]).returncode == 0               # system gzip 1.12
+    bad = bytearray(member); bad[-5] ^= 1
+    assert oracle.status_name(oracle.gunzip(bytes(bad), out_cap=len(data) + 8)[0]) == "DECOMPRESSED_CHECKSUM_MISMATCH"
+    bad = bytearray(member); bad[-1] ^= 1
+    assert oracle.status_name(oracle.gunzip(bytes(bad), out_cap=len(data) + 8)[0]) == "DECOMPRESSED_SIZE_MISMATCH"
+    bad = bytearray(member); bad[0] ^= 1
+    assert oracle.status_name(oracle.gunzip(bytes(bad), out_cap=len(data) + 8)[0]) == "GZIP_INVALID_MAGIC_NUMBER"
