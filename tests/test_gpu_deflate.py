@@ -1,0 +1,159 @@
+"""GPU parity: b2d_deflate_chunks (through the C ABI, host pointers).  Every stream must decode through the oracle
+(restating the reference decoder, decomp/Open.java) AND zlib back to the exact input; with reference framing and the
+reference's own greedy searches the bytes must equal the oracle encoder's (Lz77Huffman.java restated); the default
+search must land within 1 % of the reference's FULL_DYNAMIC at the same chunking."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from util import zlib_inflate_raw
+
+pytestmark = pytest.mark.gpu
+
+
+def _decode_both(oracle, comp, n):
+    comp = bytes(comp)
+    st, out, consumed = oracle.inflate(comp, out_cap=n + 8)
+    assert st == 0, oracle.status_name(st)
+    assert consumed == len(comp)
+    zout, zused = zlib_inflate_raw(comp)
+    assert zused == len(comp)
+    assert zout == out
+    return out
+
+
+def _text(rng, n):
+    words = [bytes(rng.choices(b"etaoinshrdlucmfw", k=rng.randrange(1, 10))) for _ in range(700)]
+    out = bytearray()
+    while len(out) < n:
+        out += rng.choice(words) + b" "
+    return bytes(out[:n])
+
+
+SIZES = [0, 1, 2, 3, 4, 5, 100, 4095, 4096, 65535, 65536, 65537, 200000, (1 << 20) - 1, 1 << 20, (1 << 20) + 1,
+         3 * (1 << 20) + 12345]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_roundtrip_default(b2d, oracle, n):
+    rng = random.Random(n)
+    data = _text(rng, n)
+    comp, crc, idx = b2d.deflate_chunks(data, b2d.make_opts(), crc=0)
+    assert _decode_both(oracle, comp, n) == data
+    assert crc == zlib.crc32(data)
+    if n:
+        assert int(idx.sum()) == len(comp)
+    if n >= 4096:
+        assert len(comp) < n * 0.6
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("search", [0, 1, 2, 3])
+def test_modes_and_searches(b2d, oracle, mode, search):
+    rng = random.Random(mode * 10 + search)
+    data = (_text(rng, 150000) + rng.randbytes(70000) + bytes(80000) + _text(rng, 30000) * 3)
+    opts = b2d.make_opts(mode=mode, search=search, chunk_bytes=1 << 17, block_bytes=1 << 15)
+    comp = b2d.deflate_chunks(data, opts)
+    assert _decode_both(oracle, comp, len(data)) == data
+
+
+def test_edge_corpora(b2d, oracle):
+    """Config-5 shapes at test size: incompressible bytes -> stored blocks; zeros -> 258/dist-1 runs; fixed only."""
+    n = 3 << 20
+    rnd = b2d.corpus("random", 0xDEF1A7E, n).tobytes()
+    comp = b2d.deflate_chunks(rnd, b2d.make_opts())
+    assert _decode_both(oracle, comp, n) == rnd
+    # a 64 KiB block is two stored pieces (<= 65535 bytes each, Uncompressed.java:51) = 10 bytes; + 5 per chunk marker
+    assert len(comp) == n + 10 * (n >> 16) + 5 * (n >> 20)
+    zeros = bytes(n)
+    comp = b2d.deflate_chunks(zeros, b2d.make_opts())
+    assert _decode_both(oracle, comp, n) == zeros
+    assert len(comp) < n // 500
+    text = b2d.corpus("text", 0xDEF1A7E, n).tobytes()
+    comp = b2d.deflate_chunks(text, b2d.make_opts(mode=b2d.MODE_FIXED))
+    assert _decode_both(oracle, comp, n) == text
+    # fixed-only: every block header is BTYPE=01 -> first 3 bits are 0,1,0 (BFINAL=0, type 1 LSB first)
+    assert comp[0] & 7 == 0b010
+
+
+@pytest.mark.parametrize("search,strat", [(1, "LITERAL"), (2, "RLE"), (3, "FULL")])
+@pytest.mark.parametrize("dynamic", [False, True])
+def test_reference_framing_is_byte_identical_to_oracle(b2d, oracle, search, strat, dynamic):
+    """framing=REFERENCE + the reference's greedy searches = the bytes DeflaterOutputStream would write
+    (oracle restatement of Lz77Huffman.java:42-288 framed per DeflaterOutputStream.java:119-137)."""
+    rng = random.Random(search)
+    datas = [b"", b"A", b"abc" * 1000, bytes(1000), bytes(range(256)), b"a" * 10 + b"b" * 10,
+             _text(rng, 200000), rng.randbytes(3000) * 30,
+             b"".join(bytes([rng.randrange(256)]) * rng.randrange(1, 600) for _ in range(400))]
+    sid = getattr(oracle, f"{strat}_{'DYNAMIC' if dynamic else 'STATIC'}")
+    for d in datas:
+        opts = b2d.make_opts(mode=b2d.MODE_DYNAMIC if dynamic else b2d.MODE_FIXED, search=search, lazy=0,
+                             framing=b2d.FRAMING_REFERENCE)
+        comp = bytes(b2d.deflate_chunks(d, opts))
+        want = oracle.deflate(d, (sid,))
+        assert comp == want, (strat, dynamic, len(d), len(comp), len(want))
+
+
+def test_reference_framing_multistrategy(b2d, oracle):
+    rng = random.Random(77)
+    d = _text(rng, 100000) + rng.randbytes(140000) + bytes(70000)
+    opts = b2d.make_opts(mode=b2d.MODE_AUTO, search=b2d.SEARCH_FULL, lazy=0, framing=b2d.FRAMING_REFERENCE)
+    comp = bytes(b2d.deflate_chunks(d, opts))
+    want = oracle.deflate(d, (oracle.UNCOMPRESSED, oracle.FULL_STATIC, oracle.FULL_DYNAMIC))
+    assert comp == want
+
+
+def test_ratio_within_one_percent_of_full_dynamic(b2d, oracle):
+    """north_star: compressed size within 1 % of the reference's dynamic-Huffman strategy at the same chunking
+    (FULL_DYNAMIC, history reset per 1 MiB chunk, 64 KiB blocks)."""
+    for kind in ("text", "mixed"):
+        data = b2d.corpus(kind, 0xDEF1A7E, 4 << 20).tobytes()
+        comp, crc, idx = b2d.deflate_chunks(data, b2d.make_opts(), crc=0)
+        assert _decode_both(oracle, comp, len(data)) == data
+        ref = 0
+        for c in range(4):
+            chunk = data[c << 20:(c + 1) << 20]
+            ref += len(oracle.deflate(chunk, (oracle.FULL_DYNAMIC,))) + 5     # + the chunk marker we add
+        assert len(comp) <= ref * 1.01, (kind, len(comp), ref)
+
+
+def test_streaming_calls_concatenate(b2d, oracle):
+    """is_last=0 calls followed by an is_last=1 call form ONE stream; the CRC runs across calls."""
+    rng = random.Random(9)
+    parts = [_text(rng, 1 << 20), rng.randbytes(300000), b"", _text(rng, 77777)]
+    out, crc = b"", 0
+    for i, p in enumerate(parts):
+        comp, crc, _ = b2d.deflate_chunks(p, b2d.make_opts(is_last=int(i == len(parts) - 1)), crc=crc)
+        out += bytes(comp)
+    whole = b"".join(parts)
+    assert _decode_both(oracle, out, len(whole)) == whole
+    assert crc == zlib.crc32(whole)
+
+
+def test_chunk_index_allows_independent_decode(b2d, oracle):
+    """Each chunk of the stream decodes on its own (chunk-indexed inflate): the multi-GPU / random-access unit."""
+    data = b2d.corpus("mixed", 5, (5 << 20) + 999).tobytes()
+    comp, crc, idx = b2d.deflate_chunks(data, b2d.make_opts(), crc=0)
+    comp = bytes(comp)
+    offs = np.concatenate([[0], np.cumsum(idx)]).astype(np.uint64)
+    members = [comp[int(offs[i]):int(offs[i + 1])] for i in range(len(idx))]
+    outs, out_len, consumed, crcs, status = b2d.inflate_batch(members, 1 << 20, flags=b2d.INFLATE_CHUNK_INDEXED | b2d.INFLATE_CRC32)
+    assert all(s == 0 for s in status), [b2d.status_name(int(s)) for s in status]
+    assert b"".join(outs) == data
+    c = 0
+    for i, o in enumerate(outs):
+        c = b2d.crc32_combine(c, int(crcs[i]), len(o))
+    assert c == zlib.crc32(data) == crc
+
+
+def test_crc32(b2d):
+    rng = random.Random(3)
+    assert b2d.crc32(b"123456789") == 0xCBF43926
+    for n in (0, 1, 15, 16, 17, 4095, 65536, (1 << 20) + 3, 5_000_001):
+        d = rng.randbytes(n)
+        assert b2d.crc32(d) == zlib.crc32(d), n
+        assert b2d.crc32(d, 0x12345678) == zlib.crc32(d, 0x12345678), n
+    d = np.frombuffer(rng.randbytes(100003), np.uint8)
+    assert b2d.crc32(d[3:]) == zlib.crc32(d[3:].tobytes())       # unaligned start

@@ -1,0 +1,185 @@
+"""GPU parity: b2d_inflate_batch (through the C ABI, host pointers) against the oracle restating
+decomp/Open.java, the reference's golden vectors, and zlib."""
+import random
+import zlib
+
+import numpy as np
+import pytest
+
+from util import BitWriter, bits_to_bytes, fixed_lit_code, golden_vectors, zlib_raw
+
+pytestmark = pytest.mark.gpu
+VECTORS = golden_vectors()
+
+
+def _check_against_oracle(b2d, oracle, members, caps, flags=0):
+    outs, out_len, consumed, crc, status = b2d.inflate_batch(members, caps, flags)
+    if isinstance(caps, int):
+        caps = [caps] * len(members)
+    for i, m in enumerate(members):
+        st, out, cons = oracle.inflate(bytes(m), out_cap=caps[i])
+        assert int(status[i]) == st, (i, b2d.status_name(int(status[i])), oracle.status_name(st))
+        assert outs[i] == out, (i, len(outs[i]), len(out))
+        if st == 0:
+            assert int(consumed[i]) == cons, i
+            if flags & b2d.INFLATE_CRC32:
+                assert int(crc[i]) == zlib.crc32(out)
+    return outs, status
+
+
+def test_golden_vectors_all_paddings(b2d, oracle):
+    """All 39 vectors x (0-pad, 1-pad, random pad) in ONE batch: a bad member must not disturb its neighbours."""
+    rng = random.Random(39)
+    members, expect = [], []
+    for v in VECTORS:
+        for pad in ("0", "1", "r", "r"):
+            members.append(bits_to_bytes(v["bits"], pad, rng))
+            expect.append(v)
+    outs, out_len, consumed, crc, status = b2d.inflate_batch(members, 1024)
+    for i, v in enumerate(expect):
+        if v["expect"] == "ok":
+            assert status[i] == 0, (v["name"], b2d.status_name(int(status[i])))
+            assert outs[i].hex() == v["output_hex"], v["name"]
+            assert consumed[i] == len(members[i]), v["name"]       # end-exactly (InflaterInputStreamTest.java:557-558)
+        else:
+            assert b2d.status_name(int(status[i])) == v["reason"], v["name"]
+    _check_against_oracle(b2d, oracle, members, 1024)
+    _check_against_oracle(b2d, oracle, members, 64)      # and with a slot too small for some vectors
+
+
+def test_empty_batch_and_empty_member(b2d):
+    outs, out_len, consumed, crc, status = b2d.inflate_batch([], 0)
+    assert outs == []
+    outs, out_len, consumed, crc, status = b2d.inflate_batch([b""], 16)
+    assert b2d.status_name(int(status[0])) == "UNEXPECTED_END_OF_STREAM"
+
+
+def _text(rng, n):
+    words = [bytes(rng.choices(b"etaoinshrdlucmfw", k=rng.randrange(1, 10))) for _ in range(700)]
+    out = bytearray()
+    while len(out) < n:
+        out += rng.choice(words) + b" "
+    return bytes(out[:n])
+
+
+def test_zlib_members(b2d, oracle):
+    rng = random.Random(101)
+    members, datas = [], []
+    for n in (0, 1, 2, 257, 258, 259, 4096, 70000, 262144, 300001):
+        data = _text(rng, n)
+        for level in (1, 6, 9):
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_RLE, zlib.Z_HUFFMAN_ONLY, zlib.Z_FIXED):
+                members.append(zlib_raw(data, level, strat))
+                datas.append(data)
+    rnd = rng.randbytes(150000)
+    members.append(zlib_raw(rnd, 0)); datas.append(rnd)           # stored blocks
+    members.append(zlib_raw(rnd, 6)); datas.append(rnd)
+    z = bytes(300000)
+    members.append(zlib_raw(z, 9)); datas.append(z)               # length 258 / distance 1
+    caps = [len(d) + 7 for d in datas]
+    outs, status = _check_against_oracle(b2d, oracle, members, caps, flags=b2d.INFLATE_CRC32)
+    for o, d in zip(outs, datas):
+        assert o == d
+
+
+def test_oracle_encoded_members_all_presets(b2d, oracle):
+    rng = random.Random(202)
+    datas = [b"", b"A", b"abc" * 1000, bytes(1000), bytes(range(256)), _text(rng, 200000), rng.randbytes(70000),
+             b"".join(bytes([rng.randrange(256)]) * rng.randrange(1, 600) for _ in range(300))]
+    members, expect = [], []
+    for d in datas:
+        for s in range(7):
+            members.append(oracle.deflate(d, (s,)))
+            expect.append(d)
+        members.append(oracle.deflate(d, (oracle.UNCOMPRESSED, oracle.FULL_STATIC, oracle.FULL_DYNAMIC)))
+        expect.append(d)
+    outs, status = _check_against_oracle(b2d, oracle, members, [len(d) + 3 for d in expect], flags=b2d.INFLATE_CRC32)
+    for o, d in zip(outs, expect):
+        assert o == d
+
+
+def test_random_constructions_of_reference_tests(b2d, oracle):
+    """Stored blocks with random padding / every start bit position / fixed literal blocks
+    (InflaterInputStreamTest.java:131-163, 166-208, 306-338) with fixed seeds."""
+    rng = random.Random(303)
+    members, expect = [], []
+    for _ in range(200):
+        bw, exp = BitWriter(), bytearray()
+        for _k in range(rng.randrange(1, 12)):
+            kind = rng.randrange(3)
+            bw.put(0, 1)
+            if kind == 0:
+                bw.put(0, 2)
+                bw.put(rng.randrange(256), (-len(bw.bits)) % 8)   # random padding bits
+                n = rng.randrange(1 << rng.randrange(1, 17))
+                payload = rng.randbytes(n)
+                bw.put(n, 16); bw.put(n ^ 0xFFFF, 16); bw.put_bytes(payload)
+                exp += payload
+            elif kind == 1:
+                bw.put(1, 2)
+                sym = rng.randrange(144, 256)
+                bw.put_code(*fixed_lit_code(sym)); bw.put_code(*fixed_lit_code(256))
+                exp.append(sym)
+            else:
+                bw.put(1, 2)
+                for _j in range(rng.randrange(1 << rng.randrange(1, 13))):
+                    b = rng.randrange(256)
+                    bw.put_code(*fixed_lit_code(b)); exp.append(b)
+                bw.put_code(*fixed_lit_code(256))
+        bw.put(1, 1); bw.put(1, 2); bw.put_code(*fixed_lit_code(256))
+        members.append(bw.tobytes()); expect.append(bytes(exp))
+    outs, status = _check_against_oracle(b2d, oracle, members, [len(e) + 1 for e in expect])
+    assert all(s == 0 for s in status)
+    for o, e in zip(outs, expect):
+        assert o == e
+
+
+def test_truncations_and_corruptions_match_oracle(b2d, oracle):
+    """Every prefix of a few streams, and random single-byte corruptions: status, delivered bytes and (for OK)
+    consumed input must equal the oracle's."""
+    rng = random.Random(404)
+    base = [zlib_raw(_text(rng, 3000), 6), zlib_raw(_text(rng, 3000), 6, zlib.Z_FIXED), zlib_raw(rng.randbytes(500), 0),
+            oracle.deflate(_text(rng, 2000), (oracle.FULL_DYNAMIC,))]
+    members = []
+    for s in base:
+        for cut in range(0, len(s), max(1, len(s) // 97)):
+            members.append(s[:cut])
+        for _ in range(150):
+            b = bytearray(s)
+            b[rng.randrange(len(b))] ^= 1 << rng.randrange(8)
+            members.append(bytes(b))
+    _check_against_oracle(b2d, oracle, members, 8192)
+
+
+def test_uncovered_reasons(b2d, oracle):
+    bw = BitWriter()
+    bw.put(1, 1); bw.put(1, 2); bw.put_code(*fixed_lit_code(257)); bw.put_code(0, 5)
+    m1 = bw.tobytes()
+    bw = BitWriter()
+    bw.put(1, 1); bw.put(1, 2); bw.put_code(*fixed_lit_code(65)); bw.put_code(*fixed_lit_code(257)); bw.put_code(1, 5)
+    m2 = bw.tobytes()
+    outs, status = _check_against_oracle(b2d, oracle, [m1, m2], 64)
+    assert [b2d.status_name(int(s)) for s in status] == ["COPY_FROM_BEFORE_DICTIONARY_START"] * 2
+    assert outs == [b"", b"A"]
+
+
+def test_output_overflow(b2d, oracle):
+    data = b"abcdefgh" * 1000 + bytes(5000)
+    m = zlib_raw(data)
+    outs, out_len, consumed, crc, status = b2d.inflate_batch([m, m, m], [100, len(data), len(data) - 1])
+    assert status[0] == b2d.ERR_OUTPUT_OVERFLOW and outs[0] == data[:100]
+    assert status[1] == 0 and outs[1] == data
+    assert status[2] == b2d.ERR_OUTPUT_OVERFLOW and outs[2] == data[:-1]
+
+
+def test_batch_shape_of_config2_small(b2d, oracle):
+    """The BASELINE config-2 shape at reduced count: independent 256 KiB members, fixed output stride."""
+    n, size = 96, 256 * 1024
+    datas = [b2d.corpus("text", 0xDEF1A7E + i, size).tobytes() for i in range(n)]
+    members = [zlib_raw(d, 6) for d in datas]
+    outs, out_len, consumed, crc, status = b2d.inflate_batch(members, size, flags=b2d.INFLATE_CRC32)
+    assert all(s == 0 for s in status)
+    for i in range(n):
+        assert outs[i] == datas[i] and consumed[i] == len(members[i]) and crc[i] == zlib.crc32(datas[i])
+    st, out, cons = oracle.inflate(members[0], out_cap=size)
+    assert st == 0 and out == outs[0]
