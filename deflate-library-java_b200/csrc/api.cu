@@ -245,7 +245,7 @@ B2D_API int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off,
 	if (n && (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_in_consumed || !d_status))
 		return B2D_ERR_BAD_ARGUMENT;
 	if ((flags & B2D_INFLATE_CRC32) && !d_crc32 && n) return B2D_ERR_BAD_ARGUMENT;
-	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	cudaStream_t st = (cudaStream_t)stream;
 	return inflate_dev_locked(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_crc32, d_status, flags, st);
 }
 
@@ -331,7 +331,7 @@ B2D_API int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b
 	if ((in_len && !d_in) || !d_out || !d_out_len_total) return B2D_ERR_BAD_ARGUMENT;
 	if (out_cap < deflate_bound_bytes(in_len, p.chunk_bytes, p.block_bytes)) return B2D_ERR_OUTPUT_OVERFLOW;
 	CK(cudaSetDevice(g.device));
-	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	cudaStream_t st = (cudaStream_t)stream;
 	return deflate_dev_locked(d_in, in_len, p, d_out, out_cap, d_out_len_total, d_chunk_out_len, d_chunk_crc32, st);
 }
 
@@ -392,7 +392,7 @@ B2D_API int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_o
 	if (!g.ready) return B2D_ERR_NO_DEVICE;
 	if ((len && !d_data) || !d_crc_out) return B2D_ERR_BAD_ARGUMENT;
 	CK(cudaSetDevice(g.device));
-	cudaStream_t st = stream ? (cudaStream_t)stream : g.st[0];
+	cudaStream_t st = (cudaStream_t)stream;
 	const uint64_t piece = 1u << 20;
 	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
 	int r = ensure(g.crc, (size_t)(n_pieces + 1) * 4);

@@ -12,7 +12,8 @@
  *     and spawn no threads; FFM downcalls may come from any JVM thread).
  *   - Host entry points take HOST pointers and include the host<->device copies.  The *_dev entry
  *     points take DEVICE pointers (e.g. torch tensor data_ptr()) and run on the given CUDA stream
- *     (a cudaStream_t passed as void*, NULL = the library's own stream) without synchronising it.
+ *     (a cudaStream_t passed as void*; NULL = the CUDA legacy default stream, which is what
+ *     torch.cuda.current_stream().cuda_stream is unless the caller switched streams) without synchronising it.
  *   - There is no CPU fallback: every call fails with B2D_ERR_NO_DEVICE if no sm_100 GPU is usable.
  *   - Format errors are per-member status codes: 0 = OK, otherwise 1 + Reason.ordinal() of the
  *     reference's DataFormatException.Reason (DataFormatException.java:61-83).  The Java wrapper
