@@ -2,18 +2,20 @@
 //
 // Replaces the decode loops of the reference (paths relative to src/io/nayuki/deflate/):
 //   decomp/Open.java:83-110   block loop            -> inflate_member()
-//   decomp/Open.java:137-170  bit reader            -> BitIn (64-bit buffer, 32-bit aligned refills, prefetch)
+//   decomp/Open.java:137-170  bit reader            -> BitIn (three words in registers, funnel-shift peek)
 //   decomp/Open.java:227-306  stored block          -> stored_block()  (warp-wide coalesced copy)
 //   decomp/Open.java:336-431  dynamic header        -> dynamic_header()
 //   decomp/Open.java:705-789  code tree + 9-bit LUT -> build_code(): canonical codes built by the whole warp
 //                                                      into a 10-bit (lit/len) / 8-bit (distance) LUT in shared
 //                                                      memory, longer codes resolved canonically (no tree walk)
-//   decomp/Open.java:438-620  symbol loop + copy    -> decode_tokens(): every lane decodes the same symbol from
-//                                                      shared tables (no divergence, no broadcast needed), then the
-//                                                      32 lanes copy the back-reference together
+//   decomp/Open.java:438-620  symbol loop + copy    -> decode_block(): every lane decodes the same symbol from
+//                                                      shared tables (no divergence, no broadcast needed); output is
+//                                                      staged in a shared-memory tile, back-references are queued
+//                                                      and resolved 32 at a time by resolve()
 // Results (bytes, out_len, consumed input, status) are identical to the reference's; the validation ORDER of
-// Open.java is kept (first failing check wins).  Not a translation: no dictionary ring (the output buffer is
-// the window), no code tree, no per-block allocation.
+// Open.java is kept (first failing check wins).  Not a translation: no dictionary ring (the output buffer plus
+// the staging tile are the window), no code tree, no per-block allocation.
+#include <cstdio>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -22,6 +24,8 @@ namespace b2d {
 constexpr int LL_TB = 10;                 // lit/len LUT index bits
 constexpr int D_TB = 8;                   // distance LUT index bits
 constexpr int WARPS_PER_CTA = 4;
+constexpr int CTAS_PER_SM = 7;            // 28 resident warps per SM: 4096 members fit one wave on 148 SMs
+constexpr int TILE = 1024;                // bytes of output staged per warp in shared memory
 
 // LUT entry: [4:0] total bits (code + extra)  [8:5] code length  [12:9] extra-bit count
 //            [31:27] flags (lit/len)  or bit 31 (distance)        [26:16] / [30:16] value
@@ -41,7 +45,8 @@ struct Canon {                            // canonical-code description for the 
 	u16 offs[16];
 };
 
-struct WarpSmem {
+struct __align__(16) WarpSmem {
+	u8 tile[TILE];                        // output staging: tile[i] <-> global byte tile_g[i]
 	u32 ll_lut[1 << LL_TB];
 	u32 d_lut[1 << D_TB];
 	Canon ll_canon, d_canon;
@@ -51,16 +56,18 @@ struct WarpSmem {
 	u8 lens[320];
 };
 
+// Bit reader: three consecutive 32-bit words of the member live in registers (cur, nxt and a prefetched
+// third); peek() funnel-shifts 32 bits out of (cur, nxt) at bit `sh`, consuming bits is `sh += n`, and
+// advance() slides the window by one word.  Loads are 4-byte aligned and never pass n_safe.
 struct BitIn {
 	const u32 *words;     // 4-byte aligned base at or before the member's first byte
 	u32 n_safe;           // words that may be read (cover the last real byte)
 	u32 n_full;           // words that hold only real bytes
 	u32 lead8;            // bits to skip in word 0
 	u64 total_bits;       // real bits in the member
-	u64 buf;
-	int cnt;              // bits in buf (may include bits past the end of input; see avail())
-	u32 next;             // prefetched word `widx`
+	u32 cur, nxt, pre;    // words widx, widx + 1, widx + 2
 	u32 widx;
+	u32 sh;               // bits of `cur` already consumed; >= 32 means advance() is due
 };
 
 __device__ __forceinline__ u32 load_word(const BitIn &b, u32 i) {
@@ -68,23 +75,23 @@ __device__ __forceinline__ u32 load_word(const BitIn &b, u32 i) {
 }
 __device__ __forceinline__ void bit_seek(BitIn &b, u64 byte_pos) {     // byte_pos relative to member start
 	u64 a = (b.lead8 >> 3) + byte_pos;
-	u32 w = (u32)(a >> 2);
-	u32 sh = (u32)(a & 3) * 8;
-	b.buf = load_word(b, w) >> sh;
-	b.cnt = 32 - (int)sh;
-	b.widx = w + 1;
-	b.next = load_word(b, b.widx);
+	b.widx = (u32)(a >> 2);
+	b.sh = (u32)(a & 3) * 8;
+	b.cur = load_word(b, b.widx);
+	b.nxt = load_word(b, b.widx + 1);
+	b.pre = load_word(b, b.widx + 2);
 }
-__device__ __forceinline__ void refill(BitIn &b) {                     // afterwards cnt >= 32
-	if (b.cnt < 32) {
-		b.buf |= (u64)b.next << b.cnt;
-		b.cnt += 32;
-		b.widx++;
-		b.next = load_word(b, b.widx);
-	}
+__device__ __forceinline__ void advance(BitIn &b) {
+	b.sh -= 32;
+	b.cur = b.nxt;
+	b.nxt = b.pre;
+	b.widx++;
+	b.pre = load_word(b, b.widx + 2);
 }
+__device__ __forceinline__ void norm(BitIn &b) { if (b.sh >= 32) advance(b); }
+__device__ __forceinline__ u32 peek(const BitIn &b) { return __funnelshift_r(b.cur, b.nxt, b.sh); }   // sh < 32
 __device__ __forceinline__ u64 consumed_bits(const BitIn &b) {
-	return (u64)b.widx * 32 - b.lead8 - (u64)b.cnt;
+	return (u64)b.widx * 32 + b.sh - b.lead8;
 }
 __device__ __forceinline__ int avail_bits(const BitIn &b) {            // real bits left, clamped to int
 	u64 c = consumed_bits(b);
@@ -92,14 +99,13 @@ __device__ __forceinline__ int avail_bits(const BitIn &b) {            // real b
 	u64 a = b.total_bits - c;
 	return a > 0x3FFFFFFFull ? 0x3FFFFFFF : (int)a;
 }
-__device__ __forceinline__ void drop(BitIn &b, int n) { b.buf >>= n; b.cnt -= n; }
 
 // checked read for headers (Open.readBits, Open.java:137-170): n <= 16
 __device__ __forceinline__ int getbits(BitIn &b, int n, int &avail, int &err) {
-	refill(b);
+	norm(b);
 	if (n > avail) { err = B2D_UNEXPECTED_END_OF_STREAM; return 0; }
-	u32 v = (u32)b.buf & ((1u << n) - 1);
-	drop(b, n);
+	u32 v = peek(b) & ((1u << n) - 1);
+	b.sh += n;
 	avail -= n;
 	return (int)v;
 }
@@ -190,114 +196,236 @@ __device__ __noinline__ u32 slow_decode(u32 lo, const Canon *cn, const u16 *sort
 	return IS_DIST ? (FD_SPECIAL | 31u << 16 | 15u << 5 | 15u) : (F_RSVD | 15u << 5 | 15u);   // unreachable for complete codes
 }
 
+// Per-member decoder state.  Output goes through a TILE-byte staging tile in shared memory: tile[i] holds the
+// byte of global address tile_g[i] (tile_g is 16-byte aligned), indices [tstart, tpos) are valid and not yet
+// flushed.  Literals are stored into the tile as they are decoded; back-references are only RECORDED (lane k of
+// the warp keeps the k-th pending one in registers) and resolved 32 at a time by resolve(), so the loads of
+// all references whose source is already in global memory are in flight together instead of one L2 round
+// trip per match, and references into the tile itself are served from shared memory.
 struct Member {
 	BitIn in;
 	u8 *out;
 	u64 cap;
-	u64 pos;
+	u8 *tile_g;          // global address of tile[0]
+	u32 tstart, tpos, tlimit;
+	int pos_base;        // min(tile_g - out, 1 << 20): output position of tile[0] for the dictionary-start check
+	u32 nm;              // pending back-references (warp-uniform)
+	u32 pa, pb;          // this lane's pending reference: pa = tile offset | length << 16, pb = distance
 	bool no_dist;        // dynamic block with an empty distance code (Open.java:398-401)
 	int tables;          // 0 none, 1 fixed tables resident
 };
 
-enum { TOK_EOB = 0, TOK_SWITCH = 1000 };
+enum { R_EOB = 0, R_SWITCH = 1000 };
 
-// Copies a back-reference with all 32 lanes.  Overlap (dist < len) replicates the pattern like the
-// reference's byte-serial loop (Open.java:596-603): byte k comes from out[pos - dist + k mod dist].
-__device__ __forceinline__ void copy_match(u8 *out, u64 pos, int len, int dist, u32 lane) {
-	u8 *dst = out + pos;
-	const u8 *src = dst - dist;
-	__syncwarp();                       // earlier stores of other lanes (literals, previous copies) are visible
-	if (dist >= len) {
-		for (int k = lane; k < len; k += 32) dst[k] = src[k];
-	} else if (dist == 1) {
-		u8 v = src[0];
-		for (int k = lane; k < len; k += 32) dst[k] = v;
+__device__ __forceinline__ u64 out_pos(const Member &m) { return (u64)((long long)(m.tile_g - m.out) + (long long)m.tpos); }
+
+__device__ __forceinline__ void set_tile_origin(Member &m, u64 pos) {
+	u8 *a = m.out + pos;
+	u32 mis = (u32)((uintptr_t)a & 15);
+	m.tile_g = a - mis;
+	m.tstart = m.tpos = mis;
+	u64 room = m.cap - pos;
+	m.tlimit = room >= (u64)(TILE - mis) ? (u32)TILE : mis + (u32)room;
+	long long rel0 = (long long)pos - (long long)mis;
+	m.pos_base = rel0 > (1 << 20) ? (1 << 20) : (int)rel0;
+}
+
+// Materialises the pending back-references into the tile.  Copies replicate the pattern when dist < len exactly
+// like the reference's byte-serial loop (Open.java:596-603): byte k comes from position pos - dist + (k mod dist).
+// (All state by value: a by-reference Member would be forced into local memory by the call.)
+__device__ __noinline__ void resolve_pending(u8 *tile, u8 *tile_g, int ts, u32 nm, u32 pa, u32 pb, u32 lane) {
+	__syncwarp();                                   // literal stores of lane 0 are visible
+	const bool have = lane < nm;
+	const int off = (int)(pa & 0xFFFFu), len = (int)(pa >> 16), dist = (int)pb;
+	const int s = off - dist;                        // tile index of the source start (may be negative)
+	const bool far = have && (s + len <= ts);        // source lies wholly in global memory (already flushed)
+	// (1) far, short: each lane gathers its own reference, 8 bytes per round, all loads issued before the stores
+	{
+		const bool mine = far && len <= 16;
+		const u8 *gs = tile_g + s;
+		if (__any_sync(FULL_MASK, mine)) {
+			u8 v[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) if (mine && k < len) v[k] = gs[k];
+#pragma unroll
+			for (int k = 0; k < 8; k++) if (mine && k < len) tile[off + k] = v[k];
+			if (__any_sync(FULL_MASK, mine && len > 8)) {
+#pragma unroll
+				for (int k = 0; k < 8; k++) if (mine && 8 + k < len) v[k] = gs[8 + k];
+#pragma unroll
+				for (int k = 0; k < 8; k++) if (mine && 8 + k < len) tile[off + 8 + k] = v[k];
+			}
+		}
+	}
+	// (2) far, long: the warp copies one reference at a time, 32 bytes per step
+	for (u32 mask = __ballot_sync(FULL_MASK, far && len > 16); mask; mask &= mask - 1) {
+		const int j = __ffs(mask) - 1;
+		const int o = __shfl_sync(FULL_MASK, off, j), l = __shfl_sync(FULL_MASK, len, j), si = __shfl_sync(FULL_MASK, s, j);
+		const u8 *gs = tile_g + si;
+		for (int k = lane; k < l; k += 32) tile[o + k] = gs[k];
+	}
+	__syncwarp();
+	// (3) near: source overlaps the tile; strictly in stream order, from shared memory
+	for (u32 mask = __ballot_sync(FULL_MASK, have && !far); mask; mask &= mask - 1) {
+		const int j = __ffs(mask) - 1;
+		const int o = __shfl_sync(FULL_MASK, off, j), l = __shfl_sync(FULL_MASK, len, j), d = __shfl_sync(FULL_MASK, dist, j);
+		const int si = o - d;
+		if (si >= ts) {
+			if (d >= l) {
+				for (int k = lane; k < l; k += 32) tile[o + k] = tile[si + k];
+			} else if (d == 1) {
+				const u8 v = tile[si];
+				for (int k = lane; k < l; k += 32) tile[o + k] = v;
+			} else {
+				for (int k = lane; k < l; k += 32) tile[o + k] = tile[si + k % d];
+			}
+		} else {                                     // source straddles the flushed / staged boundary
+			for (int k = lane; k < l; k += 32) {
+				const int idx = si + (d < l ? k % d : k);
+				tile[o + k] = idx < ts ? tile_g[idx] : tile[idx];
+			}
+		}
+		__syncwarp();
+	}
+}
+
+__device__ __forceinline__ void resolve(Member &m, WarpSmem *sm, u32 lane) {
+	resolve_pending(sm->tile, m.tile_g, (int)m.tstart, m.nm, m.pa, m.pb, lane);
+	m.nm = 0;
+}
+
+// Writes tile[lo, hi) to global memory (16-byte vectors for the aligned body).
+__device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u32 lane) {
+	__syncwarp();
+	const u32 a = (lo + 15) & ~15u, b = hi & ~15u;
+	if (a >= b) {
+		for (u32 k = lo + lane; k < hi; k += 32) g[k] = tile[k];
 	} else {
-		for (int k = lane; k < len; k += 32) dst[k] = src[k % dist];
+		if (lo + lane < a) g[lo + lane] = tile[lo + lane];
+		for (u32 v = (a >> 4) + lane; v < (b >> 4); v += 32) ((uint4 *)g)[v] = ((const uint4 *)tile)[v];
+		if (b + lane < hi) g[b + lane] = tile[b + lane];
 	}
 	__syncwarp();
 }
 
-// Decodes symbols of one Huffman block until end-of-block.  CAREFUL=false requires that two whole real
-// words remain behind `next` at the top of every iteration, so no read can pass the end of input and the
-// end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the
+// Resolves what is pending, writes the staged bytes out and re-bases the tile at the current output position.
+__device__ __forceinline__ void flush_tile(Member &m, WarpSmem *sm, u32 lane) {
+	if (m.nm) resolve(m, sm, lane);
+	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane);
+	set_tile_origin(m, out_pos(m));
+}
+
+// Makes room for at least one more byte; B2D_ERR_OUTPUT_OVERFLOW when the member's slot is full.
+__device__ __forceinline__ int make_room(Member &m, WarpSmem *sm, u32 lane) {
+	flush_tile(m, sm, lane);
+	return m.tpos >= m.tlimit ? B2D_ERR_OUTPUT_OVERFLOW : 0;
+}
+
+// Decodes symbols of one Huffman block until end-of-block.  CAREFUL=false requires that the three words
+// (cur, nxt, pre) hold only real input at the top of every iteration, so no read can pass the end of input and
+// the end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the
 // reference's order (Open.java:565-593).
 template <bool CAREFUL>
-__device__ int decode_tokens(Member &m, WarpSmem *sm, u32 lane) {
+__device__ int decode_block(Member &m, WarpSmem *sm, u32 lane) {
 	BitIn &b = m.in;
 	int avail = CAREFUL ? avail_bits(b) : 0;
+#ifdef B2D_DEBUG
+	if (lane == 0) printf("decode_block<%d> enter widx=%u sh=%u n_full=%u n_safe=%u avail=%d tpos=%u\n", (int)CAREFUL, b.widx, b.sh, b.n_full, b.n_safe, avail, m.tpos);
+#endif
+	const u32 fast_last = b.n_full - 3;              // FAST is only entered with n_full >= 3
 	for (;;) {
-		if (!CAREFUL && b.widx + 2 > b.n_full) return TOK_SWITCH;
-		refill(b);
-		u32 lo = (u32)b.buf;
+		if (b.sh >= 32) advance(b);
+		if (!CAREFUL && b.widx > fast_last) return R_SWITCH;     // (the mid-symbol norm() below may have advanced too)
+		u32 lo = peek(b);
 		u32 e = sm->ll_lut[lo & ((1u << LL_TB) - 1)];
 		if (e & F_LONG) e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted);
-		int clen = (e >> 5) & 15;
-		if (CAREFUL && clen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
 		if (e & F_LIT) {
-			if (m.pos >= m.cap) return B2D_ERR_OUTPUT_OVERFLOW;
-			if (lane == 0) m.out[m.pos] = (u8)(e >> 16);
-			m.pos++;
-			drop(b, clen);
+			const int clen = e & 31;
+#ifdef B2D_DEBUG
+			if (lane == 0 && b.widx + 4 > b.n_full) printf(" lit widx=%u sh=%u clen=%d avail=%d byte=%02x\n", b.widx, b.sh, clen, avail, (e >> 16) & 255);
+#endif
+			if (CAREFUL && clen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
+			if (m.tpos >= m.tlimit) { int r = make_room(m, sm, lane); if (r) return r; }
+			if (lane == 0) sm->tile[m.tpos] = (u8)(e >> 16);
+			m.tpos++;
+			b.sh += clen;
 			if (CAREFUL) avail -= clen;
 			continue;
 		}
+		const int clen = (e >> 5) & 15;
+		if (CAREFUL && clen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
 		if (e & F_EOB) {
-			drop(b, clen);
-			__syncwarp();
-			return TOK_EOB;
+			b.sh += clen;
+			return R_EOB;
 		}
 		if (e & F_RSVD) return B2D_RESERVED_LENGTH_SYMBOL;
-		int tot = e & 31;
+		const int tot = e & 31;
+#ifdef B2D_DEBUG
+		if (lane == 0 && b.widx + 4 > b.n_full) printf(" len widx=%u sh=%u clen=%d tot=%d avail=%d\n", b.widx, b.sh, clen, tot, avail);
+#endif
 		if (CAREFUL && tot > avail) return B2D_UNEXPECTED_END_OF_STREAM;
 		int len = (int)((e >> 16) & 0x7FF) + (int)bfe(lo, clen, (e >> 9) & 15);
-		drop(b, tot);
+		b.sh += tot;
 		if (CAREFUL) avail -= tot;
 		if (m.no_dist) return B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE;
-		refill(b);
-		lo = (u32)b.buf;
+		norm(b);
+		lo = peek(b);
 		u32 d = sm->d_lut[lo & ((1u << D_TB) - 1)];
 		if (d & FD_SPECIAL) {
 			if (((d >> 16) & 0x7FFF) == 0) d = slow_decode<D_TB, true>(lo, &sm->d_canon, sm->d_sorted);
 		}
-		int dclen = (d >> 5) & 15;
+		const int dclen = (d >> 5) & 15;
 		if (CAREFUL && dclen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
 		if (d & FD_SPECIAL) return B2D_RESERVED_DISTANCE_SYMBOL;
-		int dtot = d & 31;
+		const int dtot = d & 31;
+#ifdef B2D_DEBUG
+		if (lane == 0 && b.widx + 4 > b.n_full) printf(" dist widx=%u sh=%u dclen=%d dtot=%d avail=%d len=%d\n", b.widx, b.sh, dclen, dtot, avail, len);
+#endif
 		if (CAREFUL && dtot > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		int dist = (int)(d >> 16) + (int)bfe(lo, dclen, (d >> 9) & 15);
-		drop(b, dtot);
+		const int dist = (int)(d >> 16) + (int)bfe(lo, dclen, (d >> 9) & 15);
+		b.sh += dtot;
 		if (CAREFUL) avail -= dtot;
-		if ((u64)dist > m.pos) return B2D_COPY_FROM_BEFORE_DICTIONARY_START;     // Open.java:592-593
-		if (m.pos + (u64)len > m.cap) {
-			int fit = (int)(m.cap - m.pos);                                       // deliver what fits (Open.java:604-616)
-			copy_match(m.out, m.pos, fit, dist, lane);
-			m.pos = m.cap;
-			return B2D_ERR_OUTPUT_OVERFLOW;
+		if (dist > m.pos_base + (int)m.tpos) return B2D_COPY_FROM_BEFORE_DICTIONARY_START;     // Open.java:592-593
+		// record the reference; a reference that does not fit the tile is split (same distance), and when the
+		// member's slot is full what fits is still delivered (Open.java:604-616) before the overflow is reported
+		for (;;) {
+			const u32 fit = m.tlimit - m.tpos;
+			const u32 take = (u32)len < fit ? (u32)len : fit;
+			if (take) {
+				if (lane == m.nm) { m.pa = m.tpos | take << 16; m.pb = (u32)dist; }
+				m.nm++;
+				m.tpos += take;
+				len -= (int)take;
+				if (m.nm == 32) resolve(m, sm, lane);
+			}
+			if (len == 0) break;
+			int r = make_room(m, sm, lane);
+			if (r) return r;
 		}
-		copy_match(m.out, m.pos, len, dist, lane);
-		m.pos += len;
 	}
 }
 
 // Open.UncompressedBlock (Open.java:227-306)
-__device__ int stored_block(Member &m, int &avail, u32 lane) {
+__device__ int stored_block(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 	BitIn &b = m.in;
 	int err = 0;
-	getbits(b, b.cnt & 7, avail, err);                  // align to byte (:234); cnt%8 == unread bits of the byte
+	norm(b);
+	getbits(b, (8 - (b.sh & 7)) & 7, avail, err);       // align to byte (:234)
 	int len = getbits(b, 16, avail, err);
 	if (err) return err;
 	int nlen = getbits(b, 16, avail, err);
 	if (err) return err;
 	if (len != (nlen ^ 0xFFFF)) return B2D_UNCOMPRESSED_BLOCK_LENGTH_MISMATCH;   // :239-240
+	flush_tile(m, sm, lane);                            // the payload goes global -> global, past the tile
+	u64 pos = out_pos(m);
 	u64 byte_pos = consumed_bits(b) >> 3;
 	u64 in_len = b.total_bits >> 3;
 	u64 have = in_len - byte_pos;
 	u64 n = (u64)len < have ? (u64)len : have;
 	int status = (u64)len > have ? B2D_UNEXPECTED_END_OF_STREAM : 0;            // :279-280
-	if (m.pos + n > m.cap) { n = m.cap - m.pos; status = B2D_ERR_OUTPUT_OVERFLOW; }
+	if (pos + n > m.cap) { n = m.cap - pos; status = B2D_ERR_OUTPUT_OVERFLOW; }
 	const u8 *src = (const u8 *)b.words + (b.lead8 >> 3) + byte_pos;
-	u8 *dst = m.out + m.pos;
+	u8 *dst = m.out + pos;
 	// vector body when source and destination share 16-byte phase, bytes otherwise
 	if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0 && n >= 64) {
 		u64 head = (16 - ((uintptr_t)dst & 15)) & 15;
@@ -307,11 +435,19 @@ __device__ int stored_block(Member &m, int &avail, u32 lane) {
 		uint4 *d4 = (uint4 *)(dst + head);
 		for (u64 k = lane; k < nv; k += 32) d4[k] = __ldg(s4 + k);
 		for (u64 k = head + (nv << 4) + lane; k < n; k += 32) dst[k] = src[k];
+	} else if ((((uintptr_t)src ^ (uintptr_t)dst) & 3) == 0 && n >= 64) {
+		u64 head = (4 - ((uintptr_t)dst & 3)) & 3;
+		for (u64 k = lane; k < head; k += 32) dst[k] = src[k];
+		u64 nv = (n - head) >> 2;
+		const u32 *s4 = (const u32 *)(src + head);
+		u32 *d4 = (u32 *)(dst + head);
+		for (u64 k = lane; k < nv; k += 32) d4[k] = __ldg(s4 + k);
+		for (u64 k = head + (nv << 2) + lane; k < n; k += 32) dst[k] = src[k];
 	} else {
 		for (u64 k = lane; k < n; k += 32) dst[k] = src[k];
 	}
 	__syncwarp();
-	m.pos += n;
+	set_tile_origin(m, pos + n);
 	if (status) return status;
 	bit_seek(b, byte_pos + n);
 	return 0;
@@ -361,11 +497,11 @@ __device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 	int total = num_ll + num_d;
 	int run_val = -1;
 	for (int i = 0; i < total;) {
-		refill(b);
-		u32 e = sm->cl_lut[(u32)b.buf & 127u];
+		norm(b);
+		u32 e = sm->cl_lut[peek(b) & 127u];
 		int l = e & 15, sym = e >> 4;
 		if (l > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		drop(b, l);
+		b.sh += l;
 		avail -= l;
 		if (sym < 16) {
 			run_val = sym;
@@ -427,7 +563,7 @@ __device__ void fixed_tables(Member &m, WarpSmem *sm, u32 lane) {
 	m.tables = 1;
 }
 
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
                u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags) {
@@ -451,7 +587,9 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	bit_seek(m.in, 0);
 	m.out = out + o0;
 	m.cap = o1 - o0;
-	m.pos = 0;
+	m.nm = 0;
+	m.pa = m.pb = 0;
+	set_tile_origin(m, 0);
 	m.no_dist = false;
 	m.tables = 0;
 
@@ -459,26 +597,32 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	bool last = false;
 	const bool chunk_mode = (flags & B2D_INFLATE_CHUNK_INDEXED) != 0;
 	while (!last) {                                                        // Open.read, Open.java:83-110
+		norm(m.in);
 		int avail = avail_bits(m.in);
-		if (chunk_mode && avail == 0 && (m.in.cnt & 7) == 0) break;        // chunk ends on a block boundary
+		if (chunk_mode && avail == 0 && (m.in.sh & 7) == 0) break;         // chunk ends on a block boundary
 		last = getbits(m.in, 1, avail, err) != 0;
 		int type = getbits(m.in, 2, avail, err);
 		if (err) break;
 		if (type == 0) {
-			err = stored_block(m, avail, lane);
+			err = stored_block(m, sm, avail, lane);
 			if (err) break;
 			continue;
 		}
 		if (type == 3) { err = B2D_RESERVED_BLOCK_TYPE; break; }          // :96
 		if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
-		int r = decode_tokens<false>(m, sm, lane);
-		if (r == TOK_SWITCH) r = decode_tokens<true>(m, sm, lane);
-		if (r != TOK_EOB) { err = r; break; }
+		norm(m.in);
+		#ifdef B2D_FORCE_CAREFUL
+		int r = R_SWITCH;
+#else
+		int r = m.in.widx + 3 <= m.in.n_full ? decode_block<false>(m, sm, lane) : (int)R_SWITCH;
+#endif
+		if (r == R_SWITCH) r = decode_block<true>(m, sm, lane);
+		if (r != R_EOB) { err = r; break; }
 	}
-	__syncwarp();
+	flush_tile(m, sm, lane);                                               // also resolves what is pending
 	if (lane == 0) {
-		out_len[mi] = m.pos;
+		out_len[mi] = out_pos(m);
 		in_consumed[mi] = (consumed_bits(m.in) + 7) >> 3;                  // Open.finish, Open.java:113-124
 		status[mi] = err;
 	}
@@ -487,6 +631,13 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,
                            u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st) {
 	if (n == 0) return cudaSuccess;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+		                                     cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess) return e;
+		attr_set = true;
+	}
 	u32 grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	inflate_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(d_in, d_in_off, n, d_out, d_out_off, d_out_len,
 	                                                     d_in_consumed, d_status, flags);
