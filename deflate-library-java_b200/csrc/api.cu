@@ -9,6 +9,7 @@
 // staging logic (H2D -> kernels -> D2H, sliced so copies overlap compute).  There is no CPU codec in this
 // library: without a usable sm_100 device every entry point returns B2D_ERR_NO_DEVICE.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -28,7 +29,7 @@ struct Ctx {
 	bool ready = false;
 	int device = -1;
 	int sm_count = 0;
-	cudaStream_t st[3] = {nullptr, nullptr, nullptr};    // round-robin pipeline streams
+	cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};    // pipeline streams (one per slice)
 	cudaEvent_t ev[8] = {};
 	DevBuf in, out, meta, scratch, crc;
 	void *pinned_meta = nullptr;
@@ -249,9 +250,10 @@ B2D_API int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off,
 	return inflate_dev_locked(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_crc32, d_status, flags, st);
 }
 
-// Host entry: the batch is cut into slices of members; slice k's H2D, kernels and D2H run on stream k % 3, so
-// the copy engines and the SMs overlap (PCIe is the end-to-end bound; pinned buffers from b2d_alloc_pinned make
-// the copies asynchronous).
+// Host entry.  One member decodes at a fixed, serial pace whatever the batch size, so the batch is cut into at most
+// four large slices (>= 1024 members each, enough warps to fill the GPU together), each on its own stream: the
+// slice kernels run side by side, slice k's H2D overlaps the decode of slices < k and its D2H overlaps the decode
+// of slices > k.  Pinned buffers (b2d_alloc_pinned) make the copies asynchronous; PCIe is the end-to-end bound.
 B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint8_t *out,
                               const uint64_t *out_off, uint64_t *out_len, uint64_t *in_consumed, uint32_t *crc32,
                               int32_t *status, uint32_t flags) {
@@ -281,27 +283,42 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	uint8_t *d_in = (uint8_t *)g.in.p, *d_out = (uint8_t *)g.out.p;
 	CK(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, g.st[0]));
 	CK(cudaEventRecord(g.ev[0], g.st[0]));
-	// slices: ~16 MiB of output each, at least 1 member, at most 64 slices
-	uint32_t n_slices = (uint32_t)std::min<uint64_t>(64, std::max<uint64_t>(1, out_total >> 24));
-	n_slices = std::min(n_slices, n);
+	uint32_t n_slices = std::min<uint32_t>(4, std::max<uint32_t>(1, n / 1024));
 	uint32_t per = (n + n_slices - 1) / n_slices;
 	int k = 0;
 	for (uint32_t a = 0; a < n; a += per, k++) {
 		uint32_t b = std::min(n, a + per);
-		cudaStream_t st = g.st[k % 3];
-		if (k > 0 && k < 3) CK(cudaStreamWaitEvent(st, g.ev[0], 0));
+		cudaStream_t st = g.st[k];
+		if (k > 0) CK(cudaStreamWaitEvent(st, g.ev[0], 0));
 		uint64_t ia = h_in_off[a], ib = h_in_off[b], oa = h_out_off[a], ob = h_out_off[b];
 		// (a kernel may read the aligned words around its slice while a neighbour's copy lands in them; those bytes
 		// are shifted out / masked by the bit reader, so the race is benign)
+		cudaEvent_t te[4];
+		const char *tr_ = getenv("B2D_TRACE");
+		const bool trace = tr_ != nullptr && tr_[0] == '1';
+		if (tr_ && tr_[0] == '3') cudaStreamSynchronize(st);
+		if (trace) { for (auto &e : te) cudaEventCreate(&e); cudaEventRecord(te[0], st); }
 		if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
+		if (trace) cudaEventRecord(te[1], st);
 		r = inflate_dev_locked(d_in, (const uint64_t *)(dm + m_off_in) + a, b - a, d_out,
 		                       (const uint64_t *)(dm + m_off_out) + a, (uint64_t *)(dm + m_len) + a,
 		                       (uint64_t *)(dm + m_cons) + a, (uint32_t *)(dm + m_crc) + a,
 		                       (int32_t *)(dm + m_stat) + a, flags, st);
 		if (r) return r;
+		if (trace) cudaEventRecord(te[2], st);
 		if (ob > oa) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
+		if (tr_ && tr_[0] == '2') cudaStreamSynchronize(st);
+		if (trace) {
+			cudaEventRecord(te[3], st);
+			cudaEventSynchronize(te[3]);
+			float a_ = 0, b_ = 0, c_ = 0;
+			cudaEventElapsedTime(&a_, te[0], te[1]); cudaEventElapsedTime(&b_, te[1], te[2]); cudaEventElapsedTime(&c_, te[2], te[3]);
+			fprintf(stderr, "[b2d trace] slice %d: members %u..%u h2d %.3f ms (%llu B) kernels %.3f ms d2h %.3f ms (%llu B)\n", k, a, b, a_,
+			        (unsigned long long)(ib - ia), b_, c_, (unsigned long long)(ob - oa));
+			for (auto &e : te) cudaEventDestroy(e);
+		}
 	}
-	for (int s = 1; s < 3 && s < k; s++) {
+	for (int s = 1; s < k; s++) {
 		CK(cudaEventRecord(g.ev[s], g.st[s]));
 		CK(cudaStreamWaitEvent(g.st[0], g.ev[s], 0));
 	}

@@ -27,14 +27,16 @@ constexpr int WARPS_PER_CTA = 4;
 constexpr int CTAS_PER_SM = 7;            // 28 resident warps per SM: 4096 members fit one wave on 148 SMs
 constexpr int TILE = 1024;                // bytes of output staged per warp in shared memory
 
-// LUT entry: [4:0] total bits (code + extra)  [8:5] code length  [12:9] extra-bit count
-//            [31:27] flags (lit/len)  or bit 31 (distance)        [26:16] / [30:16] value
-constexpr u32 F_LIT = 1u << 27;
-constexpr u32 F_LEN = 1u << 28;
-constexpr u32 F_EOB = 1u << 29;
-constexpr u32 F_LONG = 1u << 30;          // code longer than the LUT index: canonical slow path
-constexpr u32 F_RSVD = 1u << 31;          // lit/len symbols 286/287
-constexpr u32 FD_SPECIAL = 1u << 31;      // distance: value 0 = long code, else reserved symbol 30/31
+// LUT entry (lit/len and distance): [4:0] total bits (code + extra)   [7:5] kind flags   [12:8] code length
+//                                   [31:16] value (literal byte, length base, distance base, or sub-kind)
+// The shift counts sit where a wrap-mode funnel shift can take them straight from the entry.
+constexpr u32 K_LIT = 1u << 5;            // lit/len: literal
+constexpr u32 K_LEN = 1u << 6;            // lit/len: length symbol 257..285
+constexpr u32 K_OTHER = 1u << 7;          // lit/len: value 0 = end of block, 1 = code longer than the LUT index,
+                                          //          286/287 = reserved length symbol (Open.java:513-517)
+constexpr u32 KD_SPECIAL = 1u << 7;       // distance: value 0 = long code, 30/31 = reserved symbol (Open.java:546-551),
+                                          //           0xFFFF = the block has no distance code (Open.java:398-401)
+constexpr u32 V_EOB = 0, V_LONG = 1, V_NODIST = 0xFFFF;
 
 __constant__ u8 CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
@@ -47,6 +49,7 @@ struct Canon {                            // canonical-code description for the 
 
 struct __align__(16) WarpSmem {
 	u8 tile[TILE];                        // output staging: tile[i] <-> global byte tile_g[i]
+	uint2 mq[32];                         // pending back-references: x = tile offset | length << 16, y = distance
 	u32 ll_lut[1 << LL_TB];
 	u32 d_lut[1 << D_TB];
 	Canon ll_canon, d_canon;
@@ -111,18 +114,24 @@ __device__ __forceinline__ int getbits(BitIn &b, int n, int &avail, int &err) {
 }
 
 __device__ __forceinline__ u32 ll_entry(int sym, int l) {
-	if (sym < 256) return F_LIT | (u32)sym << 16 | (u32)l << 5 | (u32)l;
-	if (sym == 256) return F_EOB | (u32)l << 5 | (u32)l;
-	if (sym > 285) return F_RSVD | (u32)sym << 16 | (u32)l << 5 | (u32)l;      // Open.java:513-517
+	if (sym < 256) return K_LIT | (u32)sym << 16 | (u32)l << 8 | (u32)l;
+	if (sym == 256) return K_OTHER | V_EOB << 16 | (u32)l << 8 | (u32)l;
+	if (sym > 285) return K_OTHER | (u32)sym << 16 | (u32)l << 8 | (u32)l;
 	int base, eb;
 	length_sym_info(sym, base, eb);
-	return F_LEN | (u32)base << 16 | (u32)eb << 9 | (u32)l << 5 | (u32)(l + eb);
+	return K_LEN | (u32)base << 16 | (u32)l << 8 | (u32)(l + eb);
 }
 __device__ __forceinline__ u32 d_entry(int sym, int l) {
-	if (sym > 29) return FD_SPECIAL | (u32)sym << 16 | (u32)l << 5 | (u32)l;    // Open.java:546-551
+	if (sym > 29) return KD_SPECIAL | (u32)sym << 16 | (u32)l << 8 | (u32)l;
 	int base, eb;
 	dist_sym_info(sym, base, eb);
-	return (u32)base << 16 | (u32)eb << 9 | (u32)l << 5 | (u32)(l + eb);
+	return (u32)base << 16 | (u32)l << 8 | (u32)(l + eb);
+}
+// value + extra bits of a length / distance entry: extra = (lo & ((1 << tot) - 1)) >> clen, with both shift counts
+// read by wrap-mode funnel shifts from the entry itself
+__device__ __forceinline__ u32 entry_value(u32 e, u32 lo) {
+	u32 x = lo & ~__funnelshift_l(0u, 0xFFFFFFFFu, e);
+	return (e >> 16) + __funnelshift_r(x, 0u, e >> 8);
 }
 
 // Builds LUT + canonical description for n code lengths in smem.  All 32 lanes participate.
@@ -173,7 +182,7 @@ __device__ int build_code(const u8 *lens, int n, u32 *lut, u16 *sorted, Canon *c
 				u32 e = IS_DIST ? d_entry(i, l) : ll_entry(i, l);
 				for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = e;
 			} else {
-				lut[rev & ((1u << TB) - 1)] = IS_DIST ? FD_SPECIAL : F_LONG;
+				lut[rev & ((1u << TB) - 1)] = IS_DIST ? KD_SPECIAL : (K_OTHER | V_LONG << 16);
 			}
 		}
 	}
@@ -193,15 +202,15 @@ __device__ __noinline__ u32 slow_decode(u32 lo, const Canon *cn, const u16 *sort
 			return IS_DIST ? d_entry(sym, l) : ll_entry(sym, l);
 		}
 	}
-	return IS_DIST ? (FD_SPECIAL | 31u << 16 | 15u << 5 | 15u) : (F_RSVD | 15u << 5 | 15u);   // unreachable for complete codes
+	return IS_DIST ? (KD_SPECIAL | 31u << 16 | 15u << 8 | 15u) : (K_OTHER | 287u << 16 | 15u << 8 | 15u);   // unreachable for complete codes
 }
 
 // Per-member decoder state.  Output goes through a TILE-byte staging tile in shared memory: tile[i] holds the
 // byte of global address tile_g[i] (tile_g is 16-byte aligned), indices [tstart, tpos) are valid and not yet
-// flushed.  Literals are stored into the tile as they are decoded; back-references are only RECORDED (lane k of
-// the warp keeps the k-th pending one in registers) and resolved 32 at a time by resolve(), so the loads of
-// all references whose source is already in global memory are in flight together instead of one L2 round
-// trip per match, and references into the tile itself are served from shared memory.
+// flushed.  Literals are stored into the tile as they are decoded; back-references are only QUEUED (mq[], up to
+// 32) and resolved together by resolve_pending(), so the loads of all references whose source is already in
+// global memory are in flight together instead of one L2 round trip per match, and references into the tile
+// itself are served from shared memory.
 struct Member {
 	BitIn in;
 	u8 *out;
@@ -209,9 +218,7 @@ struct Member {
 	u8 *tile_g;          // global address of tile[0]
 	u32 tstart, tpos, tlimit;
 	int pos_base;        // min(tile_g - out, 1 << 20): output position of tile[0] for the dictionary-start check
-	u32 nm;              // pending back-references (warp-uniform)
-	u32 pa, pb;          // this lane's pending reference: pa = tile offset | length << 16, pb = distance
-	bool no_dist;        // dynamic block with an empty distance code (Open.java:398-401)
+	u32 nm;              // queued back-references (warp-uniform)
 	int tables;          // 0 none, 1 fixed tables resident
 };
 
@@ -230,13 +237,15 @@ __device__ __forceinline__ void set_tile_origin(Member &m, u64 pos) {
 	m.pos_base = rel0 > (1 << 20) ? (1 << 20) : (int)rel0;
 }
 
-// Materialises the pending back-references into the tile.  Copies replicate the pattern when dist < len exactly
+// Materialises the queued back-references into the tile.  Copies replicate the pattern when dist < len exactly
 // like the reference's byte-serial loop (Open.java:596-603): byte k comes from position pos - dist + (k mod dist).
 // (All state by value: a by-reference Member would be forced into local memory by the call.)
-__device__ __noinline__ void resolve_pending(u8 *tile, u8 *tile_g, int ts, u32 nm, u32 pa, u32 pb, u32 lane) {
-	__syncwarp();                                   // literal stores of lane 0 are visible
+__device__ __noinline__ void resolve_pending(WarpSmem *sm, u8 *tile_g, int ts, u32 nm, u32 lane) {
+	u8 *tile = sm->tile;
+	__syncwarp();                                   // literal and queue stores of lane 0 are visible
 	const bool have = lane < nm;
-	const int off = (int)(pa & 0xFFFFu), len = (int)(pa >> 16), dist = (int)pb;
+	const uint2 q = sm->mq[lane];
+	const int off = (int)(q.x & 0xFFFFu), len = (int)(q.x >> 16), dist = (int)q.y;
 	const int s = off - dist;                        // tile index of the source start (may be negative)
 	const bool far = have && (s + len <= ts);        // source lies wholly in global memory (already flushed)
 	// (1) far, short: each lane gathers its own reference, 8 bytes per round, all loads issued before the stores
@@ -290,7 +299,7 @@ __device__ __noinline__ void resolve_pending(u8 *tile, u8 *tile_g, int ts, u32 n
 }
 
 __device__ __forceinline__ void resolve(Member &m, WarpSmem *sm, u32 lane) {
-	resolve_pending(sm->tile, m.tile_g, (int)m.tstart, m.nm, m.pa, m.pb, lane);
+	resolve_pending(sm, m.tile_g, (int)m.tstart, m.nm, lane);
 	m.nm = 0;
 }
 
@@ -308,101 +317,129 @@ __device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u
 	__syncwarp();
 }
 
-// Resolves what is pending, writes the staged bytes out and re-bases the tile at the current output position.
+// Resolves what is queued, writes the staged bytes out and re-bases the tile at the current output position.
 __device__ __forceinline__ void flush_tile(Member &m, WarpSmem *sm, u32 lane) {
 	if (m.nm) resolve(m, sm, lane);
 	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane);
 	set_tile_origin(m, out_pos(m));
 }
 
-// Makes room for at least one more byte; B2D_ERR_OUTPUT_OVERFLOW when the member's slot is full.
-__device__ __forceinline__ int make_room(Member &m, WarpSmem *sm, u32 lane) {
-	flush_tile(m, sm, lane);
-	return m.tpos >= m.tlimit ? B2D_ERR_OUTPUT_OVERFLOW : 0;
-}
-
-// Decodes symbols of one Huffman block until end-of-block.  CAREFUL=false requires that the three words
-// (cur, nxt, pre) hold only real input at the top of every iteration, so no read can pass the end of input and
-// the end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the
-// reference's order (Open.java:565-593).
+// Decodes symbols of one Huffman block until end-of-block.  The hot state lives in locals; the Member is only
+// synchronised around the rare calls (tile flush, queue resolve) and at exit.
+// CAREFUL=false requires that the three words (cur, nxt, pre) hold only real input at the top of every iteration
+// (a whole symbol is at most 48 bits, read from bit offset <= 31), so no read can pass the end of input and the
+// end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the reference's
+// order (Open.java:565-593).
 template <bool CAREFUL>
-__device__ int decode_block(Member &m, WarpSmem *sm, u32 lane) {
+__device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 lane) {
 	BitIn &b = m.in;
+	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;
+	u32 tpos = m.tpos, tlimit = m.tlimit, nm = m.nm;
+	int pos_base = m.pos_base;
 	int avail = CAREFUL ? avail_bits(b) : 0;
-#ifdef B2D_DEBUG
-	if (lane == 0) printf("decode_block<%d> enter widx=%u sh=%u n_full=%u n_safe=%u avail=%d tpos=%u\n", (int)CAREFUL, b.widx, b.sh, b.n_full, b.n_safe, avail, m.tpos);
-#endif
 	const u32 fast_last = b.n_full - 3;              // FAST is only entered with n_full >= 3
+	const u32 n_safe = b.n_safe;
+	const u32 *const words = b.words;
+	const u32 *const ll = sm->ll_lut;
+	const u32 *const dl = sm->d_lut;
+	u8 *const tile = sm->tile;
+	int ret;
+#define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = widx; b.sh = sh; m.tpos = tpos; m.nm = nm; } while (0)
+#define LOAD_TILE() do { tpos = m.tpos; tlimit = m.tlimit; nm = m.nm; pos_base = m.pos_base; } while (0)
 	for (;;) {
-		if (b.sh >= 32) advance(b);
-		if (!CAREFUL && b.widx > fast_last) return R_SWITCH;     // (the mid-symbol norm() below may have advanced too)
-		u32 lo = peek(b);
-		u32 e = sm->ll_lut[lo & ((1u << LL_TB) - 1)];
-		if (e & F_LONG) e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted);
-		if (e & F_LIT) {
-			const int clen = e & 31;
-#ifdef B2D_DEBUG
-			if (lane == 0 && b.widx + 4 > b.n_full) printf(" lit widx=%u sh=%u clen=%d avail=%d byte=%02x\n", b.widx, b.sh, clen, avail, (e >> 16) & 255);
-#endif
-			if (CAREFUL && clen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-			if (m.tpos >= m.tlimit) { int r = make_room(m, sm, lane); if (r) return r; }
-			if (lane == 0) sm->tile[m.tpos] = (u8)(e >> 16);
-			m.tpos++;
-			b.sh += clen;
-			if (CAREFUL) avail -= clen;
+		if (sh >= 32) {
+			sh -= 32; cur = nxt; nxt = pre; widx++;
+			pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
+			if (sh >= 32) {                                  // a long symbol crossed two words (rare)
+				sh -= 32; cur = nxt; nxt = pre; widx++;
+				pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
+			}
+			if (!CAREFUL && widx > fast_last) { ret = R_SWITCH; break; }
+		}
+		const u32 lo = __funnelshift_r(cur, nxt, sh);
+		u32 e = ll[lo & ((1u << LL_TB) - 1)];
+	dispatch:
+		if (e & K_LIT) {
+			if (CAREFUL && (int)(e & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if (tpos >= tlimit) {
+				SAVE_STATE();
+				flush_tile(m, sm, lane);
+				LOAD_TILE();
+				if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
+			}
+			if (lane == 0) tile[tpos] = (u8)(e >> 16);
+			tpos++;
+			sh += e & 31;
+			if (CAREFUL) avail -= e & 31;
 			continue;
 		}
-		const int clen = (e >> 5) & 15;
-		if (CAREFUL && clen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		if (e & F_EOB) {
-			b.sh += clen;
-			return R_EOB;
+		if (!(e & K_LEN)) {                                  // rare kinds
+			const u32 v = e >> 16;
+			if (v == V_LONG) { e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted); goto dispatch; }
+			if (CAREFUL && (int)((e >> 8) & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if (v == V_EOB) { sh += e & 31; ret = R_EOB; break; }
+			ret = B2D_RESERVED_LENGTH_SYMBOL;
+			break;
 		}
-		if (e & F_RSVD) return B2D_RESERVED_LENGTH_SYMBOL;
-		const int tot = e & 31;
-#ifdef B2D_DEBUG
-		if (lane == 0 && b.widx + 4 > b.n_full) printf(" len widx=%u sh=%u clen=%d tot=%d avail=%d\n", b.widx, b.sh, clen, tot, avail);
-#endif
-		if (CAREFUL && tot > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		int len = (int)((e >> 16) & 0x7FF) + (int)bfe(lo, clen, (e >> 9) & 15);
-		b.sh += tot;
-		if (CAREFUL) avail -= tot;
-		if (m.no_dist) return B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE;
-		norm(b);
-		lo = peek(b);
-		u32 d = sm->d_lut[lo & ((1u << D_TB) - 1)];
-		if (d & FD_SPECIAL) {
-			if (((d >> 16) & 0x7FFF) == 0) d = slow_decode<D_TB, true>(lo, &sm->d_canon, sm->d_sorted);
+		if (CAREFUL) {
+			if ((int)((e >> 8) & 31) > avail || (int)(e & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			avail -= e & 31;
 		}
-		const int dclen = (d >> 5) & 15;
-		if (CAREFUL && dclen > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		if (d & FD_SPECIAL) return B2D_RESERVED_DISTANCE_SYMBOL;
-		const int dtot = d & 31;
-#ifdef B2D_DEBUG
-		if (lane == 0 && b.widx + 4 > b.n_full) printf(" dist widx=%u sh=%u dclen=%d dtot=%d avail=%d len=%d\n", b.widx, b.sh, dclen, dtot, avail, len);
-#endif
-		if (CAREFUL && dtot > avail) return B2D_UNEXPECTED_END_OF_STREAM;
-		const int dist = (int)(d >> 16) + (int)bfe(lo, dclen, (d >> 9) & 15);
-		b.sh += dtot;
-		if (CAREFUL) avail -= dtot;
-		if (dist > m.pos_base + (int)m.tpos) return B2D_COPY_FROM_BEFORE_DICTIONARY_START;     // Open.java:592-593
-		// record the reference; a reference that does not fit the tile is split (same distance), and when the
-		// member's slot is full what fits is still delivered (Open.java:604-616) before the overflow is reported
-		for (;;) {
-			const u32 fit = m.tlimit - m.tpos;
-			const u32 take = (u32)len < fit ? (u32)len : fit;
-			if (take) {
-				if (lane == m.nm) { m.pa = m.tpos | take << 16; m.pb = (u32)dist; }
-				m.nm++;
-				m.tpos += take;
-				len -= (int)take;
-				if (m.nm == 32) resolve(m, sm, lane);
+		u32 len = entry_value(e, lo);
+		sh += e & 31;                                        // <= 51: the distance may start in nxt
+		const u32 lo2 = (sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh);
+		u32 d = dl[lo2 & ((1u << D_TB) - 1)];
+	dispatch_d:
+		if (d & KD_SPECIAL) {
+			const u32 v = d >> 16;
+			if (v == V_NODIST) { ret = B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE; break; }
+			if (v == 0) { d = slow_decode<D_TB, true>(lo2, &sm->d_canon, sm->d_sorted); goto dispatch_d; }
+			if (CAREFUL && (int)((d >> 8) & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			ret = B2D_RESERVED_DISTANCE_SYMBOL;
+			break;
+		}
+		if (CAREFUL) {
+			if ((int)((d >> 8) & 31) > avail || (int)(d & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			avail -= d & 31;
+		}
+		const u32 dist = entry_value(d, lo2);
+		sh += d & 31;
+		if ((int)dist > pos_base + (int)tpos) { ret = B2D_COPY_FROM_BEFORE_DICTIONARY_START; break; }   // Open.java:592-593
+		if (tpos + len <= tlimit) {                          // common case: the whole reference fits the tile
+			if (lane == 0) sm->mq[nm] = make_uint2(tpos | len << 16, dist);
+			tpos += len;
+			if (++nm == 32) {
+				SAVE_STATE();
+				resolve(m, sm, lane);
+				nm = 0;
 			}
-			if (len == 0) break;
-			int r = make_room(m, sm, lane);
-			if (r) return r;
+			continue;
 		}
+		// A reference that does not fit the tile is split (same distance); when the member's slot is full, what
+		// fits is still delivered (Open.java:604-616) before the overflow is reported.
+		ret = 0;
+		for (;;) {
+			const u32 fit = tlimit - tpos;
+			const u32 take = len < fit ? len : fit;
+			if (take) {
+				if (lane == 0) sm->mq[nm] = make_uint2(tpos | take << 16, dist);
+				nm++;
+				tpos += take;
+				len -= take;
+			}
+			if (len == 0 && nm < 32) break;
+			SAVE_STATE();
+			if (len == 0) { resolve(m, sm, lane); nm = 0; break; }
+			flush_tile(m, sm, lane);
+			LOAD_TILE();
+			if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
+		}
+		if (ret) break;
 	}
+	SAVE_STATE();
+#undef SAVE_STATE
+#undef LOAD_TILE
+	return ret;
 }
 
 // Open.UncompressedBlock (Open.java:227-306)
@@ -531,9 +568,10 @@ __device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 	if (e) return e;
 	// distance code special cases (:396-428)
 	u8 *dl = sm->lens + num_ll;
-	m.no_dist = false;
 	if (num_d == 1 && dl[0] == 0) {
-		m.no_dist = true;
+		// no distance code: any length symbol is an error (:526-527,578-579), reported by the distance lookup
+		for (int i = lane; i < (1 << D_TB); i += 32) sm->d_lut[i] = KD_SPECIAL | V_NODIST << 16;
+		__syncwarp();
 	} else {
 		int v = (int)lane < num_d ? dl[lane] : 0;
 		u32 ones = __popc(__ballot_sync(FULL_MASK, v == 1));
@@ -559,7 +597,6 @@ __device__ void fixed_tables(Member &m, WarpSmem *sm, u32 lane) {
 	__syncwarp();
 	build_code<LL_TB, false>(sm->lens, 288, sm->ll_lut, sm->ll_sorted, &sm->ll_canon, lane);
 	build_code<D_TB, true>(sm->lens + 288, 32, sm->d_lut, sm->d_sorted, &sm->d_canon, lane);
-	m.no_dist = false;
 	m.tables = 1;
 }
 
@@ -588,9 +625,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	m.out = out + o0;
 	m.cap = o1 - o0;
 	m.nm = 0;
-	m.pa = m.pb = 0;
 	set_tile_origin(m, 0);
-	m.no_dist = false;
 	m.tables = 0;
 
 	int err = 0;
