@@ -115,7 +115,7 @@ int normalise_opts(const b2d_deflate_opts *o, uint64_t in_len, DeflateParams &p)
 	if (p.mode < B2D_MODE_AUTO || p.mode > B2D_MODE_DYNAMIC) return B2D_ERR_BAD_ARGUMENT;
 	p.search = d.search;
 	if (p.search < B2D_SEARCH_DEFAULT || p.search > B2D_SEARCH_FULL) return B2D_ERR_BAD_ARGUMENT;
-	p.depth = d.chain_depth > 0 ? d.chain_depth : 8;
+	p.depth = d.chain_depth > 0 ? d.chain_depth : 4;
 	p.lazy = d.lazy < 0 ? 1 : (d.lazy ? 1 : 0);
 	if (p.search != B2D_SEARCH_DEFAULT) p.lazy = d.lazy > 0 ? 1 : 0;     // the reference strategies are greedy
 	p.is_last = d.is_last ? 1 : 0;

@@ -25,7 +25,7 @@
 
 namespace b2d {
 
-constexpr int HASH_BITS = 15;
+constexpr int HASH_BITS = 14;                // 32 KiB head table per warp: 7 chain warps per SM
 constexpr u32 WINDOW = 32768;
 constexpr int MAX_MATCH = 258;
 constexpr u32 TILE = 32768;                 // positions per match CTA
@@ -93,41 +93,69 @@ __device__ __forceinline__ u32 warp_sum(u32 v) {
 }
 
 // ---------------------------------------------------------------- K1a: hash chains
+// One warp per segment of the input (SEG bytes, never crossing a chunk).  The warp first re-inserts up to 32 KiB
+// before its segment so the head table is what a sequential insert would have left, then links every position of
+// the segment.  32 positions per step: match.any finds equal hashes inside the step, the shared head table (low 16
+// bits of the chunk-relative position per hash) gives the link to earlier steps.  Input words for step i + 2 are
+// requested while step i is processed, so the global-load latency is off the serial chain.
+constexpr u32 CHAIN_SEG = 256u << 10;
+
 __global__ void __launch_bounds__(32)
-chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, int hb, u16 *__restrict__ prevdist) {
-	extern __shared__ __align__(16) u16 head[];      // 1 << HASH_BITS entries: low 16 bits of the chunk-relative position
+chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 seg_bytes, int hb, u16 *__restrict__ prevdist) {
+	extern __shared__ __align__(16) u16 head[];      // 1 << HASH_BITS entries
 	const u32 lane = threadIdx.x;
-	const u64 bs = (u64)blockIdx.x * block_bytes;
-	const u64 be = min(n, bs + block_bytes);
-	const u64 cs = bs / chunk_bytes * chunk_bytes;
+	const u32 segs_per_chunk = (chunk_bytes + seg_bytes - 1) / seg_bytes;
+	const u64 cs = (u64)(blockIdx.x / segs_per_chunk) * chunk_bytes;
+	const u64 ss = cs + (u64)(blockIdx.x % segs_per_chunk) * seg_bytes;
 	const u64 ce = min(n, cs + chunk_bytes);
-	const u64 ws = (bs - cs > WINDOW) ? bs - WINDOW : cs;       // re-insert up to 32 KiB before the block
-	const u64 n_words = (n + 3) >> 2;
+	if (ss >= ce) return;
+	const u64 se = min(ce, ss + seg_bytes);
+	const u64 ws = (ss - cs > WINDOW) ? ss - WINDOW : cs;       // warm-up start
 	for (u32 i = lane; i < (2u << HASH_BITS) / 16; i += 32) ((uint4 *)head)[i] = make_uint4(0, 0, 0, 0);
 	__syncwarp();
+	// everything below in 32-bit offsets from `org` (4-byte aligned, <= ws)
+	const u64 org = ws & ~(u64)3;
+	const u32 *__restrict__ words = (const u32 *)(in + org);
+	const u32 n_words = (u32)min((u64)0x7FFFFFFF, ((n - org) + 3) >> 2);
+	const u32 o_ws = (u32)(ws - org), o_ss = (u32)(ss - org), o_se = (u32)(se - org);
+	const u32 o_ce = (u32)min((u64)0x7FFFFFFF, ce - org);      // (clamped: only compared against offsets of this segment)
+	const u32 rel0 = (u32)(org - cs);                            // chunk-relative position of offset 0
 	const u32 ws_rel = (u32)(ws - cs);
-	for (u64 base = ws; base < be; base += 32) {
-		const u64 p = base + lane;
-		const bool valid = p < be && p + hb <= ce;
-		u32 v = valid ? load4_global(in, p, n_words) : 0u;
-		const u32 h = hash4(v, hb);
-		const u32 grp = __match_any_sync(FULL_MASK, valid ? h : (0x80000000u | lane));
-		const u32 lower = grp & lanemask_lt();
-		const u32 prel = (u32)(p - cs);
+	u16 *__restrict__ pd = prevdist + org;
+	const u32 cmask = hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
+#define LOADW(i) ((i) < n_words ? __ldg(words + (i)) : 0u)
+	u32 o = o_ws + lane;
+	u32 a0 = LOADW(o >> 2), a1 = LOADW((o >> 2) + 1);
+	u32 b0 = LOADW((o + 32) >> 2), b1 = LOADW(((o + 32) >> 2) + 1);
+	for (u32 base = o_ws; base < o_se; base += 32) {
+		o = base + lane;
+		const u32 c0 = LOADW((o + 64) >> 2), c1 = LOADW(((o + 64) >> 2) + 1);    // for step + 2
+		const bool valid = o < o_se && o + (u32)hb <= o_ce;
+		const u32 v = __funnelshift_r(a0, a1, (o & 3) * 8) & cmask;
+		const u32 h = (v * 2654435761u) >> (32 - HASH_BITS);
+		const u32 prel = rel0 + o;
 		u32 dist = 0;
-		if (valid) {
-			if (lower) dist = lane - (31 - __clz(lower));       // same hash earlier in this group of 32
-			else {
-				u32 d = (prel - head[h]) & 0xFFFFu;
-				if (d == 0) d = 65536;
-				if (d <= WINDOW && d <= prel - ws_rel) dist = d;
-			}
+		if (valid) {                                            // link to the newest position of earlier steps
+			u32 d = (prel - head[h]) & 0xFFFFu;
+			if (d == 0) d = 65536;
+			if (d <= WINDOW && d <= prel - ws_rel) dist = d;
 		}
 		__syncwarp();
-		if (valid && (grp >> lane) == 1u) head[h] = (u16)prel;    // highest lane of the group
+		if (valid) head[h] = (u16)prel;                         // equal hashes in this step: one of them wins ...
 		__syncwarp();
-		if (p >= bs && p < be) prevdist[p] = (u16)dist;
+		const bool lost = valid && head[h] != (u16)prel;
+		if (__any_sync(FULL_MASK, lost)) {                      // ... then (rare) sort the step out exactly
+			const u32 grp = __match_any_sync(FULL_MASK, valid ? h : (0x80000000u | lane));
+			const u32 lower = grp & lanemask_lt();
+			if (valid && lower) dist = lane - (31 - __clz(lower));    // same hash earlier in this step
+			__syncwarp();
+			if (valid && (grp >> lane) == 1u) head[h] = (u16)prel;    // the highest lane of each group stays
+			__syncwarp();
+		}
+		if (o >= o_ss && o < o_se) pd[o] = (u16)dist;
+		a0 = b0; a1 = b1; b0 = c0; b1 = c1;
 	}
+#undef LOADW
 }
 
 // ---------------------------------------------------------------- K1b: match search
@@ -239,42 +267,55 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 	for (int i = lane; i < 320; i += 32) hist[i] = 0;
 	__syncwarp();
 	const u64 bs = (u64)g * block_bytes, be = min(n, bs + block_bytes);
+	u32 *__restrict__ tk = tokens + bs;
 	u64 i = bs;
 	u64 base = bs & ~(u64)31;
-	u32 w0 = base + lane < n ? match[base + lane] : 0u;
-	u32 w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
-	u32 ntok = 0, my_tok = 0;
+#define LOADM(k) (base + (k) * 32 + lane < n ? __ldg(match + base + (k) * 32 + lane) : 0u)
+	u32 w0 = LOADM(0), w1 = LOADM(1), w2 = LOADM(2), w3 = LOADM(3);    // four windows of 32 positions in flight
+	u32 lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);             // positions of window 0 without a match
+	u32 ntok = 0;
 	while (i < be) {
 		u32 o = (u32)(i - base);
-		if (o >= 64) {
-			base = i & ~(u64)31;
-			w0 = base + lane < n ? match[base + lane] : 0u;
-			w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
+		if (o >= 32) {
+			if (o >= 128) {                                // a long match jumped past everything loaded
+				base = i & ~(u64)31;
+				w0 = LOADM(0); w1 = LOADM(1); w2 = LOADM(2); w3 = LOADM(3);
+			} else {
+				do {
+					base += 32;
+					w0 = w1; w1 = w2; w2 = w3;
+					w3 = LOADM(3);
+				} while (i - base >= 32);
+			}
 			o = (u32)(i - base);
-		} else if (o >= 32) {
-			base += 32;
-			w0 = w1;
-			w1 = base + 32 + lane < n ? match[base + 32 + lane] : 0u;
-			o -= 32;
+			lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);
 		}
-		u32 e = __shfl_sync(FULL_MASK, w0, o);
+		// a run of positions without a match becomes that many literal tokens in one step
+		u32 run = __ffs(~(lit0 >> o)) - 1;                 // ones from bit o upwards (lit0 >> o has zeros on top)
+		if (run > 32 - o) run = 32 - o;
+		if ((u64)run > be - i) run = (u32)(be - i);
+		if (run) {
+			if (lane >= o && lane < o + run) {
+				tk[ntok + lane - o] = w0 & 0xFF000000u;
+				atomicAdd(&hist[w0 >> 24], 1u);
+			}
+			ntok += run;
+			i += run;
+			continue;
+		}
+		const u32 e = __shfl_sync(FULL_MASK, w0, o);
 		u32 len = tok_len(e);
-		if (lazy && len) {                                 // defer when the next position matches longer
-			u32 e1 = __shfl_sync(FULL_MASK, o < 31 ? w0 : w1, (o + 1) & 31);
+		if (lazy) {                                        // defer when the next position matches longer
+			const u32 e1 = __shfl_sync(FULL_MASK, o < 31 ? w0 : w1, (o + 1) & 31);
 			if (i + 1 < be && tok_len(e1) > len) len = 0;
 		}
-		u32 tok = len ? e : (e & 0xFF000000u);
-		if (lane == (ntok & 31)) my_tok = tok;
-		ntok++;
-		if ((ntok & 31) == 0) {
-			tokens[bs + ntok - 32 + lane] = my_tok;
-			hist_token(hist, my_tok);
+		if (lane == 0) {
+			const u32 tok = len ? e : (e & 0xFF000000u);
+			tk[ntok] = tok;
+			hist_token(hist, tok);
 		}
+		ntok++;
 		i += len ? len : 1;
-	}
-	if (lane < (ntok & 31)) {
-		tokens[bs + (ntok & ~31u) + lane] = my_tok;
-		hist_token(hist, my_tok);
 	}
 	__syncwarp();
 	if (lane == 0) { hist[256] += 1; recs[g].n_tokens = ntok; }   // end-of-block (Lz77Huffman.java:131-132)
@@ -282,6 +323,7 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 	for (int k = lane; k < 288; k += 32) recs[g].hist_ll[k] = hist[k];
 	recs[g].hist_d[lane] = hist[288 + lane];
 }
+#undef LOADM
 
 // ---------------------------------------------------------------- K3: Huffman construction
 constexpr int HUFF_WARPS = 2;
@@ -842,8 +884,10 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	mp.depth = p.search == 3 ? 0x7FFFFFFF : p.depth;
 	mp.nice = MAX_MATCH;
 	if (need_search) {
-		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3))
-			chains_kernel<<<n_blocks, 32, 2 << HASH_BITS, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, mp.hb, prevdist);
+		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3)) {
+			const u32 n_segs = n_chunks * ((p.chunk_bytes + CHAIN_SEG - 1) / CHAIN_SEG);
+			chains_kernel<<<n_segs, 32, 2 << HASH_BITS, st>>>(d_in, n, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist);
+		}
 		const u32 n_tiles = (u32)((n + TILE - 1) / TILE);
 		if (n_tiles) match_kernel<<<n_tiles, MATCH_THREADS, MATCH_SMEM, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, mp, prevdist, match);
 		parse_kernel<<<(n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st>>>(

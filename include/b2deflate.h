@@ -135,7 +135,7 @@ typedef struct b2d_deflate_opts {
 	                           DeflaterOutputStream.java:50-52); 0 = 64 KiB; must divide chunk_bytes */
 	int32_t mode;           /* B2D_MODE_* */
 	int32_t search;         /* B2D_SEARCH_* */
-	int32_t chain_depth;    /* candidates examined per position; 0 = default (8) */
+	int32_t chain_depth;    /* candidates examined per position; 0 = default (4) */
 	int32_t lazy;           /* -1 = default (on), 0 = greedy, 1 = lazy */
 	int32_t is_last;        /* 1: the stream ends after this call (final block emitted) */
 	int32_t framing;        /* B2D_FRAMING_* */
