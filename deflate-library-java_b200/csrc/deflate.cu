@@ -273,7 +273,7 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 #define LOADM(k) (base + (k) * 32 + lane < n ? __ldg(match + base + (k) * 32 + lane) : 0u)
 	u32 w0 = LOADM(0), w1 = LOADM(1), w2 = LOADM(2), w3 = LOADM(3);    // four windows of 32 positions in flight
 	u32 lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);             // positions of window 0 without a match
-	u32 ntok = 0;
+	u32 ntok = 0, nbuf = 0, my_tok = 0, my_idx = 0;
 	while (i < be) {
 		u32 o = (u32)(i - base);
 		if (o >= 32) {
@@ -309,13 +309,19 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 			const u32 e1 = __shfl_sync(FULL_MASK, o < 31 ? w0 : w1, (o + 1) & 31);
 			if (i + 1 < be && tok_len(e1) > len) len = 0;
 		}
-		if (lane == 0) {
-			const u32 tok = len ? e : (e & 0xFF000000u);
-			tk[ntok] = tok;
-			hist_token(hist, tok);
-		}
+		// single tokens are parked one per lane and written / counted 32 at a time by all lanes
+		if (lane == nbuf) { my_tok = len ? e : (e & 0xFF000000u); my_idx = ntok; }
 		ntok++;
 		i += len ? len : 1;
+		if (++nbuf == 32) {
+			tk[my_idx] = my_tok;
+			hist_token(hist, my_tok);
+			nbuf = 0;
+		}
+	}
+	if (lane < nbuf) {
+		tk[my_idx] = my_tok;
+		hist_token(hist, my_tok);
 	}
 	__syncwarp();
 	if (lane == 0) { hist[256] += 1; recs[g].n_tokens = ntok; }   // end-of-block (Lz77Huffman.java:131-132)
