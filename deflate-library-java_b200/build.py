@@ -50,9 +50,25 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libb2deflate build failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL",
+                                                       "-Wno-deprecated-gpu-targets"]
         subprocess.check_call(cmd)
+    build_host(force)
     return OUT
+
+
+def build_host(force=False):
+    """The host-side mirror of the reference's CLIs (host/gzip.cpp, host/gunzip.cpp) -> bin/gzip, bin/gunzip."""
+    host = os.path.join(HERE, "host")
+    bindir = os.path.join(HERE, "bin")
+    os.makedirs(bindir, exist_ok=True)
+    deps = [os.path.join(host, "b2d_streams.hpp"), os.path.join(HERE, "..", "include", "b2deflate.h"), OUT]
+    for name in ("gzip", "gunzip"):
+        src = os.path.join(host, name + ".cpp")
+        exe = os.path.join(bindir, name)
+        if force or _stale(exe, [src] + deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, src, "-L" + HERE, "-lb2deflate",
+                                   "-Wl,-rpath,$ORIGIN/.."])
 
 
 if __name__ == "__main__":

@@ -77,3 +77,17 @@ def test_no_cpu_fallback(b2d_nogpu):
     assert r == b2d_nogpu.ERR_NO_DEVICE
     with pytest.raises(b2d_nogpu.B2dError):
         b2d_nogpu.init(0)
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
+def test_cli_fails_loudly_without_gpu(tmp_path):
+    import subprocess
+    exe = os.path.join(ROOT, "deflate-library-java_b200", "bin", "gzip")
+    if not os.path.exists(exe):
+        pytest.skip("host CLIs not built")
+    src = tmp_path / "a.txt"
+    src.write_bytes(b"hello")
+    r = subprocess.run([exe, str(src), str(tmp_path / "a.gz")], capture_output=True, text=True)
+    assert r.returncode == 1 and "No usable sm_100 GPU" in r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and r.stderr.startswith("Usage:")
