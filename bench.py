@@ -446,30 +446,22 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
     total_in = sum_over_ranks(float(n_bytes))
     value = total_in / step_s / 1e9
 
-    # multi-GPU gather of the compressed stream onto GPU 0 (sizes by all_gather, payloads by NCCL send/recv)
+    # multi-GPU: the one exchange step of the path -- chunk sizes all-gathered, payloads sent to GPU 0 (NCCL over NVLink)
     gather_ms = None
     if world > 1:
-        sizes = torch.zeros(world, dtype=torch.int64, device=dev)
-        barrier()
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record(stream)
-        dist.all_gather_into_tensor(sizes, d_total)
-        szs = sizes.cpu().tolist()
+        from importlib import import_module
+        sharding = import_module("b2deflate.sharding")
+        for _ in range(2):                                   # warm-up (NCCL connection set-up), then timed
+            barrier()
+            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            g0.record(stream)
+            whole, all_sizes = sharding.gather_stream(d_out[:comp_len], d_clen)
+            g1.record(stream)
+            barrier()
+            gather_ms = max_over_ranks(g0.elapsed_time(g1))
         if rank == 0:
-            whole = torch.empty(int(sum(szs)), dtype=torch.uint8, device=dev)
-            whole[:szs[0]] = d_out[:szs[0]]
-            off = szs[0]
-            reqs = []
-            for r_ in range(1, world):
-                reqs.append(dist.irecv(whole[off:off + szs[r_]], src=r_))
-                off += szs[r_]
-            for q in reqs:
-                q.wait()
-        else:
-            dist.send(d_out[:comp_len], dst=0)
-        g1.record(stream)
-        barrier()
-        gather_ms = max_over_ranks(g0.elapsed_time(g1))
+            assert whole.numel() == int(all_sizes.sum().item()) and torch.equal(whole[:comp_len], d_out[:comp_len])
+        del whole
 
     # e2e through the host-pointer call
     h_out = torch.empty(bound, dtype=torch.uint8).pin_memory()
