@@ -187,8 +187,21 @@ def cpu_deflate(O, data, n_chunks, threads, strategy):
 
 
 # ------------------------------------------------------------------ main
+def emit(line):
+    """The ONE JSON line goes to the real stdout; everything else a library prints there (NCCL's version banner,
+    for one) was redirected to stderr in main()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -388,7 +401,7 @@ def main():
     elif "deflate" in line:
         line["deflate"].pop("_cpu", None)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -539,7 +552,7 @@ def run_reference(args, b2d, cores, n_members):
     val = n_s * MEMBER_BYTES / step_s / 1e9
     sample = (f"oracle_inflate (C restatement of decomp/Open.java; JVM absent) over the first {n_s} of {n_members} "
               f"members per step, {cores} threads")
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": "batch inflate GB/s uncompressed", "value": round(val, 4), "unit": "GB/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(step_s * 1e3, 3),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
@@ -547,7 +560,7 @@ def run_reference(args, b2d, cores, n_members):
                                f"bounded sample of {n_s} members per step"},
         "cpu_baseline": {"value": round(val, 4), "unit": "GB/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": round(val, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
     return 0
 
 
