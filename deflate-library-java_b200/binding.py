@@ -30,7 +30,7 @@ EXPORTS = [
     "b2d_init", "b2d_shutdown", "b2d_strerror", "b2d_last_error", "b2d_device_sm_count", "b2d_alloc_pinned",
     "b2d_free_pinned", "b2d_inflate_batch", "b2d_inflate_batch_dev", "b2d_deflate_bound", "b2d_deflate_chunks",
     "b2d_deflate_chunks_dev", "b2d_crc32", "b2d_crc32_dev", "b2d_crc32_combine", "b2d_corpus_random",
-    "b2d_corpus_text", "b2d_corpus_mixed",
+    "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
 ]
 
 
@@ -83,6 +83,10 @@ def lib():
     L.b2d_inflate_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32]
     L.b2d_inflate_batch_dev.restype = i32
     L.b2d_inflate_batch_dev.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.b2d_gzip_isize.restype = i32
+    L.b2d_gzip_isize.argtypes = [vp, vp, u32, vp]
+    L.b2d_gunzip_batch.restype = i32
+    L.b2d_gunzip_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp]
     L.b2d_deflate_bound.restype = u64
     L.b2d_deflate_bound.argtypes = [u64, u32]
     L.b2d_deflate_chunks.restype = ctypes.c_int64
@@ -211,3 +215,31 @@ def crc32(data, crc=0):
 
 def crc32_combine(a, b, len_b):
     return int(lib().b2d_crc32_combine(a, b, len_b))
+
+
+def gunzip_batch(members, out_caps=None):
+    """members: list of complete gzip members.  out_caps: capacities (default: each member's ISIZE).
+    -> (outputs list[bytes], out_len, in_consumed, status)."""
+    n = len(members)
+    in_off = np.zeros(n + 1, dtype=np.uint64)
+    for i, m in enumerate(members):
+        in_off[i + 1] = in_off[i] + np.uint64(len(m))
+    blob = np.frombuffer(b"".join(bytes(m) for m in members), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    if out_caps is None:
+        caps = np.zeros(max(n, 1), dtype=np.uint64)
+        _check(lib().b2d_gzip_isize(blob.ctypes.data if blob.size else None, in_off.ctypes.data, n, caps.ctypes.data), "b2d_gzip_isize")
+        out_caps = [int(c) for c in caps[:n]]
+    elif isinstance(out_caps, int):
+        out_caps = [out_caps] * n
+    out_off = np.zeros(n + 1, dtype=np.uint64)
+    for i in range(n):
+        out_off[i + 1] = out_off[i] + np.uint64(out_caps[i])
+    out = np.zeros(max(int(out_off[n]), 1), dtype=np.uint8)
+    out_len = np.zeros(max(n, 1), dtype=np.uint64)
+    consumed = np.zeros(max(n, 1), dtype=np.uint64)
+    status = np.zeros(max(n, 1), dtype=np.int32)
+    r = lib().b2d_gunzip_batch(blob.ctypes.data if blob.size else None, in_off.ctypes.data, n, out.ctypes.data, out_off.ctypes.data,
+                               out_len.ctypes.data, consumed.ctypes.data, status.ctypes.data)
+    _check(r, "b2d_gunzip_batch")
+    outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_len[i])]) for i in range(n)]
+    return outs, out_len[:n], consumed[:n], status[:n]

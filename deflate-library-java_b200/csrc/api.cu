@@ -30,7 +30,7 @@ struct Ctx {
 	int device = -1;
 	int sm_count = 0;
 	cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};    // pipeline streams (one per slice)
-	cudaEvent_t ev[8] = {};
+	cudaEvent_t ev[24] = {};
 	DevBuf in, out, meta, scratch, crc;
 	void *pinned_meta = nullptr;
 	size_t pinned_meta_cap = 0;
@@ -371,6 +371,60 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 	if ((r = ensure_pinned_meta(m_total))) return r;
 	uint8_t *dm = (uint8_t *)g.meta.p, *hm = (uint8_t *)g.pinned_meta;
 	cudaStream_t st = g.st[0];
+	if (p.framing == B2D_FRAMING_CHUNKED && n_chunks >= 512) {
+		// Pipelined: the chunks are cut into up to 4 slices of >= 512 chunks (smaller launches lose more to tail effects than the overlap wins); slice k+1's H2D (stream A) runs under slice k's kernels
+		// (stream B) and slice k-1's D2H (stream C).  The slices are ordinary calls (is_last only on the final one), so
+		// the bytes are the same as one big call.
+		const uint32_t per = std::max<uint32_t>(512, (n_chunks + 3) / 4);
+		const uint32_t n_slices = (n_chunks + per - 1) / per;
+		const uint64_t slice_in = (uint64_t)per * p.chunk_bytes;
+		const uint64_t slice_bound = (deflate_bound_bytes(slice_in, p.chunk_bytes, p.block_bytes) + 255) & ~(uint64_t)255;
+		const size_t ms_clen = 8, ms_ccrc = ms_clen + (size_t)(per + 1) * 8, ms_total = (ms_ccrc + (size_t)(per + 1) * 4 + 15) & ~(size_t)15;
+		if ((r = ensure(g.out, slice_bound * n_slices + 64))) return r;
+		if ((r = ensure(g.meta, ms_total * n_slices))) return r;
+		if ((r = ensure_pinned_meta(ms_total * n_slices))) return r;
+		DeflateParams ps = p;
+		if ((r = ensure(g.scratch, deflate_scratch_bytes(slice_in, ps)))) return r;
+		dm = (uint8_t *)g.meta.p; hm = (uint8_t *)g.pinned_meta;
+		cudaStream_t sA = g.st[1], sB = g.st[0], sC = g.st[2];
+		for (uint32_t k = 0; k < n_slices; k++) {
+			const uint64_t a = (uint64_t)k * slice_in, len = std::min<uint64_t>(slice_in, in_len - a);
+			CK(cudaMemcpyAsync((uint8_t *)g.in.p + a, in + a, len, cudaMemcpyHostToDevice, sA));
+			CK(cudaEventRecord(g.ev[k], sA));
+		}
+		for (uint32_t k = 0; k < n_slices; k++) {
+			const uint64_t a = (uint64_t)k * slice_in, len = std::min<uint64_t>(slice_in, in_len - a);
+			ps.is_last = (p.is_last && k + 1 == n_slices) ? 1 : 0;
+			uint8_t *dmk = dm + ms_total * k;
+			CK(cudaStreamWaitEvent(sB, g.ev[k], 0));
+			r = deflate_dev_locked((const uint8_t *)g.in.p + a, len, ps, (uint8_t *)g.out.p + slice_bound * k, slice_bound,
+			                       (uint64_t *)dmk, (uint64_t *)(dmk + ms_clen), crc32_inout ? (uint32_t *)(dmk + ms_ccrc) : nullptr, sB);
+			if (r) return r;
+			CK(cudaMemcpyAsync(hm + ms_total * k, dmk, ms_total, cudaMemcpyDeviceToHost, sB));
+			CK(cudaEventRecord(g.ev[8 + k], sB));
+		}
+		uint64_t total = 0;
+		uint32_t crc = crc32_inout ? *crc32_inout : 0;
+		for (uint32_t k = 0; k < n_slices; k++) {
+			CK(cudaEventSynchronize(g.ev[8 + k]));
+			const uint8_t *hmk = hm + ms_total * k;
+			const uint64_t tk = *(const uint64_t *)hmk;
+			if (total + tk > out_cap) { cudaStreamSynchronize(sC); return B2D_ERR_OUTPUT_OVERFLOW; }
+			if (tk) CK(cudaMemcpyAsync(out + total, (uint8_t *)g.out.p + slice_bound * k, tk, cudaMemcpyDeviceToHost, sC));
+			total += tk;
+			const uint64_t a = (uint64_t)k * slice_in, len = std::min<uint64_t>(slice_in, in_len - a);
+			const uint32_t nck = (uint32_t)((len + p.chunk_bytes - 1) / p.chunk_bytes);
+			if (chunk_out_len) memcpy(chunk_out_len + (size_t)k * per, hmk + ms_clen, (size_t)nck * 8);
+			if (crc32_inout) {
+				const uint32_t *cc = (const uint32_t *)(hmk + ms_ccrc);
+				for (uint32_t c = 0; c < nck; c++)
+					crc = host_crc32_combine(crc, cc[c], std::min<uint64_t>(p.chunk_bytes, len - (uint64_t)c * p.chunk_bytes));
+			}
+		}
+		CK(cudaStreamSynchronize(sC));
+		if (crc32_inout) *crc32_inout = crc;
+		return (int64_t)total;
+	}
 	if (in_len) CK(cudaMemcpyAsync(g.in.p, in, in_len, cudaMemcpyHostToDevice, st));
 	r = deflate_dev_locked((const uint8_t *)g.in.p, in_len, p, (uint8_t *)g.out.p, bound, (uint64_t *)(dm + m_total_off),
 	                       (uint64_t *)(dm + m_clen), crc32_inout ? (uint32_t *)(dm + m_ccrc) : nullptr, st);
@@ -396,6 +450,96 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 	}
 	CK(cudaStreamSynchronize(st));
 	return (int64_t)total;
+}
+
+// ---------------------------------------------------------------- gzip members
+
+namespace {
+// GzipMetadata.read (GzipMetadata.java:73-146): validates a member header in the reference's order and returns its
+// length, or a status (1 + Reason.ordinal()).
+int parse_gzip_header(const uint8_t *p, uint64_t n, uint64_t *hdr_len) {
+	uint64_t i = 0;
+	auto need = [&](uint64_t k) { return i + k <= n; };
+	if (!need(2)) return B2D_UNEXPECTED_END_OF_STREAM;
+	if (p[0] != 0x1F || p[1] != 0x8B) return B2D_GZIP_INVALID_MAGIC_NUMBER;
+	if (!need(3)) return B2D_UNEXPECTED_END_OF_STREAM;
+	if (p[2] != 8) return B2D_UNSUPPORTED_COMPRESSION_METHOD;
+	if (!need(4)) return B2D_UNEXPECTED_END_OF_STREAM;
+	const int flags = p[3];
+	if (flags & 0xE0) return B2D_GZIP_RESERVED_FLAGS_SET;
+	if (!need(10)) return B2D_UNEXPECTED_END_OF_STREAM;
+	const int os = p[9];
+	if (os > 13 && os != 0xFF) return B2D_GZIP_UNSUPPORTED_OPERATING_SYSTEM;
+	i = 10;
+	if (flags & 4) {
+		if (!need(2)) return B2D_UNEXPECTED_END_OF_STREAM;
+		uint64_t xl = p[i] | (uint64_t)p[i + 1] << 8;
+		i += 2;
+		if (!need(xl)) return B2D_UNEXPECTED_END_OF_STREAM;
+		i += xl;
+	}
+	for (int f = 8; f <= 16; f <<= 1) {
+		if (!(flags & f)) continue;
+		for (;;) {
+			if (!need(1)) return B2D_UNEXPECTED_END_OF_STREAM;
+			if (p[i++] == 0) break;
+		}
+	}
+	if (flags & 2) {
+		if (!need(2)) return B2D_UNEXPECTED_END_OF_STREAM;
+		uint32_t expect = host_crc32_bytes(0, p, (size_t)i) & 0xFFFF;
+		uint32_t actual = p[i] | (uint32_t)p[i + 1] << 8;
+		if (actual != expect) return B2D_HEADER_CHECKSUM_MISMATCH;
+		i += 2;
+	}
+	*hdr_len = i;
+	return B2D_OK;
+}
+}  // namespace
+
+// ISIZE (mod 2^32) of each member, read from its last 4 bytes: what a caller sizes the output slots with.
+B2D_API int b2d_gzip_isize(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint64_t *isize) {
+	if (n && (!in || !in_off || !isize)) return B2D_ERR_BAD_ARGUMENT;
+	for (uint32_t i = 0; i < n; i++) {
+		if (in_off[i + 1] < in_off[i]) return B2D_ERR_BAD_ARGUMENT;
+		const uint64_t len = in_off[i + 1] - in_off[i];
+		const uint8_t *e = in + in_off[i + 1];
+		isize[i] = len >= 18 ? ((uint64_t)e[-4] | (uint64_t)e[-3] << 8 | (uint64_t)e[-2] << 16 | (uint64_t)e[-1] << 24) : 0;
+	}
+	return B2D_OK;
+}
+
+// n independent gzip members, each decoded like `new GzipInputStream(in)` read to the end (GzipInputStream.java:38-90):
+// header validation on the host (tens of bytes), DEFLATE body + CRC-32 on the GPU, then the trailer checks in the
+// reference's order (CRC first, then ISIZE mod 2^32).
+B2D_API int b2d_gunzip_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint8_t *out, const uint64_t *out_off,
+                             uint64_t *out_len, uint64_t *in_consumed, int32_t *status) {
+	if (n == 0) return B2D_OK;
+	if (!in || !in_off || !out_off || !out_len || !in_consumed || !status) return B2D_ERR_BAD_ARGUMENT;
+	std::vector<uint64_t> body(n + 1), hdr(n, 0);
+	std::vector<int32_t> hst(n, 0);
+	std::vector<uint32_t> crc(n);
+	for (uint32_t i = 0; i < n; i++) {
+		if (in_off[i + 1] < in_off[i]) return B2D_ERR_BAD_ARGUMENT;
+		hst[i] = parse_gzip_header(in + in_off[i], in_off[i + 1] - in_off[i], &hdr[i]);
+	}
+	body[n] = in_off[n];
+	for (uint32_t i = n; i-- > 0;) body[i] = hst[i] ? body[i + 1] : in_off[i] + hdr[i];   // a bad header decodes nothing
+	int r = b2d_inflate_batch(in, body.data(), n, out, out_off, out_len, in_consumed, crc.data(), status, B2D_INFLATE_CRC32);
+	if (r != B2D_OK) return r;
+	for (uint32_t i = 0; i < n; i++) {
+		if (hst[i]) { status[i] = hst[i]; out_len[i] = 0; in_consumed[i] = 0; continue; }
+		if (status[i] != 0) { in_consumed[i] += hdr[i]; continue; }
+		const uint64_t end = in_off[i] + hdr[i] + in_consumed[i];
+		if (end + 8 > in_off[i + 1]) { status[i] = B2D_UNEXPECTED_END_OF_STREAM; in_consumed[i] += hdr[i]; continue; }
+		const uint8_t *t = in + end;
+		const uint32_t ec = (uint32_t)t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+		const uint32_t el = (uint32_t)t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+		if (crc[i] != ec) status[i] = B2D_DECOMPRESSED_CHECKSUM_MISMATCH;
+		else if ((uint32_t)out_len[i] != el) status[i] = B2D_DECOMPRESSED_SIZE_MISMATCH;
+		in_consumed[i] += hdr[i] + 8;
+	}
+	return B2D_OK;
 }
 
 // ---------------------------------------------------------------- CRC-32

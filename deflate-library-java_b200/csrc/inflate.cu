@@ -367,7 +367,7 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 				LOAD_TILE();
 				if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
 			}
-			if (lane == 0) tile[tpos] = (u8)(e >> 16);
+			tile[tpos] = (u8)(e >> 16);                      // every lane stores the same byte: one broadcast write, no predicate
 			tpos++;
 			sh += e & 31;
 			if (CAREFUL) avail -= e & 31;

@@ -100,6 +100,19 @@ int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off, uint32_
                           uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc32, int32_t *d_status,
                           uint32_t flags, void *stream);
 
+/* ---- gzip members: GzipInputStream.java:38-90 over a batch ---- */
+
+/* ISIZE (mod 2^32) from each member's trailer: the output capacity a caller needs for members below 4 GiB. */
+int b2d_gzip_isize(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint64_t *isize);
+
+/* Decodes n independent gzip members (host pointers): header checks of GzipMetadata.read (GzipMetadata.java:73-146) in
+ * the reference's order, body + CRC-32 on the GPU, then the trailer checks of GzipInputStream.java:73-88 (CRC, then
+ * ISIZE mod 2^32).  status[i] = 0 or 1 + Reason.ordinal() (incl. the container reasons 13..19); in_consumed[i] counts
+ * header + body + 8 trailer bytes; only the first member of each range is read, trailing bytes are ignored like
+ * GzipInputStream.java:66-74 does. */
+int b2d_gunzip_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint8_t *out, const uint64_t *out_off,
+                     uint64_t *out_len, uint64_t *in_consumed, int32_t *status);
+
 /* ---- compression: replaces comp/Lz77Huffman.java (decide/compressTo :42-288), comp/Uncompressed.java,
  *      comp/MultiStrategy.java behind DeflaterOutputStream.writeBuffer (DeflaterOutputStream.java:119-137) ---- */
 

@@ -183,3 +183,42 @@ def test_batch_shape_of_config2_small(b2d, oracle):
         assert outs[i] == datas[i] and consumed[i] == len(members[i]) and crc[i] == zlib.crc32(datas[i])
     st, out, cons = oracle.inflate(members[0], out_cap=size)
     assert st == 0 and out == outs[0]
+
+
+def test_gunzip_batch_matches_reference_gzip_reader(b2d, oracle):
+    """b2d_gunzip_batch vs the oracle's restatement of GzipInputStream (GzipInputStream.java:38-90,
+    GzipMetadata.java:73-146): good members from three writers, and every container failure reason."""
+    import gzip as pygzip
+    rng = random.Random(1952)
+    datas = [b"", b"x", _text(rng, 70000), rng.randbytes(30000), bytes(100000), _text(rng, 300000)]
+    members = []
+    for d in datas:
+        members.append(pygzip.compress(d, 6, mtime=0))                                           # Python/zlib writer
+        members.append(oracle.gzip_member(d, file_name="a.txt", mtime=1700000000))               # gzip.java as restated (FNAME + FHCRC)
+        members.append(oracle.gzip_member(d, file_name=None, mtime=0, extra=b"B2\x04\x00abcd"))   # FEXTRA
+    good = pygzip.compress(datas[2], 6, mtime=0)
+    hc = oracle.gzip_member(datas[2], file_name="h", mtime=5)
+    bad = [
+        b"", good[:1], good[:5], good[:9],                       # truncated header
+        b"\x1f\x8c" + good[2:],                                  # magic
+        good[:2] + b"\x07" + good[3:],                           # method
+        good[:3] + b"\x20" + good[4:],                           # reserved flag
+        good[:9] + b"\x0e" + good[10:],                          # operating system 14
+        good[:9] + b"\xff" + good[10:],                          # operating system "unknown" is legal
+        hc[:12] + bytes([hc[12] ^ 1]) + hc[13:],                 # header CRC-16 mismatch (file name byte flipped)
+        good[:-8] + bytes([good[-8] ^ 1]) + good[-7:],           # CRC-32
+        good[:-1] + bytes([good[-1] ^ 1]),                       # ISIZE
+        good[:-3],                                               # truncated trailer
+        good[:len(good) // 2],                                   # truncated body
+        good + b"trailing garbage is ignored",                   # GzipInputStream.java:66-74
+    ]
+    members += bad
+    caps = [400000] * len(members)
+    outs, out_len, consumed, status = b2d.gunzip_batch(members, caps)
+    for i, m in enumerate(members):
+        st, out, cons = oracle.gunzip(m, out_cap=caps[i])
+        assert int(status[i]) == st, (i, b2d.status_name(int(status[i])), oracle.status_name(st))
+        if st == 0:
+            assert outs[i] == out and int(consumed[i]) == cons, i
+    outs2, _, _, status2 = b2d.gunzip_batch(members[:18])     # capacities from ISIZE
+    assert not status2.any() and outs2 == outs[:18]
