@@ -206,7 +206,22 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	}
 	__syncthreads();
 	const u32 woff = (u32)(ts - win);                 // offset of the tile inside the window
-	for (u32 k = threadIdx.x; k < (u32)(te - ts); k += MATCH_THREADS) {
+	// Each thread takes a run of consecutive positions, so that in the default search a match found at p is
+	// inherited by p + 1 (same distance, one byte shorter, then extended): positions inside long repeats cost a few
+	// instructions instead of a full 258-byte comparison per candidate.  The exact searches (RLE / FULL) do not
+	// inherit: they must return the longest match with ties to the smallest distance (Lz77Huffman.java:71-84).
+	const u32 n_pos = (u32)(te - ts);
+	const bool inherit = mp.search == B2D_SEARCH_DEFAULT;
+	constexpr u32 RUN = 8;                            // consecutive positions per thread and round: two 16-byte stores per lane
+	for (u32 round = 0; round < TILE / (MATCH_THREADS * RUN); round++) {
+	const u32 k0 = (round * MATCH_THREADS + threadIdx.x) * RUN;
+	if (k0 >= n_pos) break;
+	u32 res[RUN];
+	int prev_len = 0, prev_dist = 0;
+#pragma unroll 1
+	for (u32 j = 0; j < RUN; j++) {
+		const u32 k = k0 + j;
+		if (k >= n_pos) { res[j] = 0; continue; }
 		const u64 p = ts + k;
 		const u32 o = woff + k;
 		const u32 cur = sm_load4(W, o);
@@ -221,14 +236,25 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 		} else if (mp.search != B2D_SEARCH_LITERAL && maxlen >= mp.hb && p + mp.hb <= ce) {
 			const u32 cmask = mp.hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
 			const u32 max_dist = (u32)min((u64)WINDOW, p - cs);
-			u32 d = P[o];
-			u32 dist = 0;
 			int depth = mp.depth;
 			best_len = mp.hb - 1;
+			if (inherit && prev_len > mp.hb) {                     // same source, shifted by one
+				int len = min(prev_len - 1, maxlen);
+				if (len < maxlen) len += sm_match_len(W, o - prev_dist + len, o + len, maxlen - len);
+				best_len = len;
+				best_dist = prev_dist;
+				if (len >= 32) depth = len >= maxlen ? 0 : 1;       // already good: barely look further
+			}
+			u32 d = P[o];
+			u32 dist = 0;
 			while (d != 0 && depth-- > 0) {
 				dist += d;
 				if (dist > max_dist) break;
 				const u32 c = o - dist;
+				d = P[c];
+				if ((int)dist == best_dist) continue;
+				// a candidate can only win if it also matches the byte that would make it longer
+				if (best_len >= 4 && sm_load4(W, c + best_len - 3) != sm_load4(W, o + best_len - 3)) continue;
 				if (((sm_load4(W, c) ^ cur) & cmask) == 0) {
 					int len = mp.hb + sm_match_len(W, c + mp.hb, o + mp.hb, maxlen - mp.hb);
 					if (len > best_len) {                          // strict: ties keep the smaller distance (:80)
@@ -237,11 +263,17 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 						if (len >= mp.nice || len >= maxlen) break;
 					}
 				}
-				d = P[c];
 			}
 			if (best_dist == 0) best_len = 0;
 		}
-		match[p] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
+		prev_len = best_len;
+		prev_dist = best_dist;
+		res[j] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
+	}
+	// ts is a multiple of TILE and k0 of RUN, so the 32 bytes are aligned; the scratch array is padded past n
+	uint4 *dst = (uint4 *)(match + ts + k0);
+	dst[0] = make_uint4(res[0], res[1], res[2], res[3]);
+	dst[1] = make_uint4(res[4], res[5], res[6], res[7]);
 	}
 }
 

@@ -26,6 +26,7 @@ constexpr int D_TB = 8;                   // distance LUT index bits
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTAS_PER_SM = 7;            // 28 resident warps per SM: 4096 members fit one wave on 148 SMs
 constexpr int TILE = 1024;                // bytes of output staged per warp in shared memory
+constexpr u32 LIT_GUARD = 80;             // see decode_block<false>
 
 // LUT entry (lit/len and distance): [4:0] total bits (code + extra)   [7:5] kind flags   [12:8] code length
 //                                   [31:16] value (literal byte, length base, distance base, or sub-kind)
@@ -354,14 +355,24 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 				sh -= 32; cur = nxt; nxt = pre; widx++;
 				pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
 			}
-			if (!CAREFUL && widx > fast_last) { ret = R_SWITCH; break; }
+			if (!CAREFUL) {
+				if (widx > fast_last) { ret = R_SWITCH; break; }
+				// FAST literals are stored without a capacity check: fewer than LIT_GUARD symbols can start before the
+				// next word boundary is crossed (<= 79 bits at >= 1 bit each), so room for that many is secured here.
+				if (tpos + LIT_GUARD > tlimit) {
+					SAVE_STATE();
+					flush_tile(m, sm, lane);
+					LOAD_TILE();
+					if (tpos + LIT_GUARD > tlimit) { ret = R_SWITCH; break; }     // the member's slot is nearly full: checked path
+				}
+			}
 		}
 		const u32 lo = __funnelshift_r(cur, nxt, sh);
 		u32 e = ll[lo & ((1u << LL_TB) - 1)];
 	dispatch:
 		if (e & K_LIT) {
 			if (CAREFUL && (int)(e & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
-			if (tpos >= tlimit) {
+			if (CAREFUL && tpos >= tlimit) {
 				SAVE_STATE();
 				flush_tile(m, sm, lane);
 				LOAD_TILE();
@@ -405,8 +416,8 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 		const u32 dist = entry_value(d, lo2);
 		sh += d & 31;
 		if ((int)dist > pos_base + (int)tpos) { ret = B2D_COPY_FROM_BEFORE_DICTIONARY_START; break; }   // Open.java:592-593
-		if (tpos + len <= tlimit) {                          // common case: the whole reference fits the tile
-			if (lane == 0) sm->mq[nm] = make_uint2(tpos | len << 16, dist);
+		if (tpos + len + (CAREFUL ? 0u : LIT_GUARD) <= tlimit) {   // common case: the whole reference fits the tile
+			sm->mq[nm] = make_uint2(tpos | len << 16, dist);     // same value from every lane: one broadcast write
 			tpos += len;
 			if (++nm == 32) {
 				SAVE_STATE();
@@ -435,6 +446,12 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 			if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
 		}
 		if (ret) break;
+		if (!CAREFUL && tpos + LIT_GUARD > tlimit) {         // re-establish the literal guard of the FAST path
+			SAVE_STATE();
+			flush_tile(m, sm, lane);
+			LOAD_TILE();
+			if (tpos + LIT_GUARD > tlimit) { ret = R_SWITCH; break; }
+		}
 	}
 	SAVE_STATE();
 #undef SAVE_STATE
@@ -650,7 +667,8 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 		#ifdef B2D_FORCE_CAREFUL
 		int r = R_SWITCH;
 #else
-		int r = m.in.widx + 3 <= m.in.n_full ? decode_block<false>(m, sm, lane) : (int)R_SWITCH;
+		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
+		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false>(m, sm, lane) : (int)R_SWITCH;
 #endif
 		if (r == R_SWITCH) r = decode_block<true>(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
