@@ -21,7 +21,8 @@ REASONS = [
     "GZIP_RESERVED_FLAGS_SET", "GZIP_UNSUPPORTED_OPERATING_SYSTEM",
 ]
 ERR_OUTPUT_OVERFLOW, ERR_BAD_ARGUMENT, ERR_NO_DEVICE, ERR_CUDA, ERR_OUT_OF_MEMORY = -1, -2, -3, -4, -5
-INFLATE_CRC32, INFLATE_CHUNK_INDEXED = 1, 2
+INFLATE_CRC32, INFLATE_CHUNK_INDEXED, INFLATE_ADLER32 = 1, 2, 4
+CHECKSUM_CRC32, CHECKSUM_ADLER32 = 0, 1
 MODE_AUTO, MODE_STORED, MODE_FIXED, MODE_DYNAMIC = 0, 1, 2, 3
 SEARCH_DEFAULT, SEARCH_LITERAL, SEARCH_RLE, SEARCH_FULL = 0, 1, 2, 3
 FRAMING_CHUNKED, FRAMING_REFERENCE = 0, 1
@@ -31,6 +32,7 @@ EXPORTS = [
     "b2d_free_pinned", "b2d_inflate_batch", "b2d_inflate_batch_dev", "b2d_deflate_bound", "b2d_deflate_chunks",
     "b2d_deflate_chunks_dev", "b2d_crc32", "b2d_crc32_dev", "b2d_crc32_combine", "b2d_corpus_random",
     "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
+    "b2d_adler32", "b2d_adler32_combine",
 ]
 
 
@@ -52,7 +54,7 @@ class B2dError(RuntimeError):
 class DeflateOpts(ctypes.Structure):
     _fields_ = [("chunk_bytes", ctypes.c_uint32), ("block_bytes", ctypes.c_uint32), ("mode", ctypes.c_int32),
                 ("search", ctypes.c_int32), ("chain_depth", ctypes.c_int32), ("lazy", ctypes.c_int32),
-                ("is_last", ctypes.c_int32), ("framing", ctypes.c_int32)]
+                ("is_last", ctypes.c_int32), ("framing", ctypes.c_int32), ("checksum", ctypes.c_int32)]
 
 
 _lib = None
@@ -99,6 +101,10 @@ def lib():
     L.b2d_crc32_dev.argtypes = [vp, u64, vp, vp]
     L.b2d_crc32_combine.restype = u32
     L.b2d_crc32_combine.argtypes = [u32, u32, u64]
+    L.b2d_adler32.restype = u32
+    L.b2d_adler32.argtypes = [u32, vp, u64]
+    L.b2d_adler32_combine.restype = u32
+    L.b2d_adler32_combine.argtypes = [u32, u32, u64]
     for name in ("b2d_corpus_random", "b2d_corpus_text", "b2d_corpus_mixed"):
         f = getattr(L, name)
         f.restype = None
@@ -136,8 +142,8 @@ def _ptr(a):
 
 
 def make_opts(chunk_bytes=0, block_bytes=0, mode=MODE_AUTO, search=SEARCH_DEFAULT, chain_depth=0, lazy=-1, is_last=1,
-              framing=FRAMING_CHUNKED):
-    return DeflateOpts(chunk_bytes, block_bytes, mode, search, chain_depth, lazy, is_last, framing)
+              framing=FRAMING_CHUNKED, checksum=0):
+    return DeflateOpts(chunk_bytes, block_bytes, mode, search, chain_depth, lazy, is_last, framing, checksum)
 
 
 # ---- corpora (host) ----
@@ -211,6 +217,15 @@ def deflate_chunks(data, opts=None, crc=None, want_index=False):
 def crc32(data, crc=0):
     data = _u8(data)
     return int(lib().b2d_crc32(crc, data.ctypes.data if data.size else None, data.size))
+
+
+def adler32(data, adler=1):
+    data = _u8(data)
+    return int(lib().b2d_adler32(adler, data.ctypes.data if data.size else None, data.size))
+
+
+def adler32_combine(a, b, len_b):
+    return int(lib().b2d_adler32_combine(a, b, len_b))
 
 
 def crc32_combine(a, b, len_b):

@@ -119,6 +119,8 @@ int normalise_opts(const b2d_deflate_opts *o, uint64_t in_len, DeflateParams &p)
 	p.lazy = d.lazy < 0 ? 1 : (d.lazy ? 1 : 0);
 	if (p.search != B2D_SEARCH_DEFAULT) p.lazy = d.lazy > 0 ? 1 : 0;     // the reference strategies are greedy
 	p.is_last = d.is_last ? 1 : 0;
+	p.checksum = d.checksum;
+	if (p.checksum != B2D_CHECKSUM_CRC32 && p.checksum != B2D_CHECKSUM_ADLER32) return B2D_ERR_BAD_ARGUMENT;
 	return 0;
 }
 
@@ -129,7 +131,8 @@ int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n
                        int32_t *d_status, uint32_t flags, cudaStream_t st) {
 	if (n == 0) return B2D_OK;
 	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st));
-	if ((flags & B2D_INFLATE_CRC32) && d_crc) CK(launch_crc32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
+	if ((flags & B2D_INFLATE_ADLER32) && d_crc) CK(launch_adler32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
+	else if ((flags & B2D_INFLATE_CRC32) && d_crc) CK(launch_crc32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
 	return B2D_OK;
 }
 
@@ -141,7 +144,8 @@ int deflate_dev_locked(const uint8_t *d_in, uint64_t in_len, const DeflateParams
 	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, g.scratch.p, g.scratch.cap, st));
 	if (d_chunk_crc) {
 		uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
-		CK(launch_crc32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
+		if (p.checksum == B2D_CHECKSUM_ADLER32) CK(launch_adler32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
+		else CK(launch_crc32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
 	}
 	return B2D_OK;
 }
@@ -245,7 +249,7 @@ B2D_API int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off,
 	if (!g.ready) return B2D_ERR_NO_DEVICE;
 	if (n && (!d_in || !d_in_off || !d_out || !d_out_off || !d_out_len || !d_in_consumed || !d_status))
 		return B2D_ERR_BAD_ARGUMENT;
-	if ((flags & B2D_INFLATE_CRC32) && !d_crc32 && n) return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) && !d_crc32 && n) return B2D_ERR_BAD_ARGUMENT;
 	cudaStream_t st = (cudaStream_t)stream;
 	return inflate_dev_locked(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_crc32, d_status, flags, st);
 }
@@ -261,7 +265,7 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	if (!g.ready) return B2D_ERR_NO_DEVICE;
 	if (n == 0) return B2D_OK;
 	if (!in_off || !out_off || !out_len || !in_consumed || !status) return B2D_ERR_BAD_ARGUMENT;
-	if ((flags & B2D_INFLATE_CRC32) && !crc32) return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) && !crc32) return B2D_ERR_BAD_ARGUMENT;
 	for (uint32_t i = 0; i < n; i++)
 		if (in_off[i + 1] < in_off[i] || out_off[i + 1] < out_off[i]) return B2D_ERR_BAD_ARGUMENT;
 	const uint64_t in0 = in_off[0], in_total = in_off[n] - in0;
@@ -326,7 +330,7 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	CK(cudaStreamSynchronize(g.st[0]));
 	memcpy(out_len, hm + m_len, (size_t)n * 8);
 	memcpy(in_consumed, hm + m_cons, (size_t)n * 8);
-	if (crc32 && (flags & B2D_INFLATE_CRC32)) memcpy(crc32, hm + m_crc, (size_t)n * 4);
+	if (crc32 && (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32))) memcpy(crc32, hm + m_crc, (size_t)n * 4);
 	memcpy(status, hm + m_stat, (size_t)n * 4);
 	return B2D_OK;
 }
@@ -418,7 +422,7 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 			if (crc32_inout) {
 				const uint32_t *cc = (const uint32_t *)(hmk + ms_ccrc);
 				for (uint32_t c = 0; c < nck; c++)
-					crc = host_crc32_combine(crc, cc[c], std::min<uint64_t>(p.chunk_bytes, len - (uint64_t)c * p.chunk_bytes));
+					crc = (p.checksum == B2D_CHECKSUM_ADLER32 ? host_adler32_combine : host_crc32_combine)(crc, cc[c], std::min<uint64_t>(p.chunk_bytes, len - (uint64_t)c * p.chunk_bytes));
 			}
 		}
 		CK(cudaStreamSynchronize(sC));
@@ -444,7 +448,7 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 		uint32_t crc = *crc32_inout;
 		for (uint32_t c = 0; c < n_chunks; c++) {
 			uint64_t len = std::min<uint64_t>(p.chunk_bytes, in_len - (uint64_t)c * p.chunk_bytes);
-			crc = host_crc32_combine(crc, cc[c], len);
+			crc = (p.checksum == B2D_CHECKSUM_ADLER32 ? host_adler32_combine : host_crc32_combine)(crc, cc[c], len);
 		}
 		*crc32_inout = crc;
 	}
@@ -561,6 +565,30 @@ B2D_API int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_o
 	CK(launch_crc32_pieces(d_data, len, piece, n_pieces, (uint32_t *)g.crc.p, st));
 	CK(launch_crc32_fold(( const uint32_t *)g.crc.p, n_pieces, piece, len, d_crc_out, st));
 	return B2D_OK;
+}
+
+B2D_API uint32_t b2d_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b) {
+	return host_adler32_combine(adler_a, adler_b, len_b);
+}
+
+B2D_API uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready || len == 0 || !data) return adler;
+	if (cudaSetDevice(g.device) != cudaSuccess) return adler;
+	if (ensure(g.in, len + 64)) return adler;
+	const uint64_t piece = 1u << 20;
+	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
+	if (ensure(g.crc, (size_t)(n_pieces + 1) * 4)) return adler;
+	if (ensure_pinned_meta((size_t)(n_pieces + 1) * 4)) return adler;
+	cudaStream_t st = g.st[0];
+	if (cudaMemcpyAsync(g.in.p, data, len, cudaMemcpyHostToDevice, st) != cudaSuccess) return adler;
+	if (launch_adler32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st) != cudaSuccess) return adler;
+	if (cudaMemcpyAsync(g.pinned_meta, g.crc.p, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return adler;
+	if (cudaStreamSynchronize(st) != cudaSuccess) return adler;
+	const uint32_t *pc = (const uint32_t *)g.pinned_meta;
+	for (uint32_t i = 0; i < n_pieces; i++)
+		adler = host_adler32_combine(adler, pc[i], std::min<uint64_t>(piece, len - (uint64_t)i * piece));
+	return adler;
 }
 
 B2D_API uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len) {

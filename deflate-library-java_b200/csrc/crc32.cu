@@ -197,4 +197,89 @@ cudaError_t launch_crc32_fold(const uint32_t *d_piece_crc, uint32_t n_pieces, ui
 	return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------- Adler-32 (zlib container)
+// Replaces java.util.zip.Adler32 at ZlibOutputStream.java:25,56,65 and ZlibInputStream.java:30,69,78.  For a piece d[0,n):
+// A = sum d[i], B = sum (n - i) d[i]; pieces concatenate as A = Ax + Ay, B = Bx + ny * Ax + By, and a running state
+// (s1, s2) advances as s1' = s1 + A, s2' = s2 + n * s1 + B  (all mod 65521).  One CTA per piece, one strip per thread,
+// thread 0 folds the 256 strips.
+constexpr u32 ADLER_MOD = 65521u;
+
+__global__ void __launch_bounds__(CRC_THREADS)
+adler32_kernel(const u8 *__restrict__ data, const u64 *__restrict__ off, const u64 *__restrict__ len,
+               u64 total, u64 piece, u32 *__restrict__ out) {
+	__shared__ u32 sa[CRC_THREADS], sb[CRC_THREADS];
+	const int t = threadIdx.x;
+	u64 s_off, s_len;
+	if (off) { s_off = off[blockIdx.x]; s_len = len[blockIdx.x]; }
+	else { s_off = (u64)blockIdx.x * piece; s_len = total - s_off < piece ? total - s_off : piece; }
+	const u64 L = (((s_len + CRC_THREADS - 1) / CRC_THREADS) + 15) & ~(u64)15;      // strip length, multiple of 16
+	const u64 lo = min(s_len, (u64)t * L), hi = min(s_len, lo + L);
+	const u8 *p = data + s_off + lo;
+	u64 A = 0, B = 0;                                   // running sums of this strip, reduced mod 65521 per block
+	u64 done = 0;
+	const u64 n = hi - lo;
+	while (done < n) {
+		const u32 blk = (u32)min((u64)2048, n - done);
+		u32 a = 0, b = 0;                                // b = sum (blk - i) * d[i]  <= 255 * 2048 * 2049 / 2 < 2^32
+		u32 i = 0;
+		if ((((uintptr_t)(p + done)) & 15) == 0) {
+			for (; i + 16 <= blk; i += 16) {
+				const uint4 v = __ldg((const uint4 *)(p + done + i));
+				const u32 w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+				for (int k = 0; k < 4; k++) {
+#pragma unroll
+					for (int q = 0; q < 4; q++) {
+						const u32 d = (w[k] >> (8 * q)) & 0xFF;
+						a += d;
+						b += (blk - (i + 4 * k + q)) * d;
+					}
+				}
+			}
+		}
+		for (; i < blk; i++) { const u32 d = p[done + i]; a += d; b += (blk - i) * d; }
+		// append the block: strip = strip || block
+		B = (B + (u64)blk * A + b) % ADLER_MOD;
+		A = (A + a) % ADLER_MOD;
+		done += blk;
+	}
+	sa[t] = (u32)A;
+	sb[t] = (u32)B;
+	__syncthreads();
+	if (t == 0) {
+		u64 a = 0, b = 0;
+		for (int k = 0; k < CRC_THREADS; k++) {
+			const u64 klo = min(s_len, (u64)k * L), khi = min(s_len, klo + L);
+			b = (b + ((khi - klo) % ADLER_MOD) * a + sb[k]) % ADLER_MOD;
+			a = (a + sa[k]) % ADLER_MOD;
+		}
+		// as an Adler-32 with the standard start (s1 = 1, s2 = 0)
+		const u64 s1 = (1 + a) % ADLER_MOD, s2 = ((s_len % ADLER_MOD) + b) % ADLER_MOD;
+		out[blockIdx.x] = (u32)(s2 << 16 | s1);
+	}
+}
+
+uint32_t host_adler32_combine(uint32_t ad1, uint32_t ad2, uint64_t len2) {    // adler(A||B) from adler(A), adler(B), |B|
+	const uint64_t M = ADLER_MOD;
+	const uint64_t a1 = ad1 & 0xFFFF, b1 = ad1 >> 16, a2 = ad2 & 0xFFFF, b2 = ad2 >> 16;
+	const uint64_t rem = len2 % M;
+	const uint64_t s1 = (a1 + a2 + M - 1) % M;
+	const uint64_t s2 = (b1 + b2 + rem * ((a1 + M - 1) % M)) % M;
+	return (uint32_t)(s2 << 16 | s1);
+}
+
+cudaError_t launch_adler32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
+                                    uint32_t n_seg, uint32_t *d_out, cudaStream_t st) {
+	if (n_seg == 0) return cudaSuccess;
+	adler32_kernel<<<n_seg, CRC_THREADS, 0, st>>>(d_data, d_off, d_len, 0, 0, d_out);
+	return cudaGetLastError();
+}
+
+cudaError_t launch_adler32_pieces(const uint8_t *d_data, uint64_t total, uint64_t piece, uint32_t n_pieces,
+                                  uint32_t *d_out, cudaStream_t st) {
+	if (n_pieces == 0) return cudaSuccess;
+	adler32_kernel<<<n_pieces, CRC_THREADS, 0, st>>>(d_data, nullptr, nullptr, total, piece, d_out);
+	return cudaGetLastError();
+}
+
 }  // namespace b2d

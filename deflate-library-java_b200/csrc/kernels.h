@@ -22,12 +22,19 @@ cudaError_t launch_crc32_pieces(const uint8_t *d_data, uint64_t total, uint64_t 
 cudaError_t launch_crc32_fold(const uint32_t *d_piece_crc, uint32_t n_pieces, uint64_t piece, uint64_t total,
                               uint32_t *d_crc_out, cudaStream_t st);
 uint32_t host_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);
+// Adler-32 (same shapes as the CRC-32 launches); host_adler32_combine = adler32 of A||B from adler(A), adler(B), |B|
+cudaError_t launch_adler32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
+                                    uint32_t n_seg, uint32_t *d_out, cudaStream_t st);
+cudaError_t launch_adler32_pieces(const uint8_t *d_data, uint64_t total, uint64_t piece, uint32_t n_pieces,
+                                  uint32_t *d_out, cudaStream_t st);
+uint32_t host_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
 uint32_t host_crc32_bytes(uint32_t crc, const uint8_t *p, size_t n);   // tiny inputs only (gzip headers)
 
 // deflate.cu
 struct DeflateParams {
 	uint32_t chunk_bytes, block_bytes;
 	int mode, search, depth, lazy, is_last;
+	int checksum;     // B2D_CHECKSUM_*: what the per-chunk checksum array holds
 	int framing;      // 0 = chunks closed by empty stored blocks; 1 = reference framing (one chunk, BFINAL on the last block)
 };
 uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t block_bytes);

@@ -204,7 +204,9 @@ public:
 	void setChunkIndex(ChunkIndex idx) { index = std::move(idx); }
 	void setOutputSizeHint(uint64_t n) { sizeHint = n; }
 	void setTrailerBytes(size_t n) { trailerBytes = n; }     // bytes after the DEFLATE data that belong to the caller
-	uint32_t crc32() { decodeAll(); return crc; }            // CRC-32 of everything decoded (computed on the GPU)
+	void setChecksumAdler32(bool on) { adler = on; }         // checksum() is Adler-32 (zlib container) instead of CRC-32
+	uint32_t crc32() { decodeAll(); return crc; }            // checksum of everything decoded (computed on the GPU)
+	uint32_t checksum() { return crc32(); }
 	uint64_t consumedBytes() { decodeAll(); return consumed; }
 
 	int read() override {                                                                // :121-134
@@ -238,6 +240,7 @@ private:
 	bool endExactly, closed = false, decoded = false;
 	std::optional<std::string> sticky;
 	ChunkIndex index;
+	bool adler = false;
 	uint64_t sizeHint = 0, consumed = 0;
 	size_t trailerBytes = 0;
 	std::vector<uint8_t> out;
@@ -268,7 +271,8 @@ private:
 			pout.reserve(cap + 64);
 			uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, cap}, out_len = 0, cons = 0;
 			int32_t st = 0;
-			int rc = b2d_inflate_batch(pin.p, in_off, 1, pout.p, out_off, &out_len, &cons, &crc, &st, B2D_INFLATE_CRC32);
+			int rc = b2d_inflate_batch(pin.p, in_off, 1, pout.p, out_off, &out_len, &cons, &crc, &st,
+			                           adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32);
 			if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_batch: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
 			if (st == B2D_ERR_OUTPUT_OVERFLOW) {                         // the size is unknown up front: retry larger
 				if (cap > ((uint64_t)1 << 40)) throw IOException("decompressed size exceeds 1 TiB");
@@ -294,14 +298,14 @@ private:
 		if (in_off[n] > in_len) throw DataFormatException::unexpectedEnd();
 		pout.reserve(out_off[n] + 64);
 		int rc = b2d_inflate_batch(pin.p, in_off.data(), n, pout.p, out_off.data(), out_len.data(), cons.data(), crcs.data(),
-		                           st.data(), B2D_INFLATE_CRC32 | B2D_INFLATE_CHUNK_INDEXED);
+		                           st.data(), (adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32) | B2D_INFLATE_CHUNK_INDEXED);
 		if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_batch: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
 		out.clear();
 		out.reserve(out_off[n]);
-		crc = 0;
+		crc = adler ? 1 : 0;
 		for (uint32_t i = 0; i < n; i++) {                               // deliver up to the first failing chunk, as a serial decode would
 			out.insert(out.end(), pout.p + out_off[i], pout.p + out_off[i] + out_len[i]);
-			crc = b2d_crc32_combine(crc, crcs[i], out_len[i]);
+			crc = adler ? b2d_adler32_combine(crc, crcs[i], out_len[i]) : b2d_crc32_combine(crc, crcs[i], out_len[i]);
 			consumed = in_off[i] + cons[i];
 			if (st[i] != 0 || cons[i] != index.sizes[i] || (i + 1 < n && out_len[i] != index.chunk_bytes)) {
 				status = st[i] != 0 ? st[i] : B2D_UNEXPECTED_END_OF_STREAM;
@@ -320,12 +324,14 @@ struct DeflaterOptions {                     // the GPU build's counterpart of (
 	int chain_depth = 0;
 	int lazy = -1;
 	uint64_t batch_bytes = 256ull << 20;     // input buffered per GPU call
+	int checksum = B2D_CHECKSUM_CRC32;       // which checksum of the input rides the GPU call (gzip: CRC-32, zlib: Adler-32)
 };
 
 class DeflaterOutputStream : public OutputStream {
 public:
 	explicit DeflaterOutputStream(OutputStream &out) : DeflaterOutputStream(out, DeflaterOptions()) {}
-	DeflaterOutputStream(OutputStream &out, const DeflaterOptions &o) : output(&out), opt(o) {
+	DeflaterOutputStream(OutputStream &out, const DeflaterOptions &o)
+	    : output(&out), opt(o), crc(o.checksum == B2D_CHECKSUM_ADLER32 ? 1u : 0u) {
 		if (o.block_bytes < 4096 || o.chunk_bytes % o.block_bytes != 0 || o.batch_bytes < o.chunk_bytes ||
 		    o.batch_bytes % o.chunk_bytes != 0)
 			throw IllegalArgumentException("Invalid capacities");                          // :58-60
@@ -356,7 +362,8 @@ public:
 		if (!ended) finish();
 		output->close();
 	}
-	uint32_t crc32() const { return crc; }               // CRC-32 of all bytes written so far that were compressed
+	uint32_t crc32() const { return crc; }               // checksum (opt.checksum) of all bytes compressed so far
+	uint32_t checksum() const { return crc; }
 	uint64_t totalIn() const { return total_in; }
 	const ChunkIndex &chunkIndex() const { return index; }
 
@@ -365,7 +372,7 @@ private:
 	DeflaterOptions opt;
 	PinnedBuffer stage, comp;
 	uint64_t fill = 0, total_in = 0;
-	uint32_t crc = 0;
+	uint32_t crc;
 	bool ended = false;
 	ChunkIndex index;
 
@@ -376,6 +383,7 @@ private:
 		memset(&o, 0, sizeof o);
 		o.chunk_bytes = opt.chunk_bytes; o.block_bytes = opt.block_bytes; o.mode = opt.mode; o.search = opt.search;
 		o.chain_depth = opt.chain_depth; o.lazy = opt.lazy; o.is_last = last ? 1 : 0; o.framing = B2D_FRAMING_CHUNKED;
+		o.checksum = opt.checksum;
 		const uint64_t bound = b2d_deflate_bound(fill, opt.chunk_bytes);
 		comp.reserve(bound);
 		stage.reserve(1);
@@ -604,6 +612,115 @@ private:
 	GzipMetadata metadata;
 	std::unique_ptr<InflaterInputStream> inflater;
 	uint64_t length = 0;
+};
+
+// ---------------------------------------------------------------- zlib container (RFC 1950)
+struct ZlibMetadata {                                                                     // ZlibMetadata.java:19-47
+	enum class CompressionMethod { DEFLATE, RESERVED };
+	enum class CompressionLevel { FASTEST, FAST, DEFAULT, MAXIMUM };
+	CompressionMethod compressionMethod = CompressionMethod::DEFLATE;
+	int compressionInfo = 7;
+	std::optional<uint32_t> presetDictionary;
+	CompressionLevel compressionLevel = CompressionLevel::DEFAULT;
+
+	ZlibMetadata() {}
+	ZlibMetadata(CompressionMethod cm, int info, std::optional<uint32_t> dict, CompressionLevel lvl)
+	    : compressionMethod(cm), compressionInfo(info), presetDictionary(dict), compressionLevel(lvl) {
+		if (((unsigned)info >> 4) != 0 || (cm == CompressionMethod::DEFLATE && info > 7))
+			throw IllegalArgumentException("Invalid compression info value");
+	}
+	static ZlibMetadata read(InputStream &in) {                                           // ZlibMetadata.java:47-80
+		int cmf = in.read(), flg = in.read();
+		if (flg == -1) throw DataFormatException::unexpectedEnd();
+		if ((cmf << 8 | flg) % 31 != 0)
+			throw DataFormatException(DataFormatException::Reason::HEADER_CHECKSUM_MISMATCH, "Header checksum mismatch");
+		ZlibMetadata m;
+		int method = cmf & 0xF;
+		if (method == 8) m.compressionMethod = CompressionMethod::DEFLATE;
+		else if (method == 15) m.compressionMethod = CompressionMethod::RESERVED;
+		else throw DataFormatException(DataFormatException::Reason::UNSUPPORTED_COMPRESSION_METHOD,
+		                               "Unsupported compression method: " + std::to_string(method));
+		const int info = cmf >> 4;
+		if ((flg >> 5) & 1) {
+			uint32_t val = 0;
+			for (int i = 0; i < 4; i++) {
+				int b = in.read();
+				if (b == -1) throw DataFormatException::unexpectedEnd();
+				val = val << 8 | (uint32_t)b;
+			}
+			m.presetDictionary = val;
+		}
+		m.compressionLevel = (CompressionLevel)(flg >> 6);
+		if (m.compressionMethod == CompressionMethod::DEFLATE && info > 7)                // the record constructor's check (:24-25)
+			throw IllegalArgumentException("Invalid compression info value");
+		m.compressionInfo = info;
+		return m;
+	}
+	void write(OutputStream &out) const {                                                 // ZlibMetadata.java:86-104
+		int cmf = (compressionMethod == CompressionMethod::DEFLATE ? 8 : 15) | compressionInfo << 4;
+		int flg = (presetDictionary ? 1 : 0) << 5 | (int)compressionLevel << 6;
+		flg |= (31 - (cmf << 8 | flg) % 31) % 31;
+		out.write(cmf);
+		out.write(flg);
+		if (presetDictionary) for (int i = 3; i >= 0; i--) out.write((int)(*presetDictionary >> (i * 8)) & 0xFF);
+	}
+};
+
+class ZlibOutputStream : public OutputStream {                                            // ZlibOutputStream.java:31-75
+public:
+	ZlibOutputStream(OutputStream &out, const ZlibMetadata &meta) : under(&out), deflater(out, adlerOptions()) { meta.write(out); }
+	using OutputStream::write;
+	void write(int b) override { uint8_t x = (uint8_t)b; write(&x, 0, 1); }
+	void write(const uint8_t *b, size_t off, size_t len) override {
+		if (ended) throw IllegalStateException("Stream already ended");
+		deflater.write(b, off, len);                       // the Adler-32 rides the GPU call (ZlibOutputStream.java:56)
+	}
+	void finish() {                                                                       // :60-67, big-endian trailer
+		if (ended) throw IllegalStateException("Stream already ended");
+		deflater.finish();
+		const uint32_t a = deflater.checksum();
+		uint8_t t[4] = {(uint8_t)(a >> 24), (uint8_t)(a >> 16), (uint8_t)(a >> 8), (uint8_t)a};
+		under->write(t, 0, 4);
+		ended = true;
+	}
+	void close() override { if (!ended) finish(); under->close(); }
+private:
+	static DeflaterOptions adlerOptions() { DeflaterOptions o; o.checksum = B2D_CHECKSUM_ADLER32; return o; }
+	OutputStream *under;
+	DeflaterOutputStream deflater;
+	bool ended = false;
+};
+
+class ZlibInputStream : public InputStream {                                              // ZlibInputStream.java:36-83
+public:
+	explicit ZlibInputStream(InputStream &in) : raw(&in), metadata(ZlibMetadata::read(in)) {
+		if (!in.markSupported()) throw IllegalArgumentException("Input stream not markable");
+		inflater.reset(new InflaterInputStream(in, true));
+		inflater->setChecksumAdler32(true);
+	}
+	const ZlibMetadata &getMetadata() const { return metadata; }
+	int read() override { uint8_t b; return read(&b, 0, 1) == 1 ? b : -1; }
+	long read(uint8_t *b, size_t off, size_t len) override {                              // :64-83
+		if (!inflater) return -1;
+		long r = inflater->read(b, off, len);
+		if (r != -1) return r;
+		const uint32_t got = inflater->checksum();
+		inflater.reset();
+		uint32_t expect = 0;
+		for (int i = 0; i < 4; i++) {
+			int v = raw->read();
+			if (v < 0) throw DataFormatException::unexpectedEnd();
+			expect = expect << 8 | (uint32_t)v;
+		}
+		if (got != expect)
+			throw DataFormatException(DataFormatException::Reason::DECOMPRESSED_CHECKSUM_MISMATCH, "Decompression Adler-32 mismatch");
+		return -1;
+	}
+	void close() override { raw->close(); inflater.reset(); }
+private:
+	InputStream *raw;
+	ZlibMetadata metadata;
+	std::unique_ptr<InflaterInputStream> inflater;
 };
 
 }  // namespace io_nayuki_deflate

@@ -85,6 +85,7 @@ public final class GpuDeflaterOutputStream extends OutputStream {
 			o.set(JAVA_INT, 20, -1);     // lazy default
 			o.set(JAVA_INT, 24, last ? 1 : 0);
 			o.set(JAVA_INT, 28, 0);      // chunked framing
+			o.set(JAVA_INT, 32, 0);      // CRC-32 alongside
 			MemorySegment crc = a.allocate(JAVA_INT);
 			crc.set(JAVA_INT, 0, crc32);
 			long n = B2Deflate.deflateChunks(stage, fill, o, comp, comp.byteSize(), crc, MemorySegment.NULL);

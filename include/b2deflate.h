@@ -79,6 +79,7 @@ void b2d_free_pinned(void *p);
  *      InflaterInputStream.read (InflaterInputStream.java:147-164) ---- */
 
 #define B2D_INFLATE_CRC32        1u   /* also compute CRC-32 of every member's output (GzipInputStream.java:72) */
+#define B2D_INFLATE_ADLER32      4u   /* the crc32[] slot receives Adler-32 instead (ZlibInputStream.java:69); wins over CRC32 */
 #define B2D_INFLATE_CHUNK_INDEXED 2u  /* unit = chunk of a b2d_deflate_chunks stream: ends at BFINAL *or* exactly
                                          at the end of its byte range on a block boundary */
 
@@ -142,6 +143,12 @@ enum {
 	                              output is byte-identical to the reference strategy of the same name. */
 };
 
+/* Checksum of the uncompressed data computed alongside compression. */
+enum {
+	B2D_CHECKSUM_CRC32 = 0,    /* gzip: java.util.zip.CRC32 at GzipOutputStream.java:57; running value starts at 0 */
+	B2D_CHECKSUM_ADLER32 = 1   /* zlib: java.util.zip.Adler32 at ZlibOutputStream.java:56; running value starts at 1 */
+};
+
 typedef struct b2d_deflate_opts {
 	uint32_t chunk_bytes;   /* independent unit, history reset at its start; 0 = 1 MiB */
 	uint32_t block_bytes;   /* one DEFLATE block per this many input bytes (dataLookaheadLimit,
@@ -152,6 +159,7 @@ typedef struct b2d_deflate_opts {
 	int32_t lazy;           /* -1 = default (on), 0 = greedy, 1 = lazy */
 	int32_t is_last;        /* 1: the stream ends after this call (final block emitted) */
 	int32_t framing;        /* B2D_FRAMING_* */
+	int32_t checksum;       /* B2D_CHECKSUM_*: which checksum of the input crc32_inout / d_chunk_crc32 carry */
 } b2d_deflate_opts;
 
 /* Worst-case output size of b2d_deflate_chunks for in_len bytes (any mode, any framing). */
@@ -179,6 +187,11 @@ int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b2d_defla
 uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len);            /* host pointer, computed on the GPU */
 int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_out, void *stream);   /* crc of d_data[0,len), init 0 */
 uint32_t b2d_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);     /* crc(A||B) from crc(A), crc(B), |B| */
+
+/* ---- Adler-32: replaces java.util.zip.Adler32 at ZlibOutputStream.java:25,56,65 / ZlibInputStream.java:30,69,78
+ *      (SURVEY.md 8f, row N4).  A fresh checksum starts at 1. ---- */
+uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len);         /* host pointer, computed on the GPU */
+uint32_t b2d_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
 
 /* ---- synthetic corpora (host; SURVEY.md Appendix D -- the reference ships no data) ---- */
 void b2d_corpus_random(uint64_t seed, uint8_t *out, size_t n);

@@ -114,6 +114,10 @@ int oracle_gzip_parse_header(const uint8_t *in, size_t n, size_t *header_len);
 int oracle_gunzip(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len,
                   size_t *in_consumed);
 
+/* ---- zlib container (ZlibMetadata.java, ZlibInputStream.java, ZlibOutputStream.java; java.util.zip.Adler32) ---- */
+uint32_t oracle_adler32(uint32_t adler, const uint8_t *p, size_t n);
+int oracle_unzlib(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len, size_t *in_consumed);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,7 +52,7 @@ def lib():
             build()
             L = ctypes.CDLL(_SO)
             u8p, szp = ctypes.c_char_p, ctypes.POINTER(ctypes.c_size_t)
-            for name in ("oracle_inflate", "oracle_inflate_slow", "oracle_gunzip"):
+            for name in ("oracle_inflate", "oracle_inflate_slow", "oracle_gunzip", "oracle_unzlib"):
                 f = getattr(L, name)
                 f.restype = ctypes.c_int
                 f.argtypes = [u8p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t, szp, szp]
@@ -63,6 +63,8 @@ def lib():
             L.oracle_deflate_bound.argtypes = [ctypes.c_size_t, ctypes.c_int]
             L.oracle_package_merge.restype = None
             L.oracle_package_merge.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int, ctypes.c_void_p]
+            L.oracle_adler32.restype = ctypes.c_uint32
+            L.oracle_adler32.argtypes = [ctypes.c_uint32, u8p, ctypes.c_size_t]
             L.oracle_crc32.restype = ctypes.c_uint32
             L.oracle_crc32.argtypes = [ctypes.c_uint32, u8p, ctypes.c_size_t]
             L.oracle_gzip_header.restype = ctypes.c_size_t
@@ -91,6 +93,16 @@ def inflate(data, out_cap=1 << 20, slow=False):
 def gunzip(data, out_cap=1 << 20):
     """-> (status, output bytes, consumed input bytes).  GzipInputStream semantics (first member only)."""
     return _inflate(lib().oracle_gunzip, data, out_cap)
+
+
+def unzlib(data, out_cap=1 << 20):
+    """-> (status, output bytes, consumed input bytes).  ZlibInputStream semantics."""
+    return _inflate(lib().oracle_unzlib, data, out_cap)
+
+
+def adler32(data, adler=1):
+    data = bytes(data)
+    return lib().oracle_adler32(adler, data, len(data))
 
 
 def deflate(data, strategies=(RLE_DYNAMIC,), lookahead=64 * 1024, history=32 * 1024, brute_force=False):

@@ -114,3 +114,44 @@ int oracle_gunzip(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, siz
 	return 0;
 }
 
+
+/* ---- zlib container (ZlibMetadata.java:47-104, ZlibInputStream.java:64-83, ZlibOutputStream.java:60-67) ---- */
+
+/* java.util.zip.Adler32 (JDK, not reference source): RFC 1950 section 9.  Fresh value = 1. */
+uint32_t oracle_adler32(uint32_t adler, const uint8_t *p, size_t n) {
+	uint32_t s1 = adler & 0xFFFF, s2 = adler >> 16;
+	for (size_t i = 0; i < n; i++) {
+		s1 += p[i];
+		if (s1 >= 65521) s1 -= 65521;
+		s2 += s1;
+		if (s2 >= 65521) s2 -= 65521;
+	}
+	return s2 << 16 | s1;
+}
+
+/* ZlibInputStream read to the end: header checks in ZlibMetadata.read's order, inflate end-exactly, big-endian
+ * Adler-32 trailer. */
+int oracle_unzlib(const uint8_t *in, size_t n, uint8_t *out, size_t out_cap, size_t *out_len, size_t *in_consumed) {
+	if (out_len) *out_len = 0;
+	if (n < 2) return ORC_UNEXPECTED_END_OF_STREAM;                              /* :50-52 */
+	int cmf = in[0], flg = in[1];
+	if ((cmf << 8 | flg) % 31 != 0) return ORC_HEADER_CHECKSUM_MISMATCH;         /* :53-54 */
+	int method = cmf & 0xF;
+	if (method != 8 && method != 15) return ORC_UNSUPPORTED_COMPRESSION_METHOD;  /* :56-61 */
+	size_t hl = 2;
+	if ((flg >> 5) & 1) {                                                        /* :65-75 preset dictionary id */
+		if (n < 6) return ORC_UNEXPECTED_END_OF_STREAM;
+		hl = 6;
+	}
+	if (method == 8 && (cmf >> 4) > 7) return ORC_BAD_ARGUMENT;                  /* IllegalArgumentException from the record (:24-25) */
+	size_t ol = 0, used = 0;
+	int st = oracle_inflate(in + hl, n - hl, out, out_cap, &ol, &used);
+	if (out_len) *out_len = ol;
+	if (st) return st;
+	size_t p = hl + used;
+	if (p + 4 > n) return ORC_UNEXPECTED_END_OF_STREAM;
+	uint32_t expect = (uint32_t)in[p] << 24 | (uint32_t)in[p + 1] << 16 | (uint32_t)in[p + 2] << 8 | (uint32_t)in[p + 3];
+	if (in_consumed) *in_consumed = p + 4;
+	if (oracle_adler32(1, out, ol) != expect) return ORC_DECOMPRESSED_CHECKSUM_MISMATCH;
+	return 0;
+}

@@ -91,3 +91,12 @@ def test_cli_fails_loudly_without_gpu(tmp_path):
     assert r.returncode == 1 and "No usable sm_100 GPU" in r.stderr
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 1 and r.stderr.startswith("Usage:")
+
+
+def test_adler32_combine_is_host_math(b2d_nogpu):
+    import random
+    import zlib
+    rng = random.Random(2)
+    for la, lb in ((0, 0), (1, 0), (0, 5), (1234, 77777), (65521, 65521 * 3 + 7)):
+        a, b = rng.randbytes(la), rng.randbytes(lb)
+        assert b2d_nogpu.adler32_combine(zlib.adler32(a), zlib.adler32(b), len(b)) == zlib.adler32(a + b)

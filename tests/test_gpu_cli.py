@@ -78,3 +78,54 @@ def test_gunzip_error_convention(b2d, tmp_path):
     assert r.returncode == 1 and r.stderr.startswith("Usage:")
     r = run(GZIP, str(tmp_path), str(tmp_path / "x.gz"))
     assert r.returncode == 1 and "Input path is a directory" in r.stderr
+
+
+def test_adler32_on_gpu(b2d):
+    import random
+    rng = random.Random(1950)
+    assert b2d.adler32(b"Wikipedia") == 0x11E60398
+    for n in (0, 1, 15, 16, 17, 4095, 65536, (1 << 20) + 3, 5_000_001):
+        d = rng.randbytes(n // 2) + b"\xff" * (n - n // 2)
+        assert b2d.adler32(d) == zlib.adler32(d), n
+        assert b2d.adler32(d, 0x12345678 % 65521 | (0x4321 << 16)) == zlib.adler32(d, 0x12345678 % 65521 | (0x4321 << 16)), n
+
+
+ZPIPE = os.path.join(BIN, "zpipe")
+
+
+@pytest.mark.parametrize("kind,n", [("text", 0), ("text", 100), ("mixed", (3 << 20) + 17), ("random", 1 << 20)])
+def test_zlib_container_roundtrip_and_interop(b2d, oracle, tmp_path, kind, n):
+    """ZlibOutputStream / ZlibInputStream of the host mirror against the oracle's restatement and
+    Python's zlib, both directions."""
+    data = b2d.corpus(kind, 0xDEF1A7E, n).tobytes()
+    src, zz, back = tmp_path / "in.bin", tmp_path / "out.zz", tmp_path / "back.bin"
+    src.write_bytes(data)
+    r = run(ZPIPE, "-c", str(src), str(zz))
+    assert r.returncode == 0, r.stderr
+    blob = zz.read_bytes()
+    assert blob[:2] == b"\x78\x9c"                                   # ZlibMetadata.DEFAULT: deflate, 32 KiB window, level DEFAULT
+    assert zlib.decompress(blob) == data
+    st, out, consumed = oracle.unzlib(blob, out_cap=n + 16)
+    assert st == 0 and out == data and consumed == len(blob)
+    r = run(ZPIPE, "-d", str(zz), str(back))
+    assert r.returncode == 0 and back.read_bytes() == data
+    foreign = tmp_path / "py.zz"
+    foreign.write_bytes(zlib.compress(data, 6))
+    r = run(ZPIPE, "-d", str(foreign), str(back))
+    assert r.returncode == 0 and back.read_bytes() == data
+
+
+def test_zlib_container_errors(b2d, tmp_path):
+    z = zlib.compress(b2d.corpus("text", 3, 100000).tobytes(), 6)
+    fix = (31 - ((0x77 << 8) % 31)) % 31
+    cases = {
+        "Header checksum mismatch": bytes([z[0], z[1] ^ 1]) + z[2:],
+        "Unsupported compression method: 7": bytes([0x77, fix]) + z[2:],
+        "Decompression Adler-32 mismatch": z[:-1] + bytes([z[-1] ^ 1]),
+        "Unexpected end of stream": z[:len(z) // 2],
+    }
+    for msg, blob in cases.items():
+        p = tmp_path / "bad.zz"
+        p.write_bytes(blob)
+        r = run(ZPIPE, "-d", str(p), str(tmp_path / "o"))
+        assert r.returncode == 1 and msg in r.stderr, (msg, r.stderr)

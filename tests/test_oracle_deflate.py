@@ -139,3 +139,22 @@ def test_crc32_and_gzip_container(oracle, tmp_path):
     assert oracle.status_name(oracle.gunzip(bytes(bad), out_cap=len(data) + 8)[0]) == "DECOMPRESSED_SIZE_MISMATCH"
     bad = bytearray(member); bad[0] ^= 1
     assert oracle.status_name(oracle.gunzip(bytes(bad), out_cap=len(data) + 8)[0]) == "GZIP_INVALID_MAGIC_NUMBER"
+
+
+def test_zlib_container_oracle(oracle):
+    """ZlibInputStream / Adler-32 restatement against Python's zlib (the reference has no tests for the containers)."""
+    rng = random.Random(1950)
+    for n in (0, 1, 5552, 5553, 70000, 300000):
+        d = rng.randbytes(n // 2) + bytes(n - n // 2)
+        assert oracle.adler32(d) == zlib.adler32(d)
+        z = zlib.compress(d, 6)
+        st, out, consumed = oracle.unzlib(z, out_cap=n + 8)
+        assert st == 0 and out == d and consumed == len(z)
+    z = zlib.compress(b"hello hello hello hello", 9)
+    assert oracle.status_name(oracle.unzlib(z[:1])[0]) == "UNEXPECTED_END_OF_STREAM"
+    assert oracle.status_name(oracle.unzlib(bytes([z[0], z[1] ^ 1]) + z[2:])[0]) == "HEADER_CHECKSUM_MISMATCH"
+    bad = bytes([0x77, 0x77 ^ 0]) + z[2:]
+    fix = (31 - ((0x77 << 8) % 31)) % 31
+    assert oracle.status_name(oracle.unzlib(bytes([0x77, fix]) + z[2:])[0]) == "UNSUPPORTED_COMPRESSION_METHOD"
+    assert oracle.status_name(oracle.unzlib(z[:-1] + bytes([z[-1] ^ 1]))[0]) == "DECOMPRESSED_CHECKSUM_MISMATCH"
+    assert oracle.status_name(oracle.unzlib(z[:-2])[0]) == "UNEXPECTED_END_OF_STREAM"
