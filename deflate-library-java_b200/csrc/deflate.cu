@@ -166,13 +166,19 @@ struct MatchParams {
 __device__ __forceinline__ u32 sm_load4(const u32 *W, u32 o) {
 	return __funnelshift_r(W[o >> 2], W[(o >> 2) + 1], (o & 3) * 8);
 }
-// number of equal bytes of a[0..] and b[0..], at most maxlen
+// number of equal bytes of a[0..] and b[0..], at most maxlen; 8 bytes per step (three aligned words per side)
 __device__ __forceinline__ int sm_match_len(const u32 *W, u32 a, u32 b, int maxlen) {
 	int len = 0;
 	while (len < maxlen) {
-		u32 x = sm_load4(W, a + len) ^ sm_load4(W, b + len);
-		if (x) { len += (__ffs(x) - 1) >> 3; break; }
-		len += 4;
+		const u32 ia = (a + len) >> 2, ib = (b + len) >> 2;
+		const u32 sa = ((a + len) & 3) * 8, sb = ((b + len) & 3) * 8;
+		const u32 a0 = W[ia], a1 = W[ia + 1], a2 = W[ia + 2];
+		const u32 b0 = W[ib], b1 = W[ib + 1], b2 = W[ib + 2];
+		const u32 x0 = __funnelshift_r(a0, a1, sa) ^ __funnelshift_r(b0, b1, sb);
+		const u32 x1 = __funnelshift_r(a1, a2, sa) ^ __funnelshift_r(b1, b2, sb);
+		if (x0) { len += (__ffs(x0) - 1) >> 3; break; }
+		if (x1) { len += 4 + ((__ffs(x1) - 1) >> 3); break; }
+		len += 8;
 	}
 	return len < maxlen ? len : maxlen;
 }
@@ -212,7 +218,7 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	// inherit: they must return the longest match with ties to the smallest distance (Lz77Huffman.java:71-84).
 	const u32 n_pos = (u32)(te - ts);
 	const bool inherit = mp.search == B2D_SEARCH_DEFAULT;
-	constexpr u32 RUN = 8;                            // consecutive positions per thread and round: two 16-byte stores per lane
+	constexpr u32 RUN = 16;                           // consecutive positions per thread and round: four 16-byte stores per lane
 	for (u32 round = 0; round < TILE / (MATCH_THREADS * RUN); round++) {
 	const u32 k0 = (round * MATCH_THREADS + threadIdx.x) * RUN;
 	if (k0 >= n_pos) break;
@@ -270,10 +276,10 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 		prev_dist = best_dist;
 		res[j] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
 	}
-	// ts is a multiple of TILE and k0 of RUN, so the 32 bytes are aligned; the scratch array is padded past n
+	// ts is a multiple of TILE and k0 of RUN, so the stores are 16-byte aligned; the scratch array is padded past n
 	uint4 *dst = (uint4 *)(match + ts + k0);
-	dst[0] = make_uint4(res[0], res[1], res[2], res[3]);
-	dst[1] = make_uint4(res[4], res[5], res[6], res[7]);
+#pragma unroll
+	for (u32 q = 0; q < RUN / 4; q++) dst[q] = make_uint4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
 	}
 }
 
