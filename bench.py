@@ -63,6 +63,16 @@ def host_threads():
         return max(1, os.cpu_count() or 1)
 
 
+def measured_traffic(kernel, n_members):
+    """DRAM bytes per launch of `kernel` from the committed ncu --set full capture (profiles/traffic.json); only valid
+    for the workload it was captured on (the default 4096-member batch)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if n_members != 4096 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get(kernel, {}).get("dram_bytes_per_launch")
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -388,7 +398,8 @@ def main():
                 "ms_per_step": round(e2e_s * 1e3, 3)},
         "gpu_launches": 2 * args.steps + args.steps,   # inflate_kernel + crc32_kernel per headline step; inflate_kernel per roofline step
         "roofline": {"bound": "hbm", "kernel": "b2d::inflate_kernel", "achieved": round(achieved, 2), "peak": hbm_peak,
-                     "unit": "GB/s", "frac": round(achieved / hbm_peak, 5), "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": round(achieved / hbm_peak, 5),
+                     "traffic": measured_traffic("inflate_kernel", n_members), "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": round(kern_s * 1e3, 4),
                      "note": "latency/issue-bound by construction (serial Huffman decode per member); see DESIGN.md"},
         "clocks": clocks,
