@@ -298,9 +298,8 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 		// (a kernel may read the aligned words around its slice while a neighbour's copy lands in them; those bytes
 		// are shifted out / masked by the bit reader, so the race is benign)
 		cudaEvent_t te[4];
-		const char *tr_ = getenv("B2D_TRACE");
+		const char *tr_ = getenv("B2D_TRACE");              // diagnostic: per-slice H2D / kernel / D2H times on stderr
 		const bool trace = tr_ != nullptr && tr_[0] == '1';
-		if (tr_ && tr_[0] == '3') cudaStreamSynchronize(st);
 		if (trace) { for (auto &e : te) cudaEventCreate(&e); cudaEventRecord(te[0], st); }
 		if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
 		if (trace) cudaEventRecord(te[1], st);
@@ -311,7 +310,6 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 		if (r) return r;
 		if (trace) cudaEventRecord(te[2], st);
 		if (ob > oa) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
-		if (tr_ && tr_[0] == '2') cudaStreamSynchronize(st);
 		if (trace) {
 			cudaEventRecord(te[3], st);
 			cudaEventSynchronize(te[3]);
