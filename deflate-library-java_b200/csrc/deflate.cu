@@ -25,7 +25,7 @@
 
 namespace b2d {
 
-constexpr int HASH_BITS = 14;                // 32 KiB head table per warp: 7 chain warps per SM
+constexpr int HASH_BITS = 13;                // 16 KiB head table per warp: 14 chain warps per SM
 constexpr u32 WINDOW = 32768;
 constexpr int MAX_MATCH = 258;
 constexpr u32 TILE = 32768;                 // positions per match CTA
