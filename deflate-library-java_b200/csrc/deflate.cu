@@ -304,19 +304,24 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 	u32 *hist = hist_sm[warp];
 	for (int i = lane; i < 320; i += 32) hist[i] = 0;
 	__syncwarp();
-	const u64 bs = (u64)g * block_bytes, be = min(n, bs + block_bytes);
+	const u64 bs = (u64)g * block_bytes, be64 = min(n, bs + block_bytes);
 	u32 *__restrict__ tk = tokens + bs;
-	u64 i = bs;
-	u64 base = bs & ~(u64)31;
-#define LOADM(k) (base + (k) * 32 + lane < n ? __ldg(match + base + (k) * 32 + lane) : 0u)
+	// 32-bit offsets relative to `org` (bs rounded down to a window of 32 positions)
+	const u64 org = bs & ~(u64)31;
+	const u32 *__restrict__ mb = match + org;
+	const u32 lim = (u32)min((u64)0x7FFFFFFF, n - org);       // positions that exist, relative to org
+	const u32 be = (u32)(be64 - org);
+	u32 i = (u32)(bs - org);
+	u32 base = 0;
+#define LOADM(k) (base + (k) * 32 + lane < lim ? __ldg(mb + base + (k) * 32 + lane) : 0u)
 	u32 w0 = LOADM(0), w1 = LOADM(1), w2 = LOADM(2), w3 = LOADM(3);    // four windows of 32 positions in flight
 	u32 lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);             // positions of window 0 without a match
 	u32 ntok = 0, nbuf = 0, my_tok = 0, my_idx = 0;
 	while (i < be) {
-		u32 o = (u32)(i - base);
+		u32 o = i - base;
 		if (o >= 32) {
 			if (o >= 128) {                                // a long match jumped past everything loaded
-				base = i & ~(u64)31;
+				base = i & ~31u;
 				w0 = LOADM(0); w1 = LOADM(1); w2 = LOADM(2); w3 = LOADM(3);
 			} else {
 				do {
@@ -325,13 +330,12 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 					w3 = LOADM(3);
 				} while (i - base >= 32);
 			}
-			o = (u32)(i - base);
+			o = i - base;
 			lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);
 		}
 		// a run of positions without a match becomes that many literal tokens in one step
 		u32 run = __ffs(~(lit0 >> o)) - 1;                 // ones from bit o upwards (lit0 >> o has zeros on top)
-		if (run > 32 - o) run = 32 - o;
-		if ((u64)run > be - i) run = (u32)(be - i);
+		run = min(run, min(32 - o, be - i));
 		if (run) {
 			if (lane >= o && lane < o + run) {
 				tk[ntok + lane - o] = w0 & 0xFF000000u;
