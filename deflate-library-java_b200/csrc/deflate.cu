@@ -224,6 +224,8 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	if (k0 >= n_pos) break;
 	u32 res[RUN];
 	int prev_len = 0, prev_dist = 0;
+	int run_len = 0, since = 1 << 20;                 // length of / positions since the last searched long match
+	constexpr int SKIP_MIN = 8;
 #pragma unroll 1
 	for (u32 j = 0; j < RUN; j++) {
 		const u32 k = k0 + j;
@@ -250,6 +252,10 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 				best_len = len;
 				best_dist = prev_dist;
 				if (len >= 32) depth = len >= maxlen ? 0 : 1;       // already good: barely look further
+				// Positions 2 .. L-1 behind the start of a searched match of length L >= SKIP_MIN are only reached by
+				// the parser when it arrives sideways; they keep the inherited match and are not searched again.
+				// (Position 1 is searched: the parser's lazy step compares it with the match before it.)
+				if (since >= 2 && since < run_len) depth = 0;
 			}
 			u32 d = P[o];
 			u32 dist = 0;
@@ -272,6 +278,8 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 			}
 			if (best_dist == 0) best_len = 0;
 		}
+		if (best_len >= SKIP_MIN && best_len > run_len - since) { run_len = best_len; since = 0; }
+		since++;
 		prev_len = best_len;
 		prev_dist = best_dist;
 		res[j] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
