@@ -63,7 +63,7 @@ def build_host(force=False):
     bindir = os.path.join(HERE, "bin")
     os.makedirs(bindir, exist_ok=True)
     deps = [os.path.join(host, "b2d_streams.hpp"), os.path.join(HERE, "..", "include", "b2deflate.h"), OUT]
-    for name in ("gzip", "gunzip", "zpipe"):
+    for name in ("gzip", "gunzip", "zpipe", "stream_tests"):
         src = os.path.join(host, name + ".cpp")
         exe = os.path.join(bindir, name)
         if force or _stale(exe, [src] + deps):

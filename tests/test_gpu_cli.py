@@ -129,3 +129,25 @@ def test_zlib_container_errors(b2d, tmp_path):
         p.write_bytes(blob)
         r = run(ZPIPE, "-d", str(p), str(tmp_path / "o"))
         assert r.returncode == 1 and msg in r.stderr, (msg, r.stderr)
+
+
+def test_reference_stream_tests_on_host_mirror(b2d, tmp_path):
+    """The reference's InflaterInputStreamTest harness (both read patterns, endExactly position check, all 39 vectors
+    under 0-, 1- and random padding) and its five DeflaterOutputStreamTest round trips, run against the C++ host mirror
+    (host/stream_tests.cpp), plus the constructor / state contract of the stream classes."""
+    import random
+    from util import bits_to_bytes, golden_vectors
+    rng = random.Random(5)
+    lines = []
+    for v in golden_vectors():
+        for pad in ("0", "1", "r"):
+            data = bits_to_bytes(v["bits"], pad, rng)
+            if v["expect"] == "ok":
+                lines.append(f"{v['name']} {data.hex() or '-'} ok {v['output_hex'] or '-'}")
+            else:
+                lines.append(f"{v['name']} {data.hex() or '-'} fail {v['reason']}")
+    p = tmp_path / "vectors.txt"
+    p.write_text("\n".join(lines) + "\n")
+    r = run(os.path.join(BIN, "stream_tests"), str(p))
+    assert r.returncode == 0, r.stderr[-3000:] + r.stdout
+    assert "passed" in r.stdout and "of" in r.stdout
