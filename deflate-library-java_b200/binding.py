@@ -32,7 +32,7 @@ EXPORTS = [
     "b2d_free_pinned", "b2d_inflate_batch", "b2d_inflate_batch_dev", "b2d_deflate_bound", "b2d_deflate_chunks",
     "b2d_deflate_chunks_dev", "b2d_crc32", "b2d_crc32_dev", "b2d_crc32_combine", "b2d_corpus_random",
     "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
-    "b2d_adler32", "b2d_adler32_combine",
+    "b2d_adler32", "b2d_adler32_combine", "b2d_crc32_update", "b2d_adler32_update",
 ]
 
 
@@ -101,6 +101,10 @@ def lib():
     L.b2d_crc32_dev.argtypes = [vp, u64, vp, vp]
     L.b2d_crc32_combine.restype = u32
     L.b2d_crc32_combine.argtypes = [u32, u32, u64]
+    L.b2d_crc32_update.restype = i32
+    L.b2d_crc32_update.argtypes = [vp, u64, vp]
+    L.b2d_adler32_update.restype = i32
+    L.b2d_adler32_update.argtypes = [vp, u64, vp]
     L.b2d_adler32.restype = u32
     L.b2d_adler32.argtypes = [u32, vp, u64]
     L.b2d_adler32_combine.restype = u32
@@ -216,12 +220,16 @@ def deflate_chunks(data, opts=None, crc=None, want_index=False):
 
 def crc32(data, crc=0):
     data = _u8(data)
-    return int(lib().b2d_crc32(crc, data.ctypes.data if data.size else None, data.size))
+    v = ctypes.c_uint32(crc)
+    _check(lib().b2d_crc32_update(data.ctypes.data if data.size else None, data.size, ctypes.byref(v)), "b2d_crc32_update")
+    return v.value
 
 
 def adler32(data, adler=1):
     data = _u8(data)
-    return int(lib().b2d_adler32(adler, data.ctypes.data if data.size else None, data.size))
+    v = ctypes.c_uint32(adler)
+    _check(lib().b2d_adler32_update(data.ctypes.data if data.size else None, data.size, ctypes.byref(v)), "b2d_adler32_update")
+    return v.value
 
 
 def adler32_combine(a, b, len_b):

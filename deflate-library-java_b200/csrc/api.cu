@@ -569,43 +569,57 @@ B2D_API uint32_t b2d_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_
 	return host_adler32_combine(adler_a, adler_b, len_b);
 }
 
-B2D_API uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len) {
-	std::lock_guard<std::mutex> lk(g_mu);
-	if (!g.ready || len == 0 || !data) return adler;
-	if (cudaSetDevice(g.device) != cudaSuccess) return adler;
-	if (ensure(g.in, len + 64)) return adler;
+// Checksums of host buffers.  The *_update forms report failure (no device, CUDA error); the value-returning forms
+// are conveniences that leave the checksum unchanged on failure and record why in b2d_last_error().
+namespace {
+int checksum_host_locked(bool adler, const uint8_t *data, uint64_t len, uint32_t *inout) {
+	if (!g.ready) { snprintf(g.last_error, sizeof g.last_error, "b2d_init not called or failed"); return B2D_ERR_NO_DEVICE; }
+	if (!inout || (len && !data)) return B2D_ERR_BAD_ARGUMENT;
+	if (len == 0) return B2D_OK;
+	CK(cudaSetDevice(g.device));
+	int r;
+	if ((r = ensure(g.in, len + 64))) return r;
 	const uint64_t piece = 1u << 20;
 	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
-	if (ensure(g.crc, (size_t)(n_pieces + 1) * 4)) return adler;
-	if (ensure_pinned_meta((size_t)(n_pieces + 1) * 4)) return adler;
+	if ((r = ensure(g.crc, (size_t)(n_pieces + 1) * 4))) return r;
+	if ((r = ensure_pinned_meta((size_t)(n_pieces + 1) * 4))) return r;
 	cudaStream_t st = g.st[0];
-	if (cudaMemcpyAsync(g.in.p, data, len, cudaMemcpyHostToDevice, st) != cudaSuccess) return adler;
-	if (launch_adler32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st) != cudaSuccess) return adler;
-	if (cudaMemcpyAsync(g.pinned_meta, g.crc.p, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return adler;
-	if (cudaStreamSynchronize(st) != cudaSuccess) return adler;
+	CK(cudaMemcpyAsync(g.in.p, data, len, cudaMemcpyHostToDevice, st));
+	if (adler) CK(launch_adler32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st));
+	else CK(launch_crc32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st));
+	CK(cudaMemcpyAsync(g.pinned_meta, g.crc.p, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
 	const uint32_t *pc = (const uint32_t *)g.pinned_meta;
-	for (uint32_t i = 0; i < n_pieces; i++)
-		adler = host_adler32_combine(adler, pc[i], std::min<uint64_t>(piece, len - (uint64_t)i * piece));
+	uint32_t v = *inout;
+	for (uint32_t i = 0; i < n_pieces; i++) {
+		const uint64_t l = std::min<uint64_t>(piece, len - (uint64_t)i * piece);
+		v = adler ? host_adler32_combine(v, pc[i], l) : host_crc32_combine(v, pc[i], l);
+	}
+	*inout = v;
+	return B2D_OK;
+}
+}  // namespace
+
+B2D_API int b2d_adler32_update(const uint8_t *data, uint64_t len, uint32_t *adler_inout) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	return checksum_host_locked(true, data, len, adler_inout);
+}
+
+B2D_API int b2d_crc32_update(const uint8_t *data, uint64_t len, uint32_t *crc_inout) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	return checksum_host_locked(false, data, len, crc_inout);
+}
+
+B2D_API uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	checksum_host_locked(true, data, len, &adler);
 	return adler;
 }
 
 B2D_API uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len) {
 	std::lock_guard<std::mutex> lk(g_mu);
-	if (!g.ready || len == 0 || !data) return crc;     // no device: unchanged (callers check b2d_init's result)
-	if (cudaSetDevice(g.device) != cudaSuccess) return crc;
-	if (ensure(g.in, len + 64)) return crc;
-	const uint64_t piece = 1u << 20;
-	const uint32_t n_pieces = (uint32_t)((len + piece - 1) / piece);
-	if (ensure(g.crc, (size_t)(n_pieces + 1) * 4)) return crc;
-	if (ensure_pinned_meta(8)) return crc;
-	cudaStream_t st = g.st[0];
-	uint32_t *d_res = (uint32_t *)g.crc.p + n_pieces;
-	if (cudaMemcpyAsync(g.in.p, data, len, cudaMemcpyHostToDevice, st) != cudaSuccess) return crc;
-	if (launch_crc32_pieces((const uint8_t *)g.in.p, len, piece, n_pieces, (uint32_t *)g.crc.p, st) != cudaSuccess) return crc;
-	if (launch_crc32_fold((const uint32_t *)g.crc.p, n_pieces, piece, len, d_res, st) != cudaSuccess) return crc;
-	if (cudaMemcpyAsync(g.pinned_meta, d_res, 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return crc;
-	if (cudaStreamSynchronize(st) != cudaSuccess) return crc;
-	return host_crc32_combine(crc, *(uint32_t *)g.pinned_meta, len);
+	checksum_host_locked(false, data, len, &crc);
+	return crc;
 }
 
 }  // extern "C"

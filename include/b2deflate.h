@@ -184,13 +184,16 @@ int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b2d_defla
                            uint64_t *d_chunk_out_len, uint32_t *d_chunk_crc32, void *stream);
 
 /* ---- CRC-32: replaces java.util.zip.CRC32 at GzipOutputStream.java:25,57 / GzipInputStream.java:32,72 ---- */
-uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len);            /* host pointer, computed on the GPU */
+int b2d_crc32_update(const uint8_t *data, uint64_t len, uint32_t *crc_inout);    /* host pointer, computed on the GPU; B2D_OK or B2D_ERR_* */
+uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len);            /* convenience: on failure the value is returned
+                                                                                    unchanged and b2d_last_error() says why */
 int b2d_crc32_dev(const uint8_t *d_data, uint64_t len, uint32_t *d_crc_out, void *stream);   /* crc of d_data[0,len), init 0 */
 uint32_t b2d_crc32_combine(uint32_t crc_a, uint32_t crc_b, uint64_t len_b);     /* crc(A||B) from crc(A), crc(B), |B| */
 
 /* ---- Adler-32: replaces java.util.zip.Adler32 at ZlibOutputStream.java:25,56,65 / ZlibInputStream.java:30,69,78
  *      (SURVEY.md 8f, row N4).  A fresh checksum starts at 1. ---- */
-uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len);         /* host pointer, computed on the GPU */
+int b2d_adler32_update(const uint8_t *data, uint64_t len, uint32_t *adler_inout);
+uint32_t b2d_adler32(uint32_t adler, const uint8_t *data, uint64_t len);         /* convenience form, like b2d_crc32 */
 uint32_t b2d_adler32_combine(uint32_t adler_a, uint32_t adler_b, uint64_t len_b);
 
 /* ---- synthetic corpora (host; SURVEY.md Appendix D -- the reference ships no data) ---- */

@@ -77,6 +77,10 @@ def test_no_cpu_fallback(b2d_nogpu):
     assert r == b2d_nogpu.ERR_NO_DEVICE
     with pytest.raises(b2d_nogpu.B2dError):
         b2d_nogpu.init(0)
+    with pytest.raises(b2d_nogpu.B2dError):
+        b2d_nogpu.crc32(b"123456789")                 # checksums too: no device, no answer
+    with pytest.raises(b2d_nogpu.B2dError):
+        b2d_nogpu.adler32(b"123456789")
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="GPU present")
