@@ -33,6 +33,7 @@ EXPORTS = [
     "b2d_deflate_chunks_dev", "b2d_crc32", "b2d_crc32_dev", "b2d_crc32_combine", "b2d_corpus_random",
     "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
     "b2d_adler32", "b2d_adler32_combine", "b2d_crc32_update", "b2d_adler32_update",
+    "b2d_deflate_chunks_indexed", "b2d_deflate_chunks_indexed_dev", "b2d_inflate_chunks", "b2d_inflate_chunks_dev",
 ]
 
 
@@ -95,6 +96,14 @@ def lib():
     L.b2d_deflate_chunks.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp]
     L.b2d_deflate_chunks_dev.restype = i32
     L.b2d_deflate_chunks_dev.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp, vp, vp]
+    L.b2d_deflate_chunks_indexed.restype = ctypes.c_int64
+    L.b2d_deflate_chunks_indexed.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp, vp]
+    L.b2d_deflate_chunks_indexed_dev.restype = i32
+    L.b2d_deflate_chunks_indexed_dev.argtypes = [vp, u64, ctypes.POINTER(DeflateOpts), vp, u64, vp, vp, vp, vp, vp]
+    L.b2d_inflate_chunks.restype = i32
+    L.b2d_inflate_chunks.argtypes = [vp, vp, u32, vp, u32, u32, vp, u64, vp, vp, u32]
+    L.b2d_inflate_chunks_dev.restype = i32
+    L.b2d_inflate_chunks_dev.argtypes = [vp, vp, u32, vp, u32, u32, u64, vp, vp, vp, u32, vp]
     L.b2d_crc32.restype = u32
     L.b2d_crc32.argtypes = [u32, vp, u64]
     L.b2d_crc32_dev.restype = i32
@@ -266,3 +275,34 @@ def gunzip_batch(members, out_caps=None):
     _check(r, "b2d_gunzip_batch")
     outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_len[i])]) for i in range(n)]
     return outs, out_len[:n], consumed[:n], status[:n]
+
+
+def deflate_chunks_indexed(data, opts=None, crc=0):
+    """-> (compressed np.uint8, checksum, chunk sizes u64[], block bit offsets u32[])."""
+    data = _u8(data)
+    opts = opts if opts is not None else make_opts()
+    cb, bb = opts.chunk_bytes or (1 << 20), opts.block_bytes or (1 << 16)
+    cap = deflate_bound(data.size, cb)
+    out = np.empty(cap, dtype=np.uint8)
+    idx = np.zeros(max(1, (data.size + cb - 1) // cb), dtype=np.uint64)
+    bits = np.zeros(max(1, (data.size + bb - 1) // bb), dtype=np.uint32)
+    c = ctypes.c_uint32(crc)
+    r = lib().b2d_deflate_chunks_indexed(data.ctypes.data if data.size else None, data.size, ctypes.byref(opts), out.ctypes.data,
+                                         cap, ctypes.byref(c), idx.ctypes.data, bits.ctypes.data)
+    _check(int(r), "b2d_deflate_chunks_indexed")
+    return out[:int(r)], c.value, idx[:(data.size + cb - 1) // cb], bits[:(data.size + bb - 1) // bb]
+
+
+def inflate_chunks(comp, chunk_sizes, block_bits, out_total, chunk_bytes=1 << 20, block_bytes=1 << 16, flags=INFLATE_CRC32):
+    """-> (out np.uint8[out_total], per-chunk checksum u32[], per-chunk status i32[])."""
+    comp = _u8(comp)
+    sizes = np.ascontiguousarray(chunk_sizes, dtype=np.uint64)
+    bits = np.ascontiguousarray(block_bits, dtype=np.uint32)
+    n = len(sizes)
+    out = np.zeros(max(out_total, 1), dtype=np.uint8)
+    crc = np.zeros(max(n, 1), dtype=np.uint32)
+    st = np.zeros(max(n, 1), dtype=np.int32)
+    r = lib().b2d_inflate_chunks(comp.ctypes.data if comp.size else None, sizes.ctypes.data, n, bits.ctypes.data, chunk_bytes,
+                                 block_bytes, out.ctypes.data, out_total, crc.ctypes.data, st.ctypes.data, flags)
+    _check(r, "b2d_inflate_chunks")
+    return out[:out_total], crc[:n], st[:n]

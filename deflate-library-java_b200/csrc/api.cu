@@ -31,7 +31,7 @@ struct Ctx {
 	int sm_count = 0;
 	cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};    // pipeline streams (one per slice)
 	cudaEvent_t ev[24] = {};
-	DevBuf in, out, meta, scratch, crc;
+	DevBuf in, out, meta, scratch, crc, scratch2, bits;
 	void *pinned_meta = nullptr;
 	size_t pinned_meta_cap = 0;
 	char last_error[256] = "";
@@ -78,7 +78,7 @@ int ensure_pinned_meta(size_t bytes) {
 }
 
 void release_all() {
-	for (DevBuf *b : {&g.in, &g.out, &g.meta, &g.scratch, &g.crc}) {
+	for (DevBuf *b : {&g.in, &g.out, &g.meta, &g.scratch, &g.crc, &g.scratch2, &g.bits}) {
 		if (b->p) cudaFree(b->p);
 		b->p = nullptr;
 		b->cap = 0;
@@ -137,11 +137,12 @@ int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n
 }
 
 int deflate_dev_locked(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out, uint64_t out_cap,
-                       uint64_t *d_total, uint64_t *d_chunk_len, uint32_t *d_chunk_crc, cudaStream_t st) {
+                       uint64_t *d_total, uint64_t *d_chunk_len, uint32_t *d_chunk_crc, cudaStream_t st,
+                       uint32_t *d_block_bits = nullptr) {
 	size_t sb = deflate_scratch_bytes(in_len, p);
 	int r = ensure(g.scratch, sb);
 	if (r) return r;
-	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, g.scratch.p, g.scratch.cap, st));
+	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, g.scratch.p, g.scratch.cap, st, d_block_bits));
 	if (d_chunk_crc) {
 		uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
 		if (p.checksum == B2D_CHECKSUM_ADLER32) CK(launch_adler32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
@@ -452,6 +453,152 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 	}
 	CK(cudaStreamSynchronize(st));
 	return (int64_t)total;
+}
+
+// ---------------------------------------------------------------- block-indexed streams (our own, fully parallel decode)
+
+B2D_API int b2d_deflate_chunks_indexed_dev(const uint8_t *d_in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *d_out,
+                                           uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
+                                           uint32_t *d_chunk_crc32, uint32_t *d_block_bits, void *stream) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	DeflateParams p;
+	int r = normalise_opts(opts, in_len, p);
+	if (r) return r;
+	if ((in_len && !d_in) || !d_out || !d_out_len_total || !d_block_bits || p.framing != B2D_FRAMING_CHUNKED) return B2D_ERR_BAD_ARGUMENT;
+	if (out_cap < deflate_bound_bytes(in_len, p.chunk_bytes, p.block_bytes)) return B2D_ERR_OUTPUT_OVERFLOW;
+	CK(cudaSetDevice(g.device));
+	return deflate_dev_locked(d_in, in_len, p, d_out, out_cap, d_out_len_total, d_chunk_out_len, d_chunk_crc32,
+	                          (cudaStream_t)stream, d_block_bits);
+}
+
+B2D_API int b2d_inflate_chunks_dev(const uint8_t *d_in, const uint64_t *d_chunk_in_off, uint32_t n_chunks,
+                                   const uint32_t *d_block_bits, uint32_t chunk_bytes, uint32_t block_bytes, uint64_t out_total,
+                                   uint8_t *d_out, uint32_t *d_chunk_crc32, int32_t *d_chunk_status, uint32_t flags, void *stream) {
+	std::lock_guard<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if (n_chunks == 0) return B2D_OK;
+	if (!d_in || !d_chunk_in_off || !d_block_bits || !d_out || !d_chunk_status || block_bytes < 4096 || block_bytes > (1u << 20) ||
+	    chunk_bytes % block_bytes != 0 || (uint64_t)n_chunks * chunk_bytes < out_total ||
+	    (uint64_t)(n_chunks - 1) * chunk_bytes >= out_total)
+		return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) && !d_chunk_crc32) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	cudaStream_t st = (cudaStream_t)stream;
+	int r = ensure(g.scratch2, inflate_units_scratch_bytes(out_total, chunk_bytes, block_bytes));
+	if (r) return r;
+	CK(launch_inflate_units(d_in, d_chunk_in_off, n_chunks, d_block_bits, chunk_bytes, block_bytes, out_total, d_out,
+	                        d_chunk_status, g.scratch2.p, st));
+	if (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) {
+		if (flags & B2D_INFLATE_ADLER32) CK(launch_adler32_pieces(d_out, out_total, chunk_bytes, n_chunks, d_chunk_crc32, st));
+		else CK(launch_crc32_pieces(d_out, out_total, chunk_bytes, n_chunks, d_chunk_crc32, st));
+	}
+	return B2D_OK;
+}
+
+// Host form of the pair above.  Compress: like b2d_deflate_chunks plus the block index.  Decompress: chunk sizes + block
+// index in, bytes out; a chunk whose block-parallel decode reports a problem is decoded again serially
+// (B2D_INFLATE_CHUNK_INDEXED) so that status and delivered bytes are exactly the sequential decoder's.
+B2D_API int64_t b2d_deflate_chunks_indexed(const uint8_t *in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *out,
+                                           uint64_t out_cap, uint32_t *crc32_inout, uint64_t *chunk_out_len, uint32_t *block_bits) {
+	std::unique_lock<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	DeflateParams p;
+	int r = normalise_opts(opts, in_len, p);
+	if (r) return r;
+	if ((in_len && !in) || !out || !block_bits || p.framing != B2D_FRAMING_CHUNKED) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	const uint64_t bound = deflate_bound_bytes(in_len, p.chunk_bytes, p.block_bytes);
+	const uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
+	const uint32_t n_blocks = (uint32_t)((in_len + p.block_bytes - 1) / p.block_bytes);
+	if ((r = ensure(g.in, in_len + 64))) return r;
+	if ((r = ensure(g.out, bound + 64))) return r;
+	if ((r = ensure(g.bits, (size_t)(n_blocks + 1) * 4))) return r;
+	const size_t m_clen = 8, m_ccrc = m_clen + (size_t)(n_chunks + 1) * 8, m_total = m_ccrc + (size_t)(n_chunks + 1) * 4;
+	if ((r = ensure(g.meta, m_total))) return r;
+	if ((r = ensure_pinned_meta(m_total))) return r;
+	uint8_t *dm = (uint8_t *)g.meta.p, *hm = (uint8_t *)g.pinned_meta;
+	cudaStream_t st = g.st[0];
+	if (in_len) CK(cudaMemcpyAsync(g.in.p, in, in_len, cudaMemcpyHostToDevice, st));
+	r = deflate_dev_locked((const uint8_t *)g.in.p, in_len, p, (uint8_t *)g.out.p, bound, (uint64_t *)dm, (uint64_t *)(dm + m_clen),
+	                       crc32_inout ? (uint32_t *)(dm + m_ccrc) : nullptr, st, (uint32_t *)g.bits.p);
+	if (r) return r;
+	CK(cudaMemcpyAsync(hm, dm, m_total, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	const uint64_t total = *(uint64_t *)hm;
+	if (total > out_cap) return B2D_ERR_OUTPUT_OVERFLOW;
+	if (total) CK(cudaMemcpyAsync(out, g.out.p, total, cudaMemcpyDeviceToHost, st));
+	if (n_blocks) CK(cudaMemcpyAsync(block_bits, g.bits.p, (size_t)n_blocks * 4, cudaMemcpyDeviceToHost, st));
+	if (chunk_out_len) memcpy(chunk_out_len, hm + m_clen, (size_t)n_chunks * 8);
+	if (crc32_inout) {
+		const uint32_t *cc = (const uint32_t *)(hm + m_ccrc);
+		uint32_t crc = *crc32_inout;
+		for (uint32_t c = 0; c < n_chunks; c++) {
+			uint64_t len = std::min<uint64_t>(p.chunk_bytes, in_len - (uint64_t)c * p.chunk_bytes);
+			crc = (p.checksum == B2D_CHECKSUM_ADLER32 ? host_adler32_combine : host_crc32_combine)(crc, cc[c], len);
+		}
+		*crc32_inout = crc;
+	}
+	CK(cudaStreamSynchronize(st));
+	return (int64_t)total;
+}
+
+B2D_API int b2d_inflate_chunks(const uint8_t *in, const uint64_t *chunk_in_len, uint32_t n_chunks, const uint32_t *block_bits,
+                               uint32_t chunk_bytes, uint32_t block_bytes, uint8_t *out, uint64_t out_total,
+                               uint32_t *chunk_crc32, int32_t *chunk_status, uint32_t flags) {
+	std::unique_lock<std::mutex> lk(g_mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if (n_chunks == 0) return B2D_OK;
+	if (!in || !chunk_in_len || !block_bits || !out || !chunk_status || block_bytes < 4096 || chunk_bytes % block_bytes != 0 ||
+	    (uint64_t)n_chunks * chunk_bytes < out_total || (uint64_t)(n_chunks - 1) * chunk_bytes >= out_total)
+		return B2D_ERR_BAD_ARGUMENT;
+	const bool want_sum = (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) != 0;
+	if (want_sum && !chunk_crc32) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	const uint32_t bpc = chunk_bytes / block_bytes;
+	std::vector<uint64_t> off(n_chunks + 1, 0);
+	for (uint32_t c = 0; c < n_chunks; c++) off[c + 1] = off[c] + chunk_in_len[c];
+	const uint64_t in_total = off[n_chunks];
+	int r;
+	if ((r = ensure(g.in, in_total + 64))) return r;
+	if ((r = ensure(g.out, out_total + 64))) return r;
+	if ((r = ensure(g.bits, (size_t)n_chunks * bpc * 4))) return r;
+	if ((r = ensure(g.scratch2, inflate_units_scratch_bytes(out_total, chunk_bytes, block_bytes)))) return r;
+	const size_t m_off = 0, m_crc = (size_t)(n_chunks + 1) * 8, m_st = m_crc + (size_t)n_chunks * 4, m_total = m_st + (size_t)n_chunks * 4;
+	if ((r = ensure(g.meta, m_total))) return r;
+	if ((r = ensure_pinned_meta(m_total))) return r;
+	uint8_t *dm = (uint8_t *)g.meta.p, *hm = (uint8_t *)g.pinned_meta;
+	memcpy(hm + m_off, off.data(), (size_t)(n_chunks + 1) * 8);
+	cudaStream_t st = g.st[0];
+	CK(cudaMemcpyAsync(dm, hm, m_crc, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(g.bits.p, block_bits, (size_t)n_chunks * bpc * 4, cudaMemcpyHostToDevice, st));
+	CK(cudaMemcpyAsync(g.in.p, in, in_total, cudaMemcpyHostToDevice, st));
+	CK(launch_inflate_units((const uint8_t *)g.in.p, (const uint64_t *)(dm + m_off), n_chunks, (const uint32_t *)g.bits.p, chunk_bytes,
+	                        block_bytes, out_total, (uint8_t *)g.out.p, (int *)(dm + m_st), g.scratch2.p, st));
+	if (want_sum) {
+		if (flags & B2D_INFLATE_ADLER32) CK(launch_adler32_pieces((const uint8_t *)g.out.p, out_total, chunk_bytes, n_chunks, (uint32_t *)(dm + m_crc), st));
+		else CK(launch_crc32_pieces((const uint8_t *)g.out.p, out_total, chunk_bytes, n_chunks, (uint32_t *)(dm + m_crc), st));
+	}
+	CK(cudaMemcpyAsync(out, g.out.p, out_total, cudaMemcpyDeviceToHost, st));
+	CK(cudaMemcpyAsync(hm + m_crc, dm + m_crc, m_total - m_crc, cudaMemcpyDeviceToHost, st));
+	CK(cudaStreamSynchronize(st));
+	memcpy(chunk_status, hm + m_st, (size_t)n_chunks * 4);
+	if (want_sum) memcpy(chunk_crc32, hm + m_crc, (size_t)n_chunks * 4);
+	lk.unlock();
+	// exact outcome for chunks the parallel decode could not finish: one serial decode each
+	for (uint32_t c = 0; c < n_chunks; c++) {
+		if (chunk_status[c] == 0) continue;
+		const uint64_t io[2] = {off[c], off[c + 1]};
+		const uint64_t o0 = (uint64_t)c * chunk_bytes, oo[2] = {o0, std::min<uint64_t>(out_total, o0 + chunk_bytes)};
+		uint64_t ol = 0, ic = 0;
+		uint32_t cr = 0;
+		int32_t s2 = 0;
+		r = b2d_inflate_batch(in, io, 1, out, oo, &ol, &ic, &cr, &s2, (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) | B2D_INFLATE_CHUNK_INDEXED);
+		if (r) return r;
+		chunk_status[c] = s2 != 0 ? s2 : (ol == oo[1] - oo[0] ? 0 : B2D_UNEXPECTED_END_OF_STREAM);
+		if (want_sum) chunk_crc32[c] = cr;
+	}
+	return B2D_OK;
 }
 
 // ---------------------------------------------------------------- gzip members

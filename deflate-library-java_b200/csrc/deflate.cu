@@ -870,6 +870,12 @@ emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, 
 	}
 }
 
+// ---------------------------------------------------------------- block index for the block-parallel decoder
+__global__ void block_bits_kernel(const BlockRec *__restrict__ recs, u32 n_blocks, u32 *__restrict__ out) {
+	const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+	if (g < n_blocks) out[g] = (u32)recs[g].out_bit;       // bit offset of the block inside its chunk's output
+}
+
 // ---------------------------------------------------------------- host side
 // Worst case over all modes: a block never costs more than 9 bits per byte (the fixed code is always available to
 // the optimiser; a flat 9-bit code bounds the length-limited dynamic code) plus 3 header bits and < 384 bytes of
@@ -898,7 +904,7 @@ static bool g_attr_set = false;
 
 cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams &p, uint8_t *d_out,
                            uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
-                           void *d_scratch, size_t scratch_bytes, cudaStream_t st) {
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits) {
 	cudaError_t e;
 	if (!g_attr_set) {
 		e = cudaFuncSetAttribute(chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << HASH_BITS);
@@ -955,6 +961,7 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	scan_kernel<<<1, 1024, 0, st>>>(chunk_len, n_chunks, chunk_off, d_out_len_total, d_chunk_out_len);
 	emit_kernel<<<n_blocks, EMIT_THREADS, 0, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, n_blocks, n_chunks, recs,
 	                                               tokens, chunk_off, chunk_tail, is_last, ref_framing, d_out);
+	if (d_block_bits) block_bits_kernel<<<(n_blocks + 255) / 256, 256, 0, st>>>(recs, n_blocks, d_block_bits);
 	return cudaGetLastError();
 }
 

@@ -221,6 +221,10 @@ struct Member {
 	int pos_base;        // min(tile_g - out, 1 << 20): output position of tile[0] for the dictionary-start check
 	u32 nm;              // queued back-references (warp-uniform)
 	int tables;          // 0 none, 1 fixed tables resident
+	// block-parallel decode of our own streams (inflate_units_kernel): back-references are not resolved here but
+	// appended to a list in global memory; hist_base = output bytes of the chunk that precede this unit
+	u64 *glist;
+	u32 gcount, gcap, hist_base;
 };
 
 enum { R_EOB = 0, R_SWITCH = 1000 };
@@ -234,18 +238,17 @@ __device__ __forceinline__ void set_tile_origin(Member &m, u64 pos) {
 	m.tstart = m.tpos = mis;
 	u64 room = m.cap - pos;
 	m.tlimit = room >= (u64)(TILE - mis) ? (u32)TILE : mis + (u32)room;
-	long long rel0 = (long long)pos - (long long)mis;
+	long long rel0 = (long long)pos - (long long)mis + (long long)m.hist_base;
 	m.pos_base = rel0 > (1 << 20) ? (1 << 20) : (int)rel0;
 }
 
 // Materialises the queued back-references into the tile.  Copies replicate the pattern when dist < len exactly
 // like the reference's byte-serial loop (Open.java:596-603): byte k comes from position pos - dist + (k mod dist).
 // (All state by value: a by-reference Member would be forced into local memory by the call.)
-__device__ __noinline__ void resolve_pending(WarpSmem *sm, u8 *tile_g, int ts, u32 nm, u32 lane) {
-	u8 *tile = sm->tile;
+__device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile_g, int ts, u32 nm, u32 lane) {
 	__syncwarp();                                   // literal and queue stores of lane 0 are visible
 	const bool have = lane < nm;
-	const uint2 q = sm->mq[lane];
+	const uint2 q = mq[lane];
 	const int off = (int)(q.x & 0xFFFFu), len = (int)(q.x >> 16), dist = (int)q.y;
 	const int s = off - dist;                        // tile index of the source start (may be negative)
 	const bool far = have && (s + len <= ts);        // source lies wholly in global memory (already flushed)
@@ -300,7 +303,7 @@ __device__ __noinline__ void resolve_pending(WarpSmem *sm, u8 *tile_g, int ts, u
 }
 
 __device__ __forceinline__ void resolve(Member &m, WarpSmem *sm, u32 lane) {
-	resolve_pending(sm, m.tile_g, (int)m.tstart, m.nm, lane);
+	resolve_pending(sm->tile, sm->mq, m.tile_g, (int)m.tstart, m.nm, lane);
 	m.nm = 0;
 }
 
@@ -331,7 +334,7 @@ __device__ __forceinline__ void flush_tile(Member &m, WarpSmem *sm, u32 lane) {
 // (a whole symbol is at most 48 bits, read from bit offset <= 31), so no read can pass the end of input and the
 // end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the reference's
 // order (Open.java:565-593).
-template <bool CAREFUL>
+template <bool CAREFUL, bool DEFER>
 __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 lane) {
 	BitIn &b = m.in;
 	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;
@@ -417,6 +420,13 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 		sh += d & 31;
 		if ((int)dist > pos_base + (int)tpos) { ret = B2D_COPY_FROM_BEFORE_DICTIONARY_START; break; }   // Open.java:592-593
 		if (tpos + len + (CAREFUL ? 0u : LIT_GUARD) <= tlimit) {   // common case: the whole reference fits the tile
+			if (DEFER) {                                     // record only: (unit-relative position, length, distance)
+				if (m.gcount >= m.gcap) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
+				const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
+				m.glist[m.gcount++] = upos | (u64)len << 24 | (u64)dist << 40;
+				tpos += len;
+				continue;
+			}
 			sm->mq[nm] = make_uint2(tpos | len << 16, dist);     // same value from every lane: one broadcast write
 			tpos += len;
 			if (++nm == 32) {
@@ -433,8 +443,14 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 			const u32 fit = tlimit - tpos;
 			const u32 take = len < fit ? len : fit;
 			if (take) {
-				if (lane == 0) sm->mq[nm] = make_uint2(tpos | take << 16, dist);
-				nm++;
+				if (DEFER) {
+					if (m.gcount >= m.gcap) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
+					const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
+					m.glist[m.gcount++] = upos | (u64)take << 24 | (u64)dist << 40;
+				} else {
+					if (lane == 0) sm->mq[nm] = make_uint2(tpos | take << 16, dist);
+					nm++;
+				}
 				tpos += take;
 				len -= take;
 			}
@@ -642,6 +658,8 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	m.out = out + o0;
 	m.cap = o1 - o0;
 	m.nm = 0;
+	m.glist = nullptr;
+	m.gcount = m.gcap = m.hist_base = 0;
 	set_tile_origin(m, 0);
 	m.tables = 0;
 
@@ -668,9 +686,9 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 		int r = R_SWITCH;
 #else
 		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false>(m, sm, lane) : (int)R_SWITCH;
+		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false, false>(m, sm, lane) : (int)R_SWITCH;
 #endif
-		if (r == R_SWITCH) r = decode_block<true>(m, sm, lane);
+		if (r == R_SWITCH) r = decode_block<true, false>(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);                                               // also resolves what is pending
@@ -679,6 +697,169 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 		in_consumed[mi] = (consumed_bits(m.in) + 7) >> 3;                  // Open.finish, Open.java:113-124
 		status[mi] = err;
 	}
+}
+
+// ---------------------------------------------------------------- block-parallel decode of our own streams
+// A stream made by b2d_deflate_chunks comes with the bit offset of every DEFLATE block inside its chunk.  The Huffman
+// decode -- the serial, expensive part -- then runs with one warp per BLOCK (16 times the units of the chunk index)
+// without resolving any back-reference (a block's references reach up to 32 KiB into the previous block, which
+// another warp is still producing): phase A writes the literals to their final places and lists the references;
+// phase B, one warp per chunk, replays the lists in stream order, 32 references and a staged region of output at
+// a time, with the same machinery the member decoder uses (resolve_pending).
+constexpr int UNIT_TILE = 4096;                    // bytes of output staged per warp in phase B
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in_off, const u32 *__restrict__ block_bits,
+                     u32 n_units, u32 bpc, u32 chunk_bytes, u32 block_bytes, u64 out_total, u8 *out,
+                     u64 *__restrict__ glist, u32 gcap, u32 *__restrict__ gcount, int *__restrict__ ustatus) {
+	__shared__ WarpSmem smem[WARPS_PER_CTA];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 u = blockIdx.x * WARPS_PER_CTA + warp;
+	if (u >= n_units) return;
+	WarpSmem *sm = &smem[warp];
+	const u32 c = u / bpc, bi = u % bpc;
+	const u64 pos0 = (u64)c * chunk_bytes + (u64)bi * block_bytes;
+	if (pos0 >= out_total) { if (lane == 0) { gcount[u] = 0; ustatus[u] = 0; } return; }
+	const u64 expect = min((u64)block_bytes, out_total - pos0);
+
+	Member m;
+	const u64 i0 = chunk_in_off[c], i1 = chunk_in_off[c + 1];
+	const u8 *src = in + i0;
+	const u32 lead = (u32)((uintptr_t)src & 3);
+	const u64 in_len = i1 - i0;
+	m.in.words = (const u32 *)(src - lead);
+	m.in.lead8 = lead * 8;
+	m.in.total_bits = in_len * 8;
+	m.in.n_safe = (u32)((lead + in_len + 3) >> 2);
+	m.in.n_full = (u32)((lead + in_len) >> 2);
+	const u32 bit0 = block_bits[u];
+	bit_seek(m.in, bit0 >> 3);
+	m.in.sh += bit0 & 7;
+	m.out = out + pos0;
+	m.cap = expect;
+	m.nm = 0;
+	m.glist = glist + (u64)u * gcap;
+	m.gcount = 0;
+	m.gcap = gcap;
+	m.hist_base = bi * block_bytes;
+	set_tile_origin(m, 0);
+	m.tables = 0;
+
+	int err = 0;
+	while (out_pos(m) < expect) {
+		norm(m.in);
+		int avail = avail_bits(m.in);
+		(void)getbits(m.in, 1, avail, err);                                 // BFINAL is only set on the stream's closing marker
+		int type = getbits(m.in, 2, avail, err);
+		if (err) break;
+		if (type == 0) {
+			err = stored_block(m, sm, avail, lane);
+			if (err) break;
+			continue;
+		}
+		if (type == 3) { err = B2D_RESERVED_BLOCK_TYPE; break; }
+		if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
+		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
+		norm(m.in);
+		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
+		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false, true>(m, sm, lane) : (int)R_SWITCH;
+		if (r == R_SWITCH) r = decode_block<true, true>(m, sm, lane);
+		if (r != R_EOB) { err = r; break; }
+	}
+	flush_tile(m, sm, lane);
+	if (err == 0 && out_pos(m) != expect) err = B2D_ERR_OUTPUT_OVERFLOW;
+	if (lane == 0) { gcount[u] = m.gcount; ustatus[u] = err; }
+}
+
+struct ResolveSmem {
+	__align__(16) u8 tile[UNIT_TILE];
+	uint2 mq[32];
+};
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32 *__restrict__ gcount,
+                     const int *__restrict__ ustatus, u32 n_chunks, u32 bpc, u32 chunk_bytes, u32 block_bytes, u64 out_total,
+                     int *__restrict__ cstatus) {
+	__shared__ ResolveSmem smem[WARPS_PER_CTA];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 c = blockIdx.x * WARPS_PER_CTA + warp;
+	if (c >= n_chunks) return;
+	ResolveSmem *sm = &smem[warp];
+	int err = 0;
+	for (u32 bi = 0; bi < bpc && err == 0; bi++) {
+		const u32 u = c * bpc + bi;
+		const u64 pos0 = (u64)c * chunk_bytes + (u64)bi * block_bytes;
+		if (pos0 >= out_total) break;
+		err = ustatus[u];
+		if (err) break;                                  // the caller re-decodes this chunk serially for the exact outcome
+		u8 *ubase = out + pos0;
+		const u64 *list = glist + (u64)u * gcap;
+		const u32 n = gcount[u];
+		for (u32 k = 0; k < n;) {
+			const u64 rec = k + lane < n ? list[k + lane] : 0;
+			const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF, dist = (u32)(rec >> 40);
+			const u32 first = __shfl_sync(FULL_MASK, pos, 0);
+			u8 *g0 = ubase + first;
+			const u32 mis = (u32)((uintptr_t)g0 & 15);
+			// as many references as fit the staged region (a single one always does: <= 258 bytes)
+			const bool fits = k + lane < n && (pos + len - first) + mis <= (u32)UNIT_TILE;
+			const u32 okmask = __ballot_sync(FULL_MASK, fits);
+			const u32 cnt = okmask == 0xFFFFFFFFu ? 32u : (u32)(__ffs(~okmask) - 1);
+			const u32 last_end = __shfl_sync(FULL_MASK, pos + len, cnt - 1);
+			const u32 hi = mis + (last_end - first);     // staged: tile[mis, hi) <-> g0 - mis + [mis, hi)
+			u8 *tile_g = g0 - mis;
+			// stage the region (literals are final, reference bytes are holes that get filled now)
+			__syncwarp();
+			{
+				const u32 a = (mis + 15) & ~15u, b = hi & ~15u;
+				if (a >= b) {
+					for (u32 i = mis + lane; i < hi; i += 32) sm->tile[i] = tile_g[i];
+				} else {
+					if (mis + lane < a) sm->tile[mis + lane] = tile_g[mis + lane];
+					for (u32 v = (a >> 4) + lane; v < (b >> 4); v += 32) ((uint4 *)sm->tile)[v] = ((const uint4 *)tile_g)[v];
+					if (b + lane < hi) sm->tile[b + lane] = tile_g[b + lane];
+				}
+			}
+			sm->mq[lane] = make_uint2((mis + (pos - first)) | len << 16, dist);
+			resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane);
+			store_tile(sm->tile, tile_g, mis, hi, lane);
+			k += cnt;
+		}
+	}
+	if (lane == 0) cstatus[c] = err;
+}
+
+size_t inflate_units_scratch_bytes(uint64_t out_total, uint32_t chunk_bytes, uint32_t block_bytes) {
+	const u64 n_chunks = (out_total + chunk_bytes - 1) / chunk_bytes;
+	const u64 n_units = n_chunks * (chunk_bytes / block_bytes);
+	const u64 gcap = block_bytes / 3 + 8;
+	return (size_t)(n_units * gcap * 8 + n_units * 8 + 1024);
+}
+
+cudaError_t launch_inflate_units(const u8 *d_in, const u64 *d_chunk_in_off, u32 n_chunks, const u32 *d_block_bits,
+                                 u32 chunk_bytes, u32 block_bytes, u64 out_total, u8 *d_out, int *d_chunk_status,
+                                 void *d_scratch, cudaStream_t st) {
+	if (n_chunks == 0) return cudaSuccess;
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(inflate_units_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+		                                     cudaSharedmemCarveoutMaxShared);
+		if (e != cudaSuccess) return e;
+		attr_set = true;
+	}
+	const u32 bpc = chunk_bytes / block_bytes;
+	const u32 n_units = n_chunks * bpc;
+	const u32 gcap = block_bytes / 3 + 8;
+	u64 *glist = (u64 *)d_scratch;
+	u32 *gcount = (u32 *)(glist + (u64)n_units * gcap);
+	int *ustatus = (int *)(gcount + n_units);
+	inflate_units_kernel<<<(n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st>>>(
+		d_in, d_chunk_in_off, d_block_bits, n_units, bpc, chunk_bytes, block_bytes, out_total, d_out, glist, gcap, gcount, ustatus);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return e;
+	resolve_units_kernel<<<(n_chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st>>>(
+		d_out, glist, gcap, gcount, ustatus, n_chunks, bpc, chunk_bytes, block_bytes, out_total, d_chunk_status);
+	return cudaGetLastError();
 }
 
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,

@@ -11,6 +11,14 @@ cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
                            int *d_status, uint32_t flags, cudaStream_t st);
 
+// block-parallel decode of a b2d_deflate_chunks stream (inflate.cu): chunk c occupies d_in[off[c], off[c+1]) and decodes
+// to d_out[c * chunk_bytes ...); d_block_bits as produced by launch_deflate; d_chunk_status = 0 or the first failing
+// block's status (such chunks are to be re-decoded serially for the exact outcome)
+size_t inflate_units_scratch_bytes(uint64_t out_total, uint32_t chunk_bytes, uint32_t block_bytes);
+cudaError_t launch_inflate_units(const uint8_t *d_in, const uint64_t *d_chunk_in_off, uint32_t n_chunks,
+                                 const uint32_t *d_block_bits, uint32_t chunk_bytes, uint32_t block_bytes,
+                                 uint64_t out_total, uint8_t *d_out, int *d_chunk_status, void *d_scratch, cudaStream_t st);
+
 // crc32.cu
 // CRC-32 of n_seg independent segments: segment i = data[off[i], off[i] + len[i])  (len from d_len, u64)
 cudaError_t launch_crc32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
@@ -41,6 +49,8 @@ uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t blo
 size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p);
 cudaError_t launch_deflate(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out,
                            uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
-                           void *d_scratch, size_t scratch_bytes, cudaStream_t st);
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits = nullptr);
+// d_block_bits (optional): bit offset of every block inside its chunk's output, one entry per block (the restart index
+// of the block-parallel decoder); only meaningful with chunked framing.
 
 }  // namespace b2d

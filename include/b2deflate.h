@@ -183,6 +183,28 @@ int b2d_deflate_chunks_dev(const uint8_t *d_in, uint64_t in_len, const b2d_defla
                            uint8_t *d_out, uint64_t out_cap, uint64_t *d_out_len_total,
                            uint64_t *d_chunk_out_len, uint32_t *d_chunk_crc32, void *stream);
 
+/* ---- block-indexed streams: the same stream as b2d_deflate_chunks, plus the bit offset of every DEFLATE block inside
+ *      its chunk (one uint32 per block_bytes of input).  With it the decoder runs one warp per BLOCK (16 x the units of
+ *      the chunk index): Huffman decode of all blocks in parallel, back-references replayed per chunk afterwards.  There
+ *      is no reference counterpart (DeflaterOutputStream.java:119-137 / Open.java:83-110 are sequential); the stream itself
+ *      stays one valid DEFLATE stream for the reference's decoder. ---- */
+int64_t b2d_deflate_chunks_indexed(const uint8_t *in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *out,
+                                   uint64_t out_cap, uint32_t *crc32_inout, uint64_t *chunk_out_len,
+                                   uint32_t *block_bits /* ceil(in_len / block_bytes) entries */);
+int b2d_deflate_chunks_indexed_dev(const uint8_t *d_in, uint64_t in_len, const b2d_deflate_opts *opts, uint8_t *d_out,
+                                   uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
+                                   uint32_t *d_chunk_crc32, uint32_t *d_block_bits, void *stream);
+/* Chunk c occupies chunk_in_len[c] bytes of `in` (back to back) and decodes to out[c * chunk_bytes, ...); out_total is the
+ * exact decompressed size.  chunk_status[c] = 0 or 1 + Reason.ordinal(); the host form re-decodes a failing chunk
+ * sequentially so that status and bytes are the sequential decoder's.  flags: B2D_INFLATE_CRC32 / _ADLER32 fill
+ * chunk_crc32[] with per-chunk checksums (fold them with b2d_crc32_combine / b2d_adler32_combine). */
+int b2d_inflate_chunks(const uint8_t *in, const uint64_t *chunk_in_len, uint32_t n_chunks, const uint32_t *block_bits,
+                       uint32_t chunk_bytes, uint32_t block_bytes, uint8_t *out, uint64_t out_total,
+                       uint32_t *chunk_crc32, int32_t *chunk_status, uint32_t flags);
+int b2d_inflate_chunks_dev(const uint8_t *d_in, const uint64_t *d_chunk_in_off /* n_chunks + 1 */, uint32_t n_chunks,
+                           const uint32_t *d_block_bits, uint32_t chunk_bytes, uint32_t block_bytes, uint64_t out_total,
+                           uint8_t *d_out, uint32_t *d_chunk_crc32, int32_t *d_chunk_status, uint32_t flags, void *stream);
+
 /* ---- CRC-32: replaces java.util.zip.CRC32 at GzipOutputStream.java:25,57 / GzipInputStream.java:32,72 ---- */
 int b2d_crc32_update(const uint8_t *data, uint64_t len, uint32_t *crc_inout);    /* host pointer, computed on the GPU; B2D_OK or B2D_ERR_* */
 uint32_t b2d_crc32(uint32_t crc, const uint8_t *data, uint64_t len);            /* convenience: on failure the value is returned

@@ -157,3 +157,56 @@ def test_crc32(b2d):
         assert b2d.crc32(d, 0x12345678) == zlib.crc32(d, 0x12345678), n
     d = np.frombuffer(rng.randbytes(100003), np.uint8)
     assert b2d.crc32(d[3:]) == zlib.crc32(d[3:].tobytes())       # unaligned start
+
+
+def _indexed_roundtrip(b2d, data, opts):
+    comp, crc, sizes, bits = b2d.deflate_chunks_indexed(data, opts, crc=0)
+    plain = b2d.deflate_chunks(data, opts)
+    assert np.array_equal(comp, plain)                             # the same stream, just with the block index beside it
+    cb, bb = opts.chunk_bytes or (1 << 20), opts.block_bytes or (1 << 16)
+    out, crcs, st = b2d.inflate_chunks(comp, sizes, bits, len(data), cb, bb)
+    assert not st.any(), [b2d.status_name(int(s)) for s in st[st != 0][:4]]
+    assert out.tobytes() == bytes(data)
+    c = 0
+    for i in range(len(sizes)):
+        c = b2d.crc32_combine(c, int(crcs[i]), min(cb, len(data) - i * cb))
+    assert c == crc == zlib.crc32(bytes(data))
+    return comp, sizes, bits
+
+
+@pytest.mark.parametrize("n", [1, 100, 65535, 65536, 65537, 200000, (1 << 20) - 1, 1 << 20, (1 << 20) + 1, 5 * (1 << 20) + 4321])
+def test_block_indexed_roundtrip_sizes(b2d, n):
+    rng = random.Random(n)
+    _indexed_roundtrip(b2d, _text(rng, n), b2d.make_opts())
+
+
+@pytest.mark.parametrize("kind,mode", [("mixed", 0), ("random", 0), ("zeros", 0), ("text", 2), ("text", 1), ("mixed", 3)])
+def test_block_indexed_roundtrip_corpora(b2d, kind, mode):
+    n = (6 << 20) + 777
+    data = bytes(n) if kind == "zeros" else b2d.corpus(kind, 0xDEF1A7E, n).tobytes()
+    _indexed_roundtrip(b2d, data, b2d.make_opts(mode=mode))
+    _indexed_roundtrip(b2d, data[:(1 << 20) + 99], b2d.make_opts(mode=mode, chunk_bytes=1 << 17, block_bytes=1 << 14))
+
+
+def test_block_indexed_failures_fall_back_to_the_sequential_outcome(b2d, oracle):
+    data = b2d.corpus("text", 11, 3 << 20).tobytes()
+    comp, sizes, bits = _indexed_roundtrip(b2d, data, b2d.make_opts())
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    # a wrong block offset: the parallel decode of that chunk stumbles, the sequential re-decode does not need the index
+    bad_bits = bits.copy()
+    bad_bits[16 + 5] += 3
+    out, crcs, st = b2d.inflate_chunks(comp, sizes, bad_bits, len(data))
+    assert not st.any() and out.tobytes() == data
+    # a corrupted chunk: its status and delivered bytes are what the sequential decoder reports; the others are intact
+    bad = comp.copy()
+    bad[int(offs[1]) + int(sizes[1]) // 2] ^= 0x55
+    out, crcs, st = b2d.inflate_chunks(bad, sizes, bits, len(data))
+    assert st[0] == 0 and st[2] == 0 and out[:1 << 20].tobytes() == data[:1 << 20] and out[2 << 20:].tobytes() == data[2 << 20:]
+    chunk = bad[int(offs[1]):int(offs[2])].tobytes()
+    ost, oout, _ = oracle.inflate(chunk, out_cap=1 << 20)
+    if ost == 0 and len(oout) == 1 << 20:                              # the flip happened to stay decodable: bytes differ, CRC tells
+        assert int(crcs[1]) != zlib.crc32(data[1 << 20:2 << 20])
+    else:
+        assert int(st[1]) != 0
+        if ost > 0:
+            assert int(st[1]) == ost
