@@ -18,8 +18,10 @@ def run(kind, mode=0):
     nc = n // CH
     d_clen = torch.zeros(nc, dtype=torch.int64, device=dev); d_crc = torch.zeros(nc, dtype=torch.int32, device=dev)
     opts = b2d.make_opts(mode=mode, chunk_bytes=CH)
+    nb = n // 65536
+    d_bits = torch.zeros(nb, dtype=torch.int32, device=dev)
     def deflate():
-        assert L.b2d_deflate_chunks_dev(d_in.data_ptr(), n, ctypes.byref(opts), d_out.data_ptr(), bound, d_total.data_ptr(), d_clen.data_ptr(), d_crc.data_ptr(), sp) == 0
+        assert L.b2d_deflate_chunks_indexed_dev(d_in.data_ptr(), n, ctypes.byref(opts), d_out.data_ptr(), bound, d_total.data_ptr(), d_clen.data_ptr(), d_crc.data_ptr(), d_bits.data_ptr(), sp) == 0
     for _ in range(2): deflate()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -37,6 +39,14 @@ def run(kind, mode=0):
     assert int(st.abs().sum()) == 0 and torch.equal(d_dec, d_in)
     e0.record(); [inflate() for _ in range(3)]; e1.record(); torch.cuda.synchronize()
     ti = e0.elapsed_time(e1) / 3
-    print(f"{kind:7s} mode={mode} ratio {n / comp:9.2f}  deflate {td:8.2f} ms = {n / td / 1e6:7.2f} GB/s   inflate ({nc} x 1 MiB chunks) {ti:8.2f} ms = {n / ti / 1e6:7.2f} GB/s", flush=True)
+    d_dec.zero_(); cst = torch.zeros(nc, dtype=torch.int32, device=dev)
+    def inflate_blocks():
+        assert L.b2d_inflate_chunks_dev(d_out.data_ptr(), coff.data_ptr(), nc, d_bits.data_ptr(), CH, 65536, n, d_dec.data_ptr(), c2.data_ptr(), cst.data_ptr(), 1, sp) == 0
+    for _ in range(2): inflate_blocks()
+    torch.cuda.synchronize()
+    assert int(cst.abs().sum()) == 0 and torch.equal(d_dec, d_in) and torch.equal(c2, d_crc)
+    e0.record(); [inflate_blocks() for _ in range(3)]; e1.record(); torch.cuda.synchronize()
+    tb = e0.elapsed_time(e1) / 3
+    print(f"{kind:7s} mode={mode} ratio {n / comp:9.2f}  deflate {td:8.2f} ms = {n / td / 1e6:7.2f} GB/s   inflate ({nc} x 1 MiB chunks) {ti:8.2f} ms = {n / ti / 1e6:7.2f} GB/s   block-indexed {tb:8.2f} ms = {n / tb / 1e6:7.2f} GB/s", flush=True)
 for kind, mode in ((('mixed', 0), ('text', 0)) if len(sys.argv) > 2 else (('mixed', 0), ('text', 0), ('random', 0), ('zeros', 0), ('text', 2))):
     run(kind, mode)
