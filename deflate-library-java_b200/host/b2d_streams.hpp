@@ -183,6 +183,8 @@ struct PinnedBuffer {                       // staging memory from b2d_alloc_pin
 struct ChunkIndex {
 	uint32_t chunk_bytes = 0;                // uncompressed bytes per chunk (the last may be shorter)
 	std::vector<uint64_t> sizes;             // compressed bytes per chunk
+	uint32_t block_bytes = 0;                // optional restart index: bit offset of every block_bytes-block inside its chunk
+	std::vector<uint32_t> block_bits;
 	bool empty() const { return sizes.empty(); }
 };
 
@@ -286,8 +288,37 @@ private:
 		}
 	}
 
+	// chunk sizes + block offsets + exact size known: every block gets its own warp (b2d_inflate_chunks)
+	bool decodeBlocks(PinnedBuffer &pin, PinnedBuffer &pout, size_t in_len) {
+		const uint32_t n = (uint32_t)index.sizes.size();
+		if (index.block_bytes == 0 || sizeHint == 0 || index.chunk_bytes % index.block_bytes != 0) return false;
+		const uint64_t bpc = index.chunk_bytes / index.block_bytes;
+		if (index.block_bits.size() != (size_t)n * bpc) return false;
+		if ((uint64_t)n * index.chunk_bytes < sizeHint || (uint64_t)(n - 1) * index.chunk_bytes >= sizeHint) return false;
+		uint64_t total_in = 0;
+		for (uint64_t sz : index.sizes) total_in += sz;
+		if (total_in > in_len) return false;
+		pout.reserve(sizeHint + 64);
+		std::vector<uint32_t> crcs(n);
+		std::vector<int32_t> st(n);
+		int rc = b2d_inflate_chunks(pin.p, index.sizes.data(), n, index.block_bits.data(), index.chunk_bytes, index.block_bytes,
+		                            pout.p, sizeHint, crcs.data(), st.data(), adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32);
+		if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_chunks: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
+		for (uint32_t i = 0; i < n; i++) if (st[i] != 0) return false;      // let the chunk-indexed path report the exact outcome
+		out.assign(pout.p, pout.p + sizeHint);
+		crc = adler ? 1 : 0;
+		for (uint32_t i = 0; i < n; i++) {
+			const uint64_t len = std::min<uint64_t>(index.chunk_bytes, sizeHint - (uint64_t)i * index.chunk_bytes);
+			crc = adler ? b2d_adler32_combine(crc, crcs[i], len) : b2d_crc32_combine(crc, crcs[i], len);
+		}
+		consumed = total_in;
+		status = 0;
+		return true;
+	}
+
 	void decodeIndexed(PinnedBuffer &pin, PinnedBuffer &pout, size_t in_len) {
 		const uint32_t n = (uint32_t)index.sizes.size();
+		if (decodeBlocks(pin, pout, in_len)) return;
 		std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0), out_len(n), cons(n);
 		std::vector<uint32_t> crcs(n);
 		std::vector<int32_t> st(n);
@@ -389,9 +420,16 @@ private:
 		stage.reserve(1);
 		const size_t n_chunks = (size_t)((fill + opt.chunk_bytes - 1) / opt.chunk_bytes);
 		std::vector<uint64_t> sizes(std::max<size_t>(n_chunks, 1));
-		int64_t n = b2d_deflate_chunks(stage.p, fill, &o, comp.p, bound, &crc, sizes.data());
+		const size_t n_blocks = (size_t)((fill + opt.block_bytes - 1) / opt.block_bytes);
+		std::vector<uint32_t> bits(std::max<size_t>(n_blocks, 1));
+		int64_t n = b2d_deflate_chunks_indexed(stage.p, fill, &o, comp.p, bound, &crc, sizes.data(), bits.data());
 		if (n < 0) throw IOException(std::string("b2d_deflate_chunks: ") + b2d_strerror((int)n) + " [" + b2d_last_error() + "]");
 		index.chunk_bytes = opt.chunk_bytes;
+		index.block_bytes = opt.block_bytes;
+		// a batch is a whole number of chunks (except the last), so block entries stay chunk-aligned across batches
+		const size_t bpc = opt.chunk_bytes / opt.block_bytes;
+		for (size_t c = 0; c < n_chunks; c++)
+			for (size_t b = 0; b < bpc; b++) index.block_bits.push_back(c * bpc + b < n_blocks ? bits[c * bpc + b] : 0u);
 		if (n_chunks) index.sizes.insert(index.sizes.end(), sizes.begin(), sizes.begin() + n_chunks);
 		else if (n > 0) {                                 // empty final call: the 5-byte closing block joins the previous chunk
 			if (index.sizes.empty()) index.sizes.push_back((uint64_t)n); else index.sizes.back() += (uint64_t)n;
@@ -512,6 +550,8 @@ struct GzipMetadata {
 
 	// FEXTRA subfield "B2" (RFC 1952 2.3.1.1): u32 chunk_bytes, then one u32 compressed size per chunk.  The reference
 	// parses and ignores extra fields (GzipMetadata.java:116-122), so files carrying it stay readable by it.
+	// A second subfield "B3" (u32 block_bytes, one u32 bit offset per block) follows when both still fit 64 KiB: with it
+	// gunzip decodes every block on its own warp.
 	static std::optional<std::vector<uint8_t>> encodeChunkIndex(const ChunkIndex &idx) {
 		size_t bytes = 4 + 4 + 4 * idx.sizes.size();
 		if (idx.empty() || bytes > 0xFFFF) return std::nullopt;
@@ -520,6 +560,12 @@ struct GzipMetadata {
 		auto put32 = [&](uint32_t v) { for (int i = 0; i < 4; i++) x.push_back((uint8_t)(v >> (8 * i))); };
 		put32(idx.chunk_bytes);
 		for (uint64_t s : idx.sizes) put32((uint32_t)s);
+		const size_t b3 = 4 + 4 + 4 * idx.block_bits.size();
+		if (idx.block_bytes && !idx.block_bits.empty() && b3 - 4 <= 0xFFFF && x.size() + b3 <= 0xFFFF) {
+			x.push_back('B'); x.push_back('3'); x.push_back((uint8_t)((b3 - 4) & 0xFF)); x.push_back((uint8_t)((b3 - 4) >> 8));
+			put32(idx.block_bytes);
+			for (uint32_t v : idx.block_bits) put32(v);
+		}
 		return x;
 	}
 	ChunkIndex chunkIndex() const {
@@ -529,15 +575,18 @@ struct GzipMetadata {
 		for (size_t p = 0; p + 4 <= x.size();) {
 			size_t len = x[p + 2] | (size_t)x[p + 3] << 8;
 			if (p + 4 + len > x.size()) break;
-			if (x[p] == 'B' && x[p + 1] == '2' && len >= 4 && len % 4 == 0) {
-				auto get32 = [&](size_t q) { return (uint32_t)x[q] | (uint32_t)x[q + 1] << 8 | (uint32_t)x[q + 2] << 16 | (uint32_t)x[q + 3] << 24; };
+			auto get32 = [&](size_t q) { return (uint32_t)x[q] | (uint32_t)x[q + 1] << 8 | (uint32_t)x[q + 2] << 16 | (uint32_t)x[q + 3] << 24; };
+			if (x[p] == 'B' && x[p + 1] == '2' && len >= 4 && len % 4 == 0 && idx.sizes.empty()) {
 				idx.chunk_bytes = get32(p + 4);
 				for (size_t q = p + 8; q < p + 4 + len; q += 4) idx.sizes.push_back(get32(q));
 				if (idx.chunk_bytes == 0) idx.sizes.clear();
-				return idx;
+			} else if (x[p] == 'B' && x[p + 1] == '3' && len >= 4 && len % 4 == 0) {
+				idx.block_bytes = get32(p + 4);
+				for (size_t q = p + 8; q < p + 4 + len; q += 4) idx.block_bits.push_back(get32(q));
 			}
 			p += 4 + len;
 		}
+		if (idx.sizes.empty()) { idx.block_bytes = 0; idx.block_bits.clear(); }
 		return idx;
 	}
 };

@@ -40,6 +40,10 @@ def test_cli_roundtrip_and_interop(b2d, oracle, tmp_path, kind, n, index):
     # header as gzip.java writes it: FNAME + FHCRC (+ FEXTRA with the chunk index), OS = Unix
     assert member[:3] == b"\x1f\x8b\x08" and member[9] == 3
     assert member[3] & 0x0A == 0x0A and bool(member[3] & 4) == (index == "1")
+    if index == "1" and n > 0:                                   # chunk sizes ("B2") and block bit offsets ("B3") in FEXTRA
+        xlen = member[10] | member[11] << 8
+        extra = member[12:12 + xlen]
+        assert extra[:2] == b"B2" and b"B3" in extra
     r = run(GUNZIP, str(gz), str(back))
     assert r.returncode == 0, r.stderr
     assert back.read_bytes() == data
