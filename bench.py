@@ -453,11 +453,13 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
     d_ccrc = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
     opts = b2d.make_opts(chunk_bytes=CHUNK_BYTES, block_bytes=65536, mode=b2d.MODE_AUTO, is_last=int(rank == world - 1))
 
+    d_bits = torch.zeros(n_bytes // 65536, dtype=torch.int32, device=dev)     # restart index: bit offset of every block
+
     def deflate_dev():
-        r = L.b2d_deflate_chunks_dev(d_in.data_ptr(), n_bytes, ctypes.byref(opts), d_out.data_ptr(), bound,
-                                     d_total.data_ptr(), d_clen.data_ptr(), d_ccrc.data_ptr(), sp)
+        r = L.b2d_deflate_chunks_indexed_dev(d_in.data_ptr(), n_bytes, ctypes.byref(opts), d_out.data_ptr(), bound,
+                                             d_total.data_ptr(), d_clen.data_ptr(), d_ccrc.data_ptr(), d_bits.data_ptr(), sp)
         if r != 0:
-            raise RuntimeError(f"b2d_deflate_chunks_dev: {b2d.status_name(r)}")
+            raise RuntimeError(f"b2d_deflate_chunks_indexed_dev: {b2d.status_name(r)}")
 
     for _ in range(3):
         deflate_dev()
@@ -482,6 +484,19 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
     torch.cuda.synchronize()
     # configs[3]'s decompress direction: the chunk-indexed stream decoded with one warp per 1 MiB chunk
     unchunk_s = timed(inflate_chunks, max(3, args.steps // 2)) / max(3, args.steps // 2)
+    # ... and with the block index: one warp per 64 KiB block, references replayed per chunk afterwards
+    d_dec.zero_()
+    d_cst = torch.zeros(n_chunks, dtype=torch.int32, device=dev)
+
+    def inflate_blocks():
+        r = L.b2d_inflate_chunks_dev(d_out.data_ptr(), d_coff.data_ptr(), n_chunks, d_bits.data_ptr(), CHUNK_BYTES, 65536,
+                                     n_bytes, d_dec.data_ptr(), d_c2.data_ptr(), d_cst.data_ptr(), b2d.INFLATE_CRC32, sp)
+        assert r == 0
+    for _ in range(3):
+        inflate_blocks()
+    torch.cuda.synchronize()
+    assert int(d_cst.abs().sum().item()) == 0 and torch.equal(d_dec, d_in) and torch.equal(d_c2, d_ccrc), "block-indexed decode differs"
+    unblock_s = timed(inflate_blocks, max(3, args.steps // 2)) / max(3, args.steps // 2)
     assert int(d_st.abs().sum().item()) == 0 and torch.equal(d_dec, d_in), "deflate: GPU round trip differs"
     assert torch.equal(d_c2, d_ccrc), "deflate: chunk CRCs differ from the CRCs of the decoded chunks"
     h_comp = d_out[:comp_len].cpu().numpy()
@@ -544,9 +559,10 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         "compressed_bytes_per_gpu": comp_len, "ratio": round(n_bytes / comp_len, 4),
         "e2e": {"value": round(total_in / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n_bytes,
                 "d2h_bytes_per_step": comp_len + n_chunks * 12 + 8, "ms_per_step": round(e2e_s * 1e3, 3)},
-        # chains, match, parse, huffman, layout, scan, emit, crc32 (+ one cudaMemsetAsync, not ours) per call
-        "gpu_launches_per_step": 8,
-        "gpu_launches": 8 * args.steps + 2 * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 512)) * e2e_steps,
+        # chains, match, parse, huffman, layout, scan, emit, block_bits, crc32 (+ one cudaMemsetAsync, not ours) per call
+        "gpu_launches_per_step": 9,
+        # deflate steps (+ block_bits_kernel), chunk-indexed decode (inflate + crc32), block-indexed decode (units + resolve + crc32), e2e
+        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 512)) * e2e_steps,
         "roofline": {"bound": "hbm", "achieved": round((n_bytes + comp_len) / step_s / 1e9, 2), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round((n_bytes + comp_len) / step_s / 1e9 / hbm_peak, 5),
                      "note": "whole pipeline (8 kernels + memset); algorithmic bytes = input read + compressed written"},
@@ -554,6 +570,9 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         "inflate_chunk_indexed": {"value": round(sum_over_ranks(float(n_bytes)) / unchunk_s / 1e9, 3), "unit": "GB/s",
                                   "ms_per_step": round(unchunk_s * 1e3, 3),
                                   "note": f"decode of this stream, one warp per 1 MiB chunk ({n_chunks} units per GPU: latency-bound below ~4096 units)"},
+        "inflate_block_indexed": {"value": round(sum_over_ranks(float(n_bytes)) / unblock_s / 1e9, 3), "unit": "GB/s",
+                                  "ms_per_step": round(unblock_s * 1e3, 3),
+                                  "note": "b2d_inflate_chunks_dev: one warp per 64 KiB block (Huffman decode), then one warp per chunk replays the back-references"},
     }
 
     def cpu(O, cores):
