@@ -166,8 +166,24 @@ def corpus(kind, seed, n):
     return out
 
 
+class PinnedBuffer:
+    """Page-locked host memory from b2d_alloc_pinned as a numpy u8 array (`.array`); freed with the object.  Handing
+    such a buffer to b2d_inflate_batch as the output lets the kernel deliver the bytes itself (no D2H copy)."""
+
+    def __init__(self, n):
+        self._p = lib().b2d_alloc_pinned(max(int(n), 1))
+        if not self._p:
+            raise B2dError(-5, "b2d_alloc_pinned")
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * max(int(n), 1)).from_address(self._p))
+
+    def __del__(self):
+        if getattr(self, "_p", None):
+            lib().b2d_free_pinned(self._p)
+            self._p = None
+
+
 # ---- host-pointer entry points ----
-def inflate_batch(members, out_caps, flags=0):
+def inflate_batch(members, out_caps, flags=0, out=None):
     """members: list of bytes-like raw-DEFLATE members; out_caps: int or list of output capacities.
     -> (outputs list[bytes], out_len, in_consumed, crc32, status) with numpy arrays for the last four."""
     n = len(members)
@@ -179,7 +195,7 @@ def inflate_batch(members, out_caps, flags=0):
         in_off[i + 1] = in_off[i] + np.uint64(len(m))
         out_off[i + 1] = out_off[i] + np.uint64(out_caps[i])
     blob = np.frombuffer(b"".join(bytes(m) for m in members), dtype=np.uint8) if n else np.zeros(0, np.uint8)
-    out, out_len, in_consumed, crc, status = inflate_batch_raw(blob, in_off, out_off, flags)
+    out, out_len, in_consumed, crc, status = inflate_batch_raw(blob, in_off, out_off, flags, out)
     outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_len[i])]) for i in range(n)]
     return outs, out_len, in_consumed, crc, status
 

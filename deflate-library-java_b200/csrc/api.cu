@@ -128,9 +128,9 @@ int normalise_opts(const b2d_deflate_opts *o, uint64_t in_len, DeflateParams &p)
 
 int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                        const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc,
-                       int32_t *d_status, uint32_t flags, cudaStream_t st) {
+                       int32_t *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr) {
 	if (n == 0) return B2D_OK;
-	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st));
+	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st, out_mirror));
 	if ((flags & B2D_INFLATE_ADLER32) && d_crc) CK(launch_adler32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
 	else if ((flags & B2D_INFLATE_CRC32) && d_crc) CK(launch_crc32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
 	return B2D_OK;
@@ -259,6 +259,9 @@ B2D_API int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off,
 // four large slices (>= 1024 members each, enough warps to fill the GPU together), each on its own stream: the
 // slice kernels run side by side, slice k's H2D overlaps the decode of slices < k and its D2H overlaps the decode
 // of slices > k.  Pinned buffers (b2d_alloc_pinned) make the copies asynchronous; PCIe is the end-to-end bound.
+// When the output buffer is pinned (mapped) host memory the kernel writes every staged tile to it directly, next to
+// the device copy it keeps for back-references and the checksum: members advance at the same pace, so a copy after
+// the kernel could not overlap anything, while the kernel's own writes cross PCIe during the decode.
 B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n, uint8_t *out,
                               const uint64_t *out_off, uint64_t *out_len, uint64_t *in_consumed, uint32_t *crc32,
                               int32_t *status, uint32_t flags) {
@@ -275,7 +278,7 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	CK(cudaSetDevice(g.device));
 	int r;
 	if ((r = ensure(g.in, in_total + 64))) return r;
-	if ((r = ensure(g.out, out_total + 64))) return r;
+	if ((r = ensure(g.out, out_total + 256))) return r;
 	// meta layout (device): in_off[n+1] out_off[n+1] out_len[n] consumed[n] crc[n] status[n]
 	const size_t m_off_in = 0, m_off_out = (size_t)(n + 1) * 8, m_len = m_off_out + (size_t)(n + 1) * 8,
 	             m_cons = m_len + (size_t)n * 8, m_crc = m_cons + (size_t)n * 8, m_stat = m_crc + (size_t)n * 4,
@@ -286,11 +289,27 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	uint64_t *h_in_off = (uint64_t *)(hm + m_off_in), *h_out_off = (uint64_t *)(hm + m_off_out);
 	for (uint32_t i = 0; i <= n; i++) { h_in_off[i] = in_off[i] - in0; h_out_off[i] = out_off[i] - out0; }
 	uint8_t *d_in = (uint8_t *)g.in.p, *d_out = (uint8_t *)g.out.p;
+	uint8_t *mirror = nullptr;
+	if (out_total) {
+		const char *nm_ = getenv("B2D_NO_MIRROR");
+		cudaPointerAttributes pa0, pa1;
+		if (!(nm_ && nm_[0] == '1') &&
+		    cudaPointerGetAttributes(&pa0, out + out0) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer &&
+		    cudaPointerGetAttributes(&pa1, out + out0 + out_total - 1) == cudaSuccess && pa1.type == cudaMemoryTypeHost &&
+		    (uint8_t *)pa1.devicePointer - (uint8_t *)pa0.devicePointer == (ptrdiff_t)(out_total - 1)) {
+			mirror = (uint8_t *)pa0.devicePointer;
+			d_out += ((uintptr_t)mirror - (uintptr_t)d_out) & 127;      // same 128-byte phase as the host buffer (256 B slack)
+		}
+		cudaGetLastError();
+	}
 	CK(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, g.st[0]));
 	CK(cudaEventRecord(g.ev[0], g.st[0]));
 	uint32_t n_slices = std::min<uint32_t>(4, std::max<uint32_t>(1, n / 1024));
 	uint32_t per = (n + n_slices - 1) / n_slices;
 	int k = 0;
+	const char *tr_ = getenv("B2D_TRACE");                  // diagnostic: the slices' H2D / kernel / D2H timeline on stderr
+	const bool trace = tr_ != nullptr && tr_[0] == '1';
+	cudaEvent_t te[4][4];
 	for (uint32_t a = 0; a < n; a += per, k++) {
 		uint32_t b = std::min(n, a + per);
 		cudaStream_t st = g.st[k];
@@ -298,28 +317,17 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 		uint64_t ia = h_in_off[a], ib = h_in_off[b], oa = h_out_off[a], ob = h_out_off[b];
 		// (a kernel may read the aligned words around its slice while a neighbour's copy lands in them; those bytes
 		// are shifted out / masked by the bit reader, so the race is benign)
-		cudaEvent_t te[4];
-		const char *tr_ = getenv("B2D_TRACE");              // diagnostic: per-slice H2D / kernel / D2H times on stderr
-		const bool trace = tr_ != nullptr && tr_[0] == '1';
-		if (trace) { for (auto &e : te) cudaEventCreate(&e); cudaEventRecord(te[0], st); }
+		if (trace) { for (int q = 0; q < 4; q++) cudaEventCreate(&te[k][q]); cudaEventRecord(te[k][0], st); }
 		if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
-		if (trace) cudaEventRecord(te[1], st);
+		if (trace) cudaEventRecord(te[k][1], st);
 		r = inflate_dev_locked(d_in, (const uint64_t *)(dm + m_off_in) + a, b - a, d_out,
 		                       (const uint64_t *)(dm + m_off_out) + a, (uint64_t *)(dm + m_len) + a,
 		                       (uint64_t *)(dm + m_cons) + a, (uint32_t *)(dm + m_crc) + a,
-		                       (int32_t *)(dm + m_stat) + a, flags, st);
+		                       (int32_t *)(dm + m_stat) + a, flags, st, mirror);
 		if (r) return r;
-		if (trace) cudaEventRecord(te[2], st);
-		if (ob > oa) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
-		if (trace) {
-			cudaEventRecord(te[3], st);
-			cudaEventSynchronize(te[3]);
-			float a_ = 0, b_ = 0, c_ = 0;
-			cudaEventElapsedTime(&a_, te[0], te[1]); cudaEventElapsedTime(&b_, te[1], te[2]); cudaEventElapsedTime(&c_, te[2], te[3]);
-			fprintf(stderr, "[b2d trace] slice %d: members %u..%u h2d %.3f ms (%llu B) kernels %.3f ms d2h %.3f ms (%llu B)\n", k, a, b, a_,
-			        (unsigned long long)(ib - ia), b_, c_, (unsigned long long)(ob - oa));
-			for (auto &e : te) cudaEventDestroy(e);
-		}
+		if (trace) cudaEventRecord(te[k][2], st);
+		if (ob > oa && !mirror) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
+		if (trace) cudaEventRecord(te[k][3], st);
 	}
 	for (int s = 1; s < k; s++) {
 		CK(cudaEventRecord(g.ev[s], g.st[s]));
@@ -327,6 +335,15 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	}
 	CK(cudaMemcpyAsync(hm + m_len, dm + m_len, m_total - m_len, cudaMemcpyDeviceToHost, g.st[0]));
 	CK(cudaStreamSynchronize(g.st[0]));
+	if (trace) {
+		for (int q = 0; q < k; q++) {
+			float t[4];
+			for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], te[0][0], te[q][j]);
+			fprintf(stderr, "[b2d trace] slice %d: h2d %.3f..%.3f ms, kernels ..%.3f ms, d2h ..%.3f ms%s\n", q, t[0], t[1], t[2], t[3],
+			        mirror ? " [output mirrored by the kernel]" : "");
+			for (int j = 0; j < 4; j++) cudaEventDestroy(te[q][j]);
+		}
+	}
 	memcpy(out_len, hm + m_len, (size_t)n * 8);
 	memcpy(in_consumed, hm + m_cons, (size_t)n * 8);
 	if (crc32 && (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32))) memcpy(crc32, hm + m_crc, (size_t)n * 4);
@@ -561,7 +578,7 @@ B2D_API int b2d_inflate_chunks(const uint8_t *in, const uint64_t *chunk_in_len, 
 	const uint64_t in_total = off[n_chunks];
 	int r;
 	if ((r = ensure(g.in, in_total + 64))) return r;
-	if ((r = ensure(g.out, out_total + 64))) return r;
+	if ((r = ensure(g.out, out_total + 256))) return r;
 	if ((r = ensure(g.bits, (size_t)n_chunks * bpc * 4))) return r;
 	if ((r = ensure(g.scratch2, inflate_units_scratch_bytes(out_total, chunk_bytes, block_bytes)))) return r;
 	const size_t m_off = 0, m_crc = (size_t)(n_chunks + 1) * 8, m_st = m_crc + (size_t)n_chunks * 4, m_total = m_st + (size_t)n_chunks * 4;

@@ -28,15 +28,24 @@ constexpr int CTAS_PER_SM = 7;            // 28 resident warps per SM: 4096 memb
 constexpr int TILE = 1024;                // bytes of output staged per warp in shared memory
 constexpr u32 LIT_GUARD = 80;             // see decode_block<false>
 
-// LUT entry (lit/len and distance): [4:0] total bits (code + extra)   [7:5] kind flags   [12:8] code length
-//                                   [31:16] value (literal byte, length base, distance base, or sub-kind)
-// The shift counts sit where a wrap-mode funnel shift can take them straight from the entry.
-constexpr u32 K_LIT = 1u << 5;            // lit/len: literal
-constexpr u32 K_LEN = 1u << 6;            // lit/len: length symbol 257..285
-constexpr u32 K_OTHER = 1u << 7;          // lit/len: value 0 = end of block, 1 = code longer than the LUT index,
-                                          //          286/287 = reserved length symbol (Open.java:513-517)
-constexpr u32 KD_SPECIAL = 1u << 7;       // distance: value 0 = long code, 30/31 = reserved symbol (Open.java:546-551),
-                                          //           0xFFFF = the block has no distance code (Open.java:398-401)
+// lit/len LUT entry:  [31:27] bits this entry consumes   [19:16] kind   [15:0] value
+//   K_LIT    value = the literal byte (a byte store takes it from the low bits as it is)
+//   K_LEN    value = the run length 3..258: the extra bits of a length symbol are part of the LUT index whenever
+//            code + extra bits fit the index, so the common lengths cost no bit arithmetic at all
+//   K_LENX   length symbol whose extra bits do not all fit the index: value = base, [22:20] extra-bit count,
+//            [26:23] code length (the consumed-bits field already counts code + extra)
+//   K_OTHER  value 0 = end of block, 1 = code longer than the LUT index, 286/287 = reserved length symbol
+//            (Open.java:513-517); the consumed-bits field is the code length
+// The consumed bits sit on top so that `sh += e >> 27` is one LEA.HI, and nothing but the value sits in the low half
+// so that `tile offset + (length << 16)`, the queued form of a reference, is one IMAD on the entry itself.
+constexpr u32 K_LIT = 1u << 16;
+constexpr u32 K_LEN = 1u << 17;
+constexpr u32 K_LENX = 1u << 18;
+constexpr u32 K_OTHER = 1u << 19;
+// distance LUT entry: [4:0] total bits (code + extra)   [7] special   [12:8] code length   [31:16] distance base
+// (the two shift counts sit where a wrap-mode funnel shift can take them straight from the entry)
+constexpr u32 KD_SPECIAL = 1u << 7;       // value 0 = long code, 30/31 = reserved symbol (Open.java:546-551),
+                                          //       0xFFFF = the block has no distance code (Open.java:398-401)
 constexpr u32 V_EOB = 0, V_LONG = 1, V_NODIST = 0xFFFF;
 
 __constant__ u8 CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
@@ -50,15 +59,43 @@ struct Canon {                            // canonical-code description for the 
 
 struct __align__(16) WarpSmem {
 	u8 tile[TILE];                        // output staging: tile[i] <-> global byte tile_g[i]
-	uint2 mq[32];                         // pending back-references: x = tile offset | length << 16, y = distance
-	u32 ll_lut[1 << LL_TB];
-	u32 d_lut[1 << D_TB];
+	uint2 mq[32];                         // pending back-references: x = shared-window address of the tile byte
+	                                      // | length << 16, y = distance
 	Canon ll_canon, d_canon;
 	u16 ll_sorted[288];
 	u16 d_sorted[32];
 	u16 cl_lut[128];
 	u8 lens[320];
+	// host mirror (see mirror_progress): the member's output base and how many of its bytes are mirrored already.
+	// Kept here, reachable from the tile pointer, rather than in the Member.
+	u8 *m_out;
+	u64 m_done;
 };
+// Shared memory of a CTA.  The LUTs are placed so that each lit/len LUT is 4 KiB-aligned and each distance LUT 1 KiB-
+// aligned IN THE SHARED WINDOW: an entry's address is then (index bits << 2) OR-ed into the table address, one LOP3.
+// On sm_100 the static shared segment of a CTA starts at window address 0x400 (the first KiB is the system's), so the
+// 3 KiB up to 0x1000 hold three of the four distance LUTs, the lit/len LUTs follow at 0x1000..0x4FFF, then the fourth
+// distance LUT and the small per-warp state.  Kernels check the segment address once and trap if it ever differs.
+static_assert(WARPS_PER_CTA == 4 && LL_TB == 10 && D_TB == 8, "shared-memory layout below is written for these");
+constexpr u32 SM_WINDOW_BASE = 0x400;
+constexpr int SM_LL_OFF = 0xC00;                         // window 0x1000
+constexpr int SM_D3_OFF = SM_LL_OFF + 4 * 4096;          // window 0x5000
+constexpr int SM_W_OFF = SM_D3_OFF + 1024;
+constexpr int SM_BYTES = SM_W_OFF + WARPS_PER_CTA * (int)sizeof(WarpSmem);
+struct Sm {                               // one warp's view, in registers
+	WarpSmem *w;
+	u32 *ll;                              // 1 << LL_TB entries
+	u32 *dl;                              // 1 << D_TB entries
+	__device__ __forceinline__ WarpSmem *operator->() const { return w; }
+};
+__device__ __forceinline__ Sm warp_smem(u8 *raw, u32 warp) {
+	if ((u32)__cvta_generic_to_shared(raw) != SM_WINDOW_BASE) __trap();
+	Sm s;
+	s.ll = (u32 *)(raw + SM_LL_OFF) + (warp << LL_TB);
+	s.dl = (u32 *)(raw + (warp < 3 ? warp * 1024 : SM_D3_OFF));
+	s.w = (WarpSmem *)(raw + SM_W_OFF) + warp;
+	return s;
+}
 
 // Bit reader: three consecutive 32-bit words of the member live in registers (cur, nxt and a prefetched
 // third); peek() funnel-shifts 32 bits out of (cur, nxt) at bit `sh`, consuming bits is `sh += n`, and
@@ -114,13 +151,21 @@ __device__ __forceinline__ int getbits(BitIn &b, int n, int &avail, int &err) {
 	return (int)v;
 }
 
-__device__ __forceinline__ u32 ll_entry(int sym, int l) {
-	if (sym < 256) return K_LIT | (u32)sym << 16 | (u32)l << 8 | (u32)l;
-	if (sym == 256) return K_OTHER | V_EOB << 16 | (u32)l << 8 | (u32)l;
-	if (sym > 285) return K_OTHER | (u32)sym << 16 | (u32)l << 8 | (u32)l;
+// lit/len entry of symbol `sym` with code length l; `idx_hi` = the index bits above the code (they hold the extra
+// bits when the whole symbol fits the index); TB = index bits, or 0 for an entry made outside the LUT
+__device__ __forceinline__ u32 ll_entry(int sym, int l, u32 idx_hi, int tb) {
+	if (sym < 256) return (u32)l << 27 | K_LIT | (u32)sym;
+	if (sym == 256) return (u32)l << 27 | K_OTHER | V_EOB;
+	if (sym > 285) return (u32)l << 27 | K_OTHER | (u32)sym;
 	int base, eb;
 	length_sym_info(sym, base, eb);
-	return K_LEN | (u32)base << 16 | (u32)l << 8 | (u32)(l + eb);
+	if (l + eb <= tb) return (u32)(l + eb) << 27 | K_LEN | (u32)(base + (int)(idx_hi & ((1u << eb) - 1)));
+	return (u32)(l + eb) << 27 | (u32)l << 23 | (u32)eb << 20 | K_LENX | (u32)base;
+}
+// K_LENX -> K_LEN with the extra bits taken from the stream bits `lo` (code at bit 0)
+__device__ __forceinline__ u32 lenx_resolve(u32 e, u32 lo) {
+	const u32 eb = (e >> 20) & 7, cl = (e >> 23) & 15;
+	return (e & 0xF8000000u) | K_LEN | ((e & 0xFFFF) + ((lo >> cl) & ((1u << eb) - 1)));
 }
 __device__ __forceinline__ u32 d_entry(int sym, int l) {
 	if (sym > 29) return KD_SPECIAL | (u32)sym << 16 | (u32)l << 8 | (u32)l;
@@ -128,8 +173,8 @@ __device__ __forceinline__ u32 d_entry(int sym, int l) {
 	dist_sym_info(sym, base, eb);
 	return (u32)base << 16 | (u32)l << 8 | (u32)(l + eb);
 }
-// value + extra bits of a length / distance entry: extra = (lo & ((1 << tot) - 1)) >> clen, with both shift counts
-// read by wrap-mode funnel shifts from the entry itself
+// base + extra bits of a distance entry: extra = (lo & ((1 << tot) - 1)) >> clen, with both shift counts read by
+// wrap-mode funnel shifts from the entry itself
 __device__ __forceinline__ u32 entry_value(u32 e, u32 lo) {
 	u32 x = lo & ~__funnelshift_l(0u, 0xFFFFFFFFu, e);
 	return (e >> 16) + __funnelshift_r(x, 0u, e >> 8);
@@ -180,10 +225,14 @@ __device__ int build_code(const u8 *lens, int n, u32 *lut, u16 *sorted, Canon *c
 			sorted[cn->offs[l] + rank] = (u16)i;
 			u32 rev = __brev(c) >> (32 - l);
 			if (l <= TB) {
-				u32 e = IS_DIST ? d_entry(i, l) : ll_entry(i, l);
-				for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = e;
+				if (IS_DIST) {
+					const u32 e = d_entry(i, l);
+					for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = e;
+				} else {
+					for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = ll_entry(i, l, j >> l, TB);
+				}
 			} else {
-				lut[rev & ((1u << TB) - 1)] = IS_DIST ? KD_SPECIAL : (K_OTHER | V_LONG << 16);
+				lut[rev & ((1u << TB) - 1)] = IS_DIST ? KD_SPECIAL : ((u32)TB << 27 | K_OTHER | V_LONG);
 			}
 		}
 	}
@@ -200,10 +249,12 @@ __device__ __noinline__ u32 slow_decode(u32 lo, const Canon *cn, const u16 *sort
 		u32 idx = c - cn->first[l];
 		if (idx < cn->cnt[l]) {
 			int sym = sorted[cn->offs[l] + idx];
-			return IS_DIST ? d_entry(sym, l) : ll_entry(sym, l);
+			if (IS_DIST) return d_entry(sym, l);
+			const u32 e = ll_entry(sym, l, 0, 0);
+			return (e & K_LENX) ? lenx_resolve(e, lo) : e;
 		}
 	}
-	return IS_DIST ? (KD_SPECIAL | 31u << 16 | 15u << 8 | 15u) : (K_OTHER | 287u << 16 | 15u << 8 | 15u);   // unreachable for complete codes
+	return IS_DIST ? (KD_SPECIAL | 31u << 16 | 15u << 8 | 15u) : (15u << 27 | K_OTHER | 287u);   // unreachable for complete codes
 }
 
 // Per-member decoder state.  Output goes through a TILE-byte staging tile in shared memory: tile[i] holds the
@@ -225,6 +276,10 @@ struct Member {
 	// appended to a list in global memory; hist_base = output bytes of the chunk that precede this unit
 	u64 *glist;
 	u32 gcount, gcap, hist_base;
+	// host mirror (b2d_inflate_batch with a pinned output buffer): the member's output is also delivered to
+	// out + x + mdelta, a mapped host address with the same 128-byte phase, by the decoding warp itself, so no
+	// device-to-host copy follows the kernel (see mirror_progress)
+	long long mdelta;
 };
 
 enum { R_EOB = 0, R_SWITCH = 1000 };
@@ -242,40 +297,73 @@ __device__ __forceinline__ void set_tile_origin(Member &m, u64 pos) {
 	m.pos_base = rel0 > (1 << 20) ? (1 << 20) : (int)rel0;
 }
 
+// shared-memory accesses by 32-bit shared-window address, and plain (L1-cached, coherent) global loads: through a
+// generic pointer every access would carry the generic -> shared / -> global conversion
+__device__ __forceinline__ u32 lds_u32(u32 a) {
+	u32 v;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ void sts_u8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_v2(u32 a, u32 x, u32 y) {
+	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
+}
+
+__device__ __forceinline__ u32 lds_u8(u32 a) {
+	u32 v;
+	asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
+	return v;
+}
+__device__ __forceinline__ u32 ldg_u8(const u8 *p) {
+	u32 v;
+	asm volatile("ld.global.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ u32 ldg_u32(const u32 *p) {
+	u32 v;
+	asm volatile("ld.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+
 // Materialises the queued back-references into the tile.  Copies replicate the pattern when dist < len exactly
 // like the reference's byte-serial loop (Open.java:596-603): byte k comes from position pos - dist + (k mod dist).
 // (All state by value: a by-reference Member would be forced into local memory by the call.)
-__device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile_g, int ts, u32 nm, u32 lane) {
+__device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile_g, int ts, u32 nm, u32 lane, u32 qbase) {
 	__syncwarp();                                   // literal and queue stores of lane 0 are visible
 	const bool have = lane < nm;
 	const uint2 q = mq[lane];
-	const int off = (int)(q.x & 0xFFFFu), len = (int)(q.x >> 16), dist = (int)q.y;
+	const int off = (int)((q.x & 0xFFFFu) - qbase), len = (int)(q.x >> 16), dist = (int)q.y;
 	const int s = off - dist;                        // tile index of the source start (may be negative)
 	const bool far = have && (s + len <= ts);        // source lies wholly in global memory (already flushed)
-	// (1) far, short: each lane gathers its own reference, 8 bytes per round, all loads issued before the stores
+	// (1) far, short: each lane gathers its own reference with aligned 32-bit loads (only words that hold a needed
+	// byte are touched), shifts the up to 16 bytes into place and stores them byte by byte; all loads are issued
+	// before the first store
 	{
 		const bool mine = far && len <= 16;
-		const u8 *gs = tile_g + s;
 		if (__any_sync(FULL_MASK, mine)) {
-			u8 v[8];
+			const uintptr_t a = (uintptr_t)(tile_g + s);
+			const u32 *wp = (const u32 *)(a & ~(uintptr_t)3);
+			const u32 lead = (u32)(a & 3);
+			const int nw = mine ? (int)((lead + (u32)len + 3) >> 2) : 0;     // 1..5 words
+			u32 w[5];
 #pragma unroll
-			for (int k = 0; k < 8; k++) if (mine && k < len) v[k] = gs[k];
+			for (int k = 0; k < 5; k++) w[k] = k < nw ? ldg_u32(wp + k) : 0u;
+			u32 v[4];
 #pragma unroll
-			for (int k = 0; k < 8; k++) if (mine && k < len) tile[off + k] = v[k];
-			if (__any_sync(FULL_MASK, mine && len > 8)) {
+			for (int k = 0; k < 4; k++) v[k] = __funnelshift_r(w[k], w[k + 1], lead * 8);
+			const u32 dst = (u32)__cvta_generic_to_shared(tile) + (u32)off;
 #pragma unroll
-				for (int k = 0; k < 8; k++) if (mine && 8 + k < len) v[k] = gs[8 + k];
-#pragma unroll
-				for (int k = 0; k < 8; k++) if (mine && 8 + k < len) tile[off + 8 + k] = v[k];
-			}
+			for (int k = 0; k < 16; k++)
+				if (k < len && mine) sts_u8(dst + k, v[k >> 2] >> ((k & 3) * 8));
 		}
 	}
 	// (2) far, long: the warp copies one reference at a time, 32 bytes per step
+	const u32 t_s = (u32)__cvta_generic_to_shared(tile);
 	for (u32 mask = __ballot_sync(FULL_MASK, far && len > 16); mask; mask &= mask - 1) {
 		const int j = __ffs(mask) - 1;
 		const int o = __shfl_sync(FULL_MASK, off, j), l = __shfl_sync(FULL_MASK, len, j), si = __shfl_sync(FULL_MASK, s, j);
 		const u8 *gs = tile_g + si;
-		for (int k = lane; k < l; k += 32) tile[o + k] = gs[k];
+		for (int k = lane; k < l; k += 32) sts_u8(t_s + o + k, ldg_u8(gs + k));
 	}
 	__syncwarp();
 	// (3) near: source overlaps the tile; strictly in stream order, from shared memory
@@ -285,30 +373,69 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 		const int si = o - d;
 		if (si >= ts) {
 			if (d >= l) {
-				for (int k = lane; k < l; k += 32) tile[o + k] = tile[si + k];
+				for (int k = lane; k < l; k += 32) sts_u8(t_s + o + k, lds_u8(t_s + si + k));
 			} else if (d == 1) {
-				const u8 v = tile[si];
-				for (int k = lane; k < l; k += 32) tile[o + k] = v;
+				const u32 v = lds_u8(t_s + si);
+				for (int k = lane; k < l; k += 32) sts_u8(t_s + o + k, v);
 			} else {
-				for (int k = lane; k < l; k += 32) tile[o + k] = tile[si + k % d];
+				for (int k = lane; k < l; k += 32) sts_u8(t_s + o + k, lds_u8(t_s + si + k % d));
 			}
 		} else {                                     // source straddles the flushed / staged boundary
 			for (int k = lane; k < l; k += 32) {
 				const int idx = si + (d < l ? k % d : k);
-				tile[o + k] = idx < ts ? tile_g[idx] : tile[idx];
+				sts_u8(t_s + o + k, idx < ts ? ldg_u8(tile_g + idx) : lds_u8(t_s + idx));
 			}
 		}
 		__syncwarp();
 	}
 }
 
-__device__ __forceinline__ void resolve(Member &m, WarpSmem *sm, u32 lane) {
-	resolve_pending(sm->tile, sm->mq, m.tile_g, (int)m.tstart, m.nm, lane);
+__device__ __forceinline__ void resolve(Member &m, const Sm &sm, u32 lane) {
+	resolve_pending(sm->tile, sm->mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
 	m.nm = 0;
 }
 
-// Writes tile[lo, hi) to global memory (16-byte vectors for the aligned body).
-__device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u32 lane) {
+// Host mirror.  Stores from an SM reach pinned host memory at PCIe speed only as whole 128-byte lines (measured with
+// tools/pcie_probe.cu: 46-49 GB/s against 29 GB/s for tile-shaped pieces at byte alignment, where every piece ends in
+// partial lines the host has to merge).  So the mirror does not follow the tile flushes: whenever MIRROR_STEP more
+// bytes of the member are final in device memory, the warp copies them (L2 hits) to the host address as whole lines,
+// 64 bytes per lane in flight; the unaligned head and tail of the member are the only partial lines.
+constexpr u64 MIRROR_STEP = 4096;
+__device__ __forceinline__ void mirror_copy(const u8 *dev, long long mdelta, u64 n, u32 lane) {
+	__syncwarp();                                    // the bytes were stored by other lanes of this warp
+	u8 *h = (u8 *)dev + mdelta;
+	u64 head = (16 - ((uintptr_t)dev & 15)) & 15;
+	if (head > n) head = n;
+	for (u64 k = lane; k < head; k += 32) h[k] = dev[k];
+	const uint4 *s4 = (const uint4 *)(dev + head);
+	uint4 *d4 = (uint4 *)(h + head);
+	const u64 nv = (n - head) >> 4;
+	u64 i = lane;
+	for (; i + 32 < nv; i += 64) {
+		const uint4 a = __ldcg(s4 + i), b = __ldcg(s4 + i + 32);     // L2: keep L1 for the decoder
+		d4[i] = a; d4[i + 32] = b;
+	}
+	for (; i < nv; i += 32) d4[i] = __ldcg(s4 + i);
+	for (u64 k = head + (nv << 4) + lane; k < n; k += 32) h[k] = dev[k];
+}
+// end = device address just past the member's bytes that are final in device memory
+__device__ __forceinline__ void mirror_progress(WarpSmem *w, const u8 *end, long long mdelta, bool final, u32 lane) {
+	const u8 *base = w->m_out;
+	const u64 done = w->m_done, pos = (u64)(end - base);
+	u64 upto = pos;
+	if (!final) {
+		upto = pos - ((uintptr_t)end & 127);                         // whole lines only
+		if (upto < done + MIRROR_STEP || upto > pos) return;        // (upto > pos: the subtraction wrapped)
+	}
+	if (upto > done) mirror_copy(base + done, mdelta, upto - done, lane);
+	__syncwarp();
+	if (lane == 0) w->m_done = upto;
+	__syncwarp();
+}
+
+// Writes tile[lo, hi) to global memory (16-byte vectors for the aligned body); with a host mirror (mdelta != 0; `tile`
+// is then the tile of a WarpSmem) the mirror is moved on as well.
+__device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u32 lane, long long mdelta) {
 	__syncwarp();
 	const u32 a = (lo + 15) & ~15u, b = hi & ~15u;
 	if (a >= b) {
@@ -319,54 +446,244 @@ __device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u
 		if (b + lane < hi) g[b + lane] = tile[b + lane];
 	}
 	__syncwarp();
+	if (mdelta) mirror_progress((WarpSmem *)tile, g + hi, mdelta, false, lane);
 }
 
 // Resolves what is queued, writes the staged bytes out and re-bases the tile at the current output position.
-__device__ __forceinline__ void flush_tile(Member &m, WarpSmem *sm, u32 lane) {
+__device__ __forceinline__ void flush_tile(Member &m, const Sm &sm, u32 lane) {
 	if (m.nm) resolve(m, sm, lane);
-	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane);
+	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane, m.mdelta);
 	set_tile_origin(m, out_pos(m));
 }
 
-// Decodes symbols of one Huffman block until end-of-block.  The hot state lives in locals; the Member is only
-// synchronised around the rare calls (tile flush, queue resolve) and at exit.
-// CAREFUL=false requires that the three words (cur, nxt, pre) hold only real input at the top of every iteration
-// (a whole symbol is at most 48 bits, read from bit offset <= 31), so no read can pass the end of input and the
-// end-of-stream checks are skipped; the CAREFUL=true instantiation checks after every field, in the reference's
-// order (Open.java:565-593).
-template <bool CAREFUL, bool DEFER>
-__device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 lane) {
+// Decodes symbols of one Huffman block until end-of-block.  Two implementations with identical results:
+//  * decode_block_fast: requires that the three buffered words (cur, nxt, pre) hold only real input at every symbol
+//    start (a whole symbol is at most 48 bits, read from bit offset <= 31), so no read can pass the end of input and
+//    the end-of-stream checks are skipped.  Its inner loop contains nothing but the two common symbols -- a literal,
+//    and a length/distance pair whose reference exists and fits the tile -- with the next LUT lookup issued at the
+//    end of the current symbol; everything else (window nearly at the end of input, tile full, reference queue full,
+//    rare symbol kinds, split or invalid references) leaves the inner loop with an event code and is handled outside
+//    it, which keeps the register allocation of the hot loop free of the calls' save/restore traffic.
+//  * decode_block_careful: checks after every field, in the reference's order (Open.java:565-593); used for the
+//    last <= 12 bytes of a member and when the member's output slot is nearly full.
+enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
+
+template <bool DEFER>
+__device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32 lane) {
+	BitIn &b = m.in;
+	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;     // sh < 32, widx + 3 <= n_full
+	// The output position is kept as the shared-window ADDRESS of the next tile byte (tp = tile_s + tpos), so a
+	// literal store needs no address arithmetic; limits and the queued references are in the same terms.
+	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile);
+	const u32 mq_s = (u32)__cvta_generic_to_shared(sm->mq);
+	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);       // 4 KiB-aligned
+	const u32 dlb = (u32)__cvta_generic_to_shared(sm.dl);       // 1 KiB-aligned
+	u32 tp = tile_s + m.tpos;
+	u32 tend = tile_s + m.tlimit;                    // end of the usable tile
+	int tguard = (int)tend - (int)LIT_GUARD;         // tp <= tguard at every word boundary (see NEXT_SYMBOL)
+	int pos_off = m.pos_base - (int)tile_s;          // output position of the byte at tp = pos_off + tp
+	u32 qp = mq_s + m.nm * 8;                        // next free slot of the reference queue
+	const u32 qend = mq_s + 32 * 8;
+	const u32 fast_last = b.n_full - 3;
+	const u32 *const words = b.words;
+	u64 *gp = DEFER ? m.glist + m.gcount : nullptr;  // DEFER: next free record, end of the list, unit offset of tile[0]
+	u64 *const gend = DEFER ? m.glist + m.gcap : nullptr;
+	u32 ubase = DEFER ? (u32)(m.tile_g - m.out) - tile_s : 0;
+#define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = widx; b.sh = sh; m.tpos = tp - tile_s; \
+                          m.nm = (qp - mq_s) >> 3; if (DEFER) m.gcount = (u32)(gp - m.glist); } while (0)
+#define LOAD_TILE() do { tp = tile_s + m.tpos; tend = tile_s + m.tlimit; qp = mq_s + m.nm * 8; \
+                         pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; \
+                         if (DEFER) ubase = (u32)(m.tile_g - m.out) - tile_s; } while (0)
+	// LUT entry addresses: (bits << 2) masked and OR-ed into the aligned table address
+#define LL_AT(bits) lds_u32(llb | (((bits) << 2) & ((4u << LL_TB) - 4)))
+#define DL_AT(bits) lds_u32(dlb | (((bits) << 2) & ((4u << D_TB) - 4)))
+	// Window refill at a symbol boundary.  The three buffered words must stay real input, so the word about to be
+	// loaded (widx + 3) has to be a full one; otherwise the hot loop is left with the window untouched (the checked
+	// path advances by itself).  A length/distance pair can cross two words: then the loop runs twice.  Literals are
+	// stored without a capacity check: fewer than LIT_GUARD symbols can start before the next word boundary is crossed
+	// (<= 79 bits at >= 1 bit each), so room for that many is secured here, once per word.
+#define NEXT_SYMBOL()                                                     \
+	if (sh >= 32) {                                                       \
+		_Pragma("unroll 1")                                               \
+		do {                                                              \
+			if (widx >= fast_last) break;                                 \
+			sh -= 32; cur = nxt; nxt = pre; widx++;                       \
+			pre = __ldg(words + widx + 2);                                \
+		} while (sh >= 32);                                               \
+		if (sh >= 32) { ev = EV_SWITCH; break; }                          \
+		if ((int)tp > tguard) { ev = EV_FLUSH; break; }                   \
+	}                                                                     \
+	lo = __funnelshift_r(cur, nxt, sh);                                   \
+	e = LL_AT(lo);
+	u32 lo = __funnelshift_r(cur, nxt, sh);
+	u32 e = LL_AT(lo);
+	for (;;) {
+		int ev;
+		u32 len = 0, d = 0, lo2 = 0;
+		for (;;) {                                       // ---- the hot loop: no call inside
+			if (e & K_LIT) {
+				sts_u8(tp, e);                               // every lane stores the same byte: one broadcast write, no predicate
+				tp++;
+				sh += e >> 27;
+				NEXT_SYMBOL();
+				continue;
+			}
+			if (!(e & K_LEN)) { ev = EV_RARE; break; }
+			sh += e >> 27;                                   // <= 51: the distance may start in nxt
+			lo2 = (sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh);
+			d = DL_AT(lo2);
+			if (d & KD_SPECIAL) { len = e & 0xFFFF; ev = EV_DSPECIAL; break; }
+			const u32 dist = entry_value(d, lo2);
+			sh += d & 31;
+			// the source must exist (Open.java:592-593) and the whole reference fit the tile with the literal guard
+			// kept; tp is advanced first so that the update is in place (the slow path takes it back)
+			const u32 qx = tp + (e << 16);                   // tile address | length << 16 (the kind bits shift out)
+			const int dmax = pos_off + (int)tp;
+			tp += qx >> 16;
+			if ((int)dist > dmax || (int)tp > tguard) { len = qx >> 16; ev = EV_SLOWMATCH; break; }
+			if (DEFER) {                                     // record only: (unit-relative position, length, distance)
+				if (gp >= gend) { len = qx >> 16; ev = EV_SLOWMATCH; break; }
+				*gp++ = (u64)(ubase + (qx & 0xFFFF)) | (u64)(qx >> 16) << 24 | (u64)dist << 40;
+			} else {
+				sts_v2(qp, qx, dist);                        // same value from every lane: one broadcast write
+				qp += 8;
+				if (qp == qend) { ev = EV_QFULL; break; }
+			}
+			NEXT_SYMBOL();
+		}
+		// ---- events
+		if (ev == EV_RARE) {
+			if (e & K_LENX) { e = lenx_resolve(e, lo); continue; }
+			u32 v = e & 0xFFFF;
+			if (v == V_LONG) {
+				e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted);
+				if (!(e & K_OTHER)) continue;
+				v = e & 0xFFFF;
+			}
+			if (v == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
+			SAVE_STATE();
+			return B2D_RESERVED_LENGTH_SYMBOL;
+		}
+		if (ev == EV_SWITCH) { SAVE_STATE(); return R_SWITCH; }
+		if (ev == EV_DSPECIAL) {
+			u32 v = d >> 16;
+			if (v == 0) {
+				d = slow_decode<D_TB, true>(lo2, &sm->d_canon, sm->d_sorted);
+				v = (d & KD_SPECIAL) ? d >> 16 : 0;
+			}
+			if (v) {
+				SAVE_STATE();
+				return v == V_NODIST ? B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE : B2D_RESERVED_DISTANCE_SYMBOL;
+			}
+			sh += d & 31;
+			tp += len;
+			ev = EV_SLOWMATCH;
+		}
+		if (ev == EV_SLOWMATCH) {
+			tp -= len;                                       // the hot loop had advanced it already
+			const u32 dist = entry_value(d, lo2);
+			if ((int)dist > pos_off + (int)tp) {             // Open.java:592-593 (the distance bits stay unconsumed)
+				sh -= d & 31;
+				SAVE_STATE();
+				return B2D_COPY_FROM_BEFORE_DICTIONARY_START;
+			}
+			// A reference that does not fit the tile is split (same distance); when the member's slot is full, what
+			// fits is still delivered (Open.java:604-616) before the overflow is reported.
+			for (;;) {
+				const u32 fit = tend - tp;
+				const u32 take = len < fit ? len : fit;
+				if (take) {
+					if (DEFER) {
+						if (gp >= gend) { SAVE_STATE(); return B2D_ERR_OUTPUT_OVERFLOW; }
+						*gp++ = (u64)(ubase + tp) | (u64)take << 24 | (u64)dist << 40;
+					} else {
+						sts_v2(qp, tp | take << 16, dist);
+						qp += 8;
+					}
+					tp += take;
+					len -= take;
+				}
+				if (len == 0 && qp != qend) break;
+				SAVE_STATE();
+				if (len == 0) { resolve(m, sm, lane); qp = mq_s; break; }
+				flush_tile(m, sm, lane);
+				LOAD_TILE();
+				if (tp >= tend) { SAVE_STATE(); return B2D_ERR_OUTPUT_OVERFLOW; }
+			}
+		}
+		if (ev == EV_QFULL) {
+			SAVE_STATE();
+			resolve(m, sm, lane);
+			qp = mq_s;
+		}
+		// ---- back to a symbol boundary of the hot loop: window, literal guard, lookup
+		while (sh >= 32) {
+			if (widx >= fast_last) { SAVE_STATE(); return R_SWITCH; }
+			sh -= 32; cur = nxt; nxt = pre; widx++;
+			pre = __ldg(words + widx + 2);
+		}
+		if ((int)tp > tguard) {
+			SAVE_STATE();
+			flush_tile(m, sm, lane);
+			LOAD_TILE();
+			if ((int)tp > tguard) { SAVE_STATE(); return R_SWITCH; }         // the member's slot is nearly full: checked path
+		}
+		lo = __funnelshift_r(cur, nxt, sh);
+		e = LL_AT(lo);
+	}
+#undef SAVE_STATE
+#undef LOAD_TILE
+#undef NEXT_SYMBOL
+#undef LL_AT
+#undef DL_AT
+}
+
+template <bool DEFER>
+__device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
 	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;
 	u32 tpos = m.tpos, tlimit = m.tlimit, nm = m.nm;
 	int pos_base = m.pos_base;
-	int avail = CAREFUL ? avail_bits(b) : 0;
+	int tguard = (int)tlimit - (int)LIT_GUARD;      // FAST keeps tpos <= tguard at every word boundary
+	constexpr bool CAREFUL = true;
+	int avail = avail_bits(b);
 	const u32 fast_last = b.n_full - 3;              // FAST is only entered with n_full >= 3
 	const u32 n_safe = b.n_safe;
 	const u32 *const words = b.words;
-	const u32 *const ll = sm->ll_lut;
-	const u32 *const dl = sm->d_lut;
+	const u32 *const ll = sm.ll;
+	const u32 *const dl = sm.dl;
 	u8 *const tile = sm->tile;
+	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile);
 	int ret;
 #define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = widx; b.sh = sh; m.tpos = tpos; m.nm = nm; } while (0)
-#define LOAD_TILE() do { tpos = m.tpos; tlimit = m.tlimit; nm = m.nm; pos_base = m.pos_base; } while (0)
+#define LOAD_TILE() do { tpos = m.tpos; tlimit = m.tlimit; nm = m.nm; pos_base = m.pos_base; tguard = (int)tlimit - (int)LIT_GUARD; } while (0)
 	for (;;) {
 		if (sh >= 32) {
-			sh -= 32; cur = nxt; nxt = pre; widx++;
-			pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
-			if (sh >= 32) {                                  // a long symbol crossed two words (rare)
+			if (CAREFUL) {
 				sh -= 32; cur = nxt; nxt = pre; widx++;
 				pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
-			}
-			if (!CAREFUL) {
-				if (widx > fast_last) { ret = R_SWITCH; break; }
+				if (sh >= 32) {                              // a long symbol crossed two words (rare)
+					sh -= 32; cur = nxt; nxt = pre; widx++;
+					pre = (widx + 2 < n_safe) ? __ldg(words + widx + 2) : 0u;
+				}
+			} else {
+				// FAST: the three buffered words must stay real input, so the word about to be loaded (widx + 3) has to
+				// be a full one; otherwise leave with the window untouched (the checked path advances by itself)
+				if (widx >= fast_last) { ret = R_SWITCH; break; }
+				sh -= 32; cur = nxt; nxt = pre; widx++;
+				pre = __ldg(words + widx + 2);
+				if (sh >= 32) {
+					if (widx >= fast_last) { ret = R_SWITCH; break; }
+					sh -= 32; cur = nxt; nxt = pre; widx++;
+					pre = __ldg(words + widx + 2);
+				}
 				// FAST literals are stored without a capacity check: fewer than LIT_GUARD symbols can start before the
 				// next word boundary is crossed (<= 79 bits at >= 1 bit each), so room for that many is secured here.
-				if (tpos + LIT_GUARD > tlimit) {
+				if ((int)tpos > tguard) {
 					SAVE_STATE();
 					flush_tile(m, sm, lane);
 					LOAD_TILE();
-					if (tpos + LIT_GUARD > tlimit) { ret = R_SWITCH; break; }     // the member's slot is nearly full: checked path
+					if ((int)tpos > tguard) { ret = R_SWITCH; break; }       // the member's slot is nearly full: checked path
 				}
 			}
 		}
@@ -374,33 +691,36 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 		u32 e = ll[lo & ((1u << LL_TB) - 1)];
 	dispatch:
 		if (e & K_LIT) {
-			if (CAREFUL && (int)(e & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if (CAREFUL && (int)(e >> 27) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			if (CAREFUL && tpos >= tlimit) {
 				SAVE_STATE();
 				flush_tile(m, sm, lane);
 				LOAD_TILE();
 				if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
 			}
-			tile[tpos] = (u8)(e >> 16);                      // every lane stores the same byte: one broadcast write, no predicate
+			tile[tpos] = (u8)e;                              // every lane stores the same byte: one broadcast write, no predicate
 			tpos++;
-			sh += e & 31;
-			if (CAREFUL) avail -= e & 31;
+			sh += e >> 27;
+			if (CAREFUL) avail -= e >> 27;
 			continue;
 		}
 		if (!(e & K_LEN)) {                                  // rare kinds
-			const u32 v = e >> 16;
+			if (e & K_LENX) { e = lenx_resolve(e, lo); goto dispatch; }
+			const u32 v = e & 0xFFFF;
 			if (v == V_LONG) { e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted); goto dispatch; }
-			if (CAREFUL && (int)((e >> 8) & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
-			if (v == V_EOB) { sh += e & 31; ret = R_EOB; break; }
+			if (CAREFUL && (int)(e >> 27) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if (v == V_EOB) { sh += e >> 27; ret = R_EOB; break; }
 			ret = B2D_RESERVED_LENGTH_SYMBOL;
 			break;
 		}
+		// code and extra bits of the length are both missing-checked by the consumed-bits field: either is the same
+		// UNEXPECTED_END_OF_STREAM (Open.java:565-577)
 		if (CAREFUL) {
-			if ((int)((e >> 8) & 31) > avail || (int)(e & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
-			avail -= e & 31;
+			if ((int)(e >> 27) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			avail -= e >> 27;
 		}
-		u32 len = entry_value(e, lo);
-		sh += e & 31;                                        // <= 51: the distance may start in nxt
+		u32 len = e & 0xFFFF;
+		sh += e >> 27;                                       // <= 51: the distance may start in nxt
 		const u32 lo2 = (sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh);
 		u32 d = dl[lo2 & ((1u << D_TB) - 1)];
 	dispatch_d:
@@ -418,8 +738,8 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 		}
 		const u32 dist = entry_value(d, lo2);
 		sh += d & 31;
-		if ((int)dist > pos_base + (int)tpos) { ret = B2D_COPY_FROM_BEFORE_DICTIONARY_START; break; }   // Open.java:592-593
-		if (tpos + len + (CAREFUL ? 0u : LIT_GUARD) <= tlimit) {   // common case: the whole reference fits the tile
+		// common case: the source exists (Open.java:592-593) and the whole reference fits the tile
+		if ((int)dist <= pos_base + (int)tpos && (int)(tpos + len) <= (CAREFUL ? (int)tlimit : tguard)) {
 			if (DEFER) {                                     // record only: (unit-relative position, length, distance)
 				if (m.gcount >= m.gcap) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
 				const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
@@ -427,7 +747,7 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 				tpos += len;
 				continue;
 			}
-			sm->mq[nm] = make_uint2(tpos | len << 16, dist);     // same value from every lane: one broadcast write
+			sm->mq[nm] = make_uint2(tile_s + tpos + (len << 16), dist);   // same value from every lane: one broadcast write
 			tpos += len;
 			if (++nm == 32) {
 				SAVE_STATE();
@@ -436,6 +756,7 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 			}
 			continue;
 		}
+		if ((int)dist > pos_base + (int)tpos) { ret = B2D_COPY_FROM_BEFORE_DICTIONARY_START; break; }   // Open.java:592-593
 		// A reference that does not fit the tile is split (same distance); when the member's slot is full, what
 		// fits is still delivered (Open.java:604-616) before the overflow is reported.
 		ret = 0;
@@ -448,7 +769,7 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 					const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
 					m.glist[m.gcount++] = upos | (u64)take << 24 | (u64)dist << 40;
 				} else {
-					if (lane == 0) sm->mq[nm] = make_uint2(tpos | take << 16, dist);
+					if (lane == 0) sm->mq[nm] = make_uint2((tile_s + tpos) | take << 16, dist);
 					nm++;
 				}
 				tpos += take;
@@ -462,11 +783,11 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 			if (tpos >= tlimit) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
 		}
 		if (ret) break;
-		if (!CAREFUL && tpos + LIT_GUARD > tlimit) {         // re-establish the literal guard of the FAST path
+		if (!CAREFUL && (int)tpos > tguard) {                // re-establish the literal guard of the FAST path
 			SAVE_STATE();
 			flush_tile(m, sm, lane);
 			LOAD_TILE();
-			if (tpos + LIT_GUARD > tlimit) { ret = R_SWITCH; break; }
+			if ((int)tpos > tguard) { ret = R_SWITCH; break; }
 		}
 	}
 	SAVE_STATE();
@@ -475,28 +796,8 @@ __device__ __forceinline__ int decode_block(Member &m, WarpSmem *sm, const u32 l
 	return ret;
 }
 
-// Open.UncompressedBlock (Open.java:227-306)
-__device__ int stored_block(Member &m, WarpSmem *sm, int &avail, u32 lane) {
-	BitIn &b = m.in;
-	int err = 0;
-	norm(b);
-	getbits(b, (8 - (b.sh & 7)) & 7, avail, err);       // align to byte (:234)
-	int len = getbits(b, 16, avail, err);
-	if (err) return err;
-	int nlen = getbits(b, 16, avail, err);
-	if (err) return err;
-	if (len != (nlen ^ 0xFFFF)) return B2D_UNCOMPRESSED_BLOCK_LENGTH_MISMATCH;   // :239-240
-	flush_tile(m, sm, lane);                            // the payload goes global -> global, past the tile
-	u64 pos = out_pos(m);
-	u64 byte_pos = consumed_bits(b) >> 3;
-	u64 in_len = b.total_bits >> 3;
-	u64 have = in_len - byte_pos;
-	u64 n = (u64)len < have ? (u64)len : have;
-	int status = (u64)len > have ? B2D_UNEXPECTED_END_OF_STREAM : 0;            // :279-280
-	if (pos + n > m.cap) { n = m.cap - pos; status = B2D_ERR_OUTPUT_OVERFLOW; }
-	const u8 *src = (const u8 *)b.words + (b.lead8 >> 3) + byte_pos;
-	u8 *dst = m.out + pos;
-	// vector body when source and destination share 16-byte phase, bytes otherwise
+// warp-wide global -> global copy: vector body when source and destination share 16-byte (or 4-byte) phase
+__device__ __noinline__ void copy_global(u8 *dst, const u8 *src, u64 n, u32 lane) {
 	if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0 && n >= 64) {
 		u64 head = (16 - ((uintptr_t)dst & 15)) & 15;
 		for (u64 k = lane; k < head; k += 32) dst[k] = src[k];
@@ -516,6 +817,31 @@ __device__ int stored_block(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 	} else {
 		for (u64 k = lane; k < n; k += 32) dst[k] = src[k];
 	}
+}
+
+// Open.UncompressedBlock (Open.java:227-306)
+__device__ int stored_block(Member &m, const Sm &sm, int &avail, u32 lane) {
+	BitIn &b = m.in;
+	int err = 0;
+	norm(b);
+	getbits(b, (8 - (b.sh & 7)) & 7, avail, err);       // align to byte (:234)
+	int len = getbits(b, 16, avail, err);
+	if (err) return err;
+	int nlen = getbits(b, 16, avail, err);
+	if (err) return err;
+	if (len != (nlen ^ 0xFFFF)) return B2D_UNCOMPRESSED_BLOCK_LENGTH_MISMATCH;   // :239-240
+	flush_tile(m, sm, lane);                            // the payload goes global -> global, past the tile
+	u64 pos = out_pos(m);
+	u64 byte_pos = consumed_bits(b) >> 3;
+	u64 in_len = b.total_bits >> 3;
+	u64 have = in_len - byte_pos;
+	u64 n = (u64)len < have ? (u64)len : have;
+	int status = (u64)len > have ? B2D_UNEXPECTED_END_OF_STREAM : 0;            // :279-280
+	if (pos + n > m.cap) { n = m.cap - pos; status = B2D_ERR_OUTPUT_OVERFLOW; }
+	const u8 *src = (const u8 *)b.words + (b.lead8 >> 3) + byte_pos;
+	u8 *dst = m.out + pos;
+	copy_global(dst, src, n, lane);
+	if (m.mdelta) mirror_progress(sm.w, dst + n, m.mdelta, false, lane);
 	__syncwarp();
 	set_tile_origin(m, pos + n);
 	if (status) return status;
@@ -524,7 +850,7 @@ __device__ int stored_block(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 }
 
 // Open.HuffmanBlock constructor, dynamic branch (Open.java:336-431)
-__device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
+__device__ int dynamic_header(Member &m, const Sm &sm, int &avail, u32 lane) {
 	BitIn &b = m.in;
 	int err = 0;
 	int num_ll = getbits(b, 5, avail, err) + 257;
@@ -597,13 +923,13 @@ __device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 	}
 	__syncwarp();
 	if (sm->lens[256] == 0) return B2D_END_OF_BLOCK_CODE_ZERO_LENGTH;               // :383-384
-	int e = build_code<LL_TB, false>(sm->lens, num_ll, sm->ll_lut, sm->ll_sorted, &sm->ll_canon, lane);   // :385
+	int e = build_code<LL_TB, false>(sm->lens, num_ll, sm.ll, sm->ll_sorted, &sm->ll_canon, lane);   // :385
 	if (e) return e;
 	// distance code special cases (:396-428)
 	u8 *dl = sm->lens + num_ll;
 	if (num_d == 1 && dl[0] == 0) {
 		// no distance code: any length symbol is an error (:526-527,578-579), reported by the distance lookup
-		for (int i = lane; i < (1 << D_TB); i += 32) sm->d_lut[i] = KD_SPECIAL | V_NODIST << 16;
+		for (int i = lane; i < (1 << D_TB); i += 32) sm.dl[i] = KD_SPECIAL | V_NODIST << 16;
 		__syncwarp();
 	} else {
 		int v = (int)lane < num_d ? dl[lane] : 0;
@@ -616,7 +942,7 @@ __device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 			num_d = 32;
 			__syncwarp();
 		}
-		e = build_code<D_TB, true>(dl, num_d, sm->d_lut, sm->d_sorted, &sm->d_canon, lane);   // :426
+		e = build_code<D_TB, true>(dl, num_d, sm.dl, sm->d_sorted, &sm->d_canon, lane);   // :426
 		if (e) return e;
 	}
 	m.tables = 0;
@@ -624,24 +950,25 @@ __device__ int dynamic_header(Member &m, WarpSmem *sm, int &avail, u32 lane) {
 }
 
 // fixed code of Open.java:812-830 (288 lit/len lengths incl. the reserved 286/287, 32 distance lengths)
-__device__ void fixed_tables(Member &m, WarpSmem *sm, u32 lane) {
+__device__ void fixed_tables(Member &m, const Sm &sm, u32 lane) {
 	for (int i = lane; i < 288; i += 32) sm->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
 	sm->lens[288 + lane] = 5;
 	__syncwarp();
-	build_code<LL_TB, false>(sm->lens, 288, sm->ll_lut, sm->ll_sorted, &sm->ll_canon, lane);
-	build_code<D_TB, true>(sm->lens + 288, 32, sm->d_lut, sm->d_sorted, &sm->d_canon, lane);
+	build_code<LL_TB, false>(sm->lens, 288, sm.ll, sm->ll_sorted, &sm->ll_canon, lane);
+	build_code<D_TB, true>(sm->lens + 288, 32, sm.dl, sm->d_sorted, &sm->d_canon, lane);
 	m.tables = 1;
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
-               u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags) {
-	__shared__ WarpSmem smem[WARPS_PER_CTA];
+               u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags,
+               long long mdelta) {
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	u32 mi = blockIdx.x * WARPS_PER_CTA + warp;
 	if (mi >= n_members) return;
-	WarpSmem *sm = &smem[warp];
+	const Sm sm = warp_smem(smem_raw, warp);
 
 	Member m;
 	u64 i0 = in_off[mi], i1 = in_off[mi + 1];
@@ -660,6 +987,9 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	m.nm = 0;
 	m.glist = nullptr;
 	m.gcount = m.gcap = m.hist_base = 0;
+	m.mdelta = mdelta;
+	if (lane == 0) { sm->m_out = m.out; sm->m_done = 0; }
+	__syncwarp();
 	set_tile_origin(m, 0);
 	m.tables = 0;
 
@@ -686,12 +1016,13 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 		int r = R_SWITCH;
 #else
 		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false, false>(m, sm, lane) : (int)R_SWITCH;
+		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<false>(m, sm, lane) : (int)R_SWITCH;
 #endif
-		if (r == R_SWITCH) r = decode_block<true, false>(m, sm, lane);
+		if (r == R_SWITCH) r = decode_block_careful<false>(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);                                               // also resolves what is pending
+	if (m.mdelta) mirror_progress(sm.w, m.out + out_pos(m), m.mdelta, true, lane);
 	if (lane == 0) {
 		out_len[mi] = out_pos(m);
 		in_consumed[mi] = (consumed_bits(m.in) + 7) >> 3;                  // Open.finish, Open.java:113-124
@@ -712,11 +1043,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in_off, const u32 *__restrict__ block_bits,
                      u32 n_units, u32 bpc, u32 chunk_bytes, u32 block_bytes, u64 out_total, u8 *out,
                      u64 *__restrict__ glist, u32 gcap, u32 *__restrict__ gcount, int *__restrict__ ustatus) {
-	__shared__ WarpSmem smem[WARPS_PER_CTA];
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 u = blockIdx.x * WARPS_PER_CTA + warp;
 	if (u >= n_units) return;
-	WarpSmem *sm = &smem[warp];
+	const Sm sm = warp_smem(smem_raw, warp);
 	const u32 c = u / bpc, bi = u % bpc;
 	const u64 pos0 = (u64)c * chunk_bytes + (u64)bi * block_bytes;
 	if (pos0 >= out_total) { if (lane == 0) { gcount[u] = 0; ustatus[u] = 0; } return; }
@@ -742,6 +1073,7 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 	m.gcount = 0;
 	m.gcap = gcap;
 	m.hist_base = bi * block_bytes;
+	m.mdelta = 0;
 	set_tile_origin(m, 0);
 	m.tables = 0;
 
@@ -762,8 +1094,8 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
 		norm(m.in);
 		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block<false, true>(m, sm, lane) : (int)R_SWITCH;
-		if (r == R_SWITCH) r = decode_block<true, true>(m, sm, lane);
+		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<true>(m, sm, lane) : (int)R_SWITCH;
+		if (r == R_SWITCH) r = decode_block_careful<true>(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);
@@ -821,8 +1153,8 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 				}
 			}
 			sm->mq[lane] = make_uint2((mis + (pos - first)) | len << 16, dist);
-			resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane);
-			store_tile(sm->tile, tile_g, mis, hi, lane);
+			resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane, 0);
+			store_tile(sm->tile, tile_g, mis, hi, lane, 0);
 			k += cnt;
 		}
 	}
@@ -863,7 +1195,8 @@ cudaError_t launch_inflate_units(const u8 *d_in, const u64 *d_chunk_in_off, u32 
 }
 
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,
-                           u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st) {
+                           u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st,
+                           uint8_t *out_mirror) {
 	if (n == 0) return cudaSuccess;
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -874,7 +1207,8 @@ cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out
 	}
 	u32 grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	inflate_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(d_in, d_in_off, n, d_out, d_out_off, d_out_len,
-	                                                     d_in_consumed, d_status, flags);
+	                                                     d_in_consumed, d_status, flags,
+	                                                     out_mirror ? (long long)(out_mirror - d_out) : 0ll);
 	return cudaGetLastError();
 }
 

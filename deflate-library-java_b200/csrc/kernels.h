@@ -9,7 +9,9 @@ namespace b2d {
 // inflate.cu
 cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
-                           int *d_status, uint32_t flags, cudaStream_t st);
+                           int *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr);
+// out_mirror (optional): a mapped host address for d_out[0] with (out_mirror - d_out) % 128 == 0; every output byte is
+// then delivered there as well by the kernel itself (no device-to-host copy afterwards)
 
 // block-parallel decode of a b2d_deflate_chunks stream (inflate.cu): chunk c occupies d_in[off[c], off[c+1]) and decodes
 // to d_out[c * chunk_bytes ...); d_block_bits as produced by launch_deflate; d_chunk_status = 0 or the first failing

@@ -89,6 +89,9 @@ void b2d_free_pinned(void *p);
  *   in_consumed[i] ceil(bits consumed / 8): the end-exactly position of Open.finish (Open.java:113-124)
  *   crc32[i]       CRC-32 of the member's output if B2D_INFLATE_CRC32 (may be NULL otherwise)
  *   status[i]      0 or 1 + Reason.ordinal(); a bad member does not disturb the others
+ * If `out` is page-locked memory (b2d_alloc_pinned, cudaHostAlloc, cudaHostRegister) the decoding kernel delivers the
+ * bytes to it directly while it decodes and only out[out_off[i], out_off[i] + out_len[i]) is written; otherwise the
+ * whole slots are copied back after the kernels.
  * Returns B2D_OK if the batch ran (inspect status[]), or a negative B2D_ERR_*. */
 int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_t n,
                       uint8_t *out, const uint64_t *out_off,

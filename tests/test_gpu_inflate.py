@@ -247,3 +247,44 @@ def test_random_garbage_members(b2d, oracle):
         assert outs[i] == out, i
         n_ok += st == 0
     assert n_ok < len(members) // 2
+
+
+def test_pinned_output_is_delivered_by_the_kernel(b2d, oracle):
+    """With a page-locked output buffer b2d_inflate_batch skips the D2H copy: the decoding warps write whole 128-byte
+    lines to the mapped host address themselves.  Same bytes, lengths, statuses as the pageable path, for ragged
+    slots at odd addresses, stored blocks, empty and failing members."""
+    rng = random.Random(4242)
+    members, caps = [], []
+    for n in (0, 1, 100, 127, 128, 129, 4095, 4096, 4097, 8191, 70000, 262144, 300001):
+        data = _text(rng, n)
+        for level, strat in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_FIXED), (0, zlib.Z_DEFAULT_STRATEGY)):
+            members.append(zlib_raw(data, level, strat))
+            caps.append(n + rng.randrange(0, 40))
+    rnd = rng.randbytes(200000)
+    members.append(zlib_raw(rnd, 0)); caps.append(200000)                    # stored blocks only
+    members.append(zlib_raw(bytes(500000), 9)); caps.append(500001)          # length 258 / distance 1
+    members.append(zlib_raw(_text(rng, 50000), 6)); caps.append(30000)       # slot too small: overflow after 30000 bytes
+    members.append(zlib_raw(_text(rng, 50000), 6)[:9000]); caps.append(50000)   # truncated stream
+    for v in VECTORS[:12]:
+        members.append(bits_to_bytes(v["bits"], "0", rng)); caps.append(64)
+    order = list(range(len(members)))
+    rng.shuffle(order)
+    members = [members[i] for i in order]
+    caps = [caps[i] for i in order]
+    ref = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32)
+    total = sum(caps)
+    for phase in (0, 3, 77):                                                 # the slots start at odd host addresses too
+        buf = b2d.PinnedBuffer(total + 256)
+        buf.array[:] = 0xEE
+        got = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32, out=buf.array[phase:phase + max(total, 1)])
+        assert got[0] == ref[0]
+        for k in range(1, 5):
+            assert np.array_equal(got[k], ref[k]), k
+        # nothing outside the delivered bytes is touched
+        assert (buf.array[:phase] == 0xEE).all() and (buf.array[phase + total:] == 0xEE).all()
+        off = phase
+        for i, c in enumerate(caps):
+            n = int(got[1][i])
+            assert (buf.array[off + n:off + c] == 0xEE).all(), i
+            off += c
+    _check_against_oracle(b2d, oracle, members, caps, flags=b2d.INFLATE_CRC32)
