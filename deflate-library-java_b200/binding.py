@@ -183,8 +183,9 @@ class PinnedBuffer:
 
 
 # ---- host-pointer entry points ----
-def inflate_batch(members, out_caps, flags=0, out=None):
+def inflate_batch(members, out_caps, flags=0, out=None, pinned_in=False):
     """members: list of bytes-like raw-DEFLATE members; out_caps: int or list of output capacities.
+    out: optional output array (e.g. PinnedBuffer(...).array); pinned_in: stage the members in page-locked memory.
     -> (outputs list[bytes], out_len, in_consumed, crc32, status) with numpy arrays for the last four."""
     n = len(members)
     if isinstance(out_caps, int):
@@ -195,6 +196,11 @@ def inflate_batch(members, out_caps, flags=0, out=None):
         in_off[i + 1] = in_off[i] + np.uint64(len(m))
         out_off[i + 1] = out_off[i] + np.uint64(out_caps[i])
     blob = np.frombuffer(b"".join(bytes(m) for m in members), dtype=np.uint8) if n else np.zeros(0, np.uint8)
+    keep = None
+    if pinned_in and blob.size:
+        keep = PinnedBuffer(blob.size + 5)
+        keep.array[1:1 + blob.size] = blob                       # odd start address on purpose
+        blob = keep.array[1:1 + blob.size]
     out, out_len, in_consumed, crc, status = inflate_batch_raw(blob, in_off, out_off, flags, out)
     outs = [bytes(out[int(out_off[i]):int(out_off[i]) + int(out_len[i])]) for i in range(n)]
     return outs, out_len, in_consumed, crc, status

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
 #include <mutex>
 #include <vector>
 #include <algorithm>
@@ -29,7 +30,7 @@ struct Ctx {
 	bool ready = false;
 	int device = -1;
 	int sm_count = 0;
-	cudaStream_t st[4] = {nullptr, nullptr, nullptr, nullptr};    // pipeline streams (one per slice)
+	cudaStream_t st[16] = {};                                    // pipeline streams (one per slice)
 	cudaEvent_t ev[24] = {};
 	DevBuf in, out, meta, scratch, crc, scratch2, bits;
 	void *pinned_meta = nullptr;
@@ -266,6 +267,7 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
                               const uint64_t *out_off, uint64_t *out_len, uint64_t *in_consumed, uint32_t *crc32,
                               int32_t *status, uint32_t flags) {
 	std::lock_guard<std::mutex> lk(g_mu);
+	const auto t_entry = std::chrono::steady_clock::now();
 	if (!g.ready) return B2D_ERR_NO_DEVICE;
 	if (n == 0) return B2D_OK;
 	if (!in_off || !out_off || !out_len || !in_consumed || !status) return B2D_ERR_BAD_ARGUMENT;
@@ -304,12 +306,19 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 	}
 	CK(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, g.st[0]));
 	CK(cudaEventRecord(g.ev[0], g.st[0]));
-	uint32_t n_slices = std::min<uint32_t>(4, std::max<uint32_t>(1, n / 1024));
+	uint32_t max_slices = 4, min_per = 1024;
+	if (const char *sl_ = getenv("B2D_INFLATE_SLICES")) {      // diagnostic: "slices[,members per slice at least]"
+		unsigned a_ = 0, b_ = 0;
+		int got = sscanf(sl_, "%u,%u", &a_, &b_);
+		if (got >= 1 && a_ >= 1 && a_ <= 16) max_slices = a_;
+		if (got >= 2 && b_ >= 1) min_per = b_;
+	}
+	uint32_t n_slices = std::min<uint32_t>(max_slices, std::max<uint32_t>(1, n / min_per));
 	uint32_t per = (n + n_slices - 1) / n_slices;
 	int k = 0;
 	const char *tr_ = getenv("B2D_TRACE");                  // diagnostic: the slices' H2D / kernel / D2H timeline on stderr
 	const bool trace = tr_ != nullptr && tr_[0] == '1';
-	cudaEvent_t te[4][4];
+	cudaEvent_t te[16][4];
 	for (uint32_t a = 0; a < n; a += per, k++) {
 		uint32_t b = std::min(n, a + per);
 		cudaStream_t st = g.st[k];
@@ -334,15 +343,24 @@ B2D_API int b2d_inflate_batch(const uint8_t *in, const uint64_t *in_off, uint32_
 		CK(cudaStreamWaitEvent(g.st[0], g.ev[s], 0));
 	}
 	CK(cudaMemcpyAsync(hm + m_len, dm + m_len, m_total - m_len, cudaMemcpyDeviceToHost, g.st[0]));
+	const auto t_issued = std::chrono::steady_clock::now();
 	CK(cudaStreamSynchronize(g.st[0]));
 	if (trace) {
+		const auto t_done = std::chrono::steady_clock::now();
+		fprintf(stderr, "[b2d trace] host: entry -> all work issued %.3f ms, -> synchronized %.3f ms\n",
+		        std::chrono::duration<double, std::milli>(t_issued - t_entry).count(),
+		        std::chrono::duration<double, std::milli>(t_done - t_entry).count());
 		for (int q = 0; q < k; q++) {
-			float t[4];
-			for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], te[0][0], te[q][j]);
+			float t[4] = {-1, -1, -1, -1};
+			for (int j = 0; j < 4; j++) {
+				cudaError_t ee = cudaEventElapsedTime(&t[j], te[0][0], te[q][j]);
+				if (ee != cudaSuccess) { fprintf(stderr, "[b2d trace] event (%d,%d): %s\n", q, j, cudaGetErrorString(ee)); cudaGetLastError(); }
+			}
 			fprintf(stderr, "[b2d trace] slice %d: h2d %.3f..%.3f ms, kernels ..%.3f ms, d2h ..%.3f ms%s\n", q, t[0], t[1], t[2], t[3],
 			        mirror ? " [output mirrored by the kernel]" : "");
-			for (int j = 0; j < 4; j++) cudaEventDestroy(te[q][j]);
 		}
+		for (int q = 0; q < k; q++)
+			for (int j = 0; j < 4; j++) cudaEventDestroy(te[q][j]);
 	}
 	memcpy(out_len, hm + m_len, (size_t)n * 8);
 	memcpy(in_consumed, hm + m_cons, (size_t)n * 8);

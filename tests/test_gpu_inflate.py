@@ -273,10 +273,16 @@ def test_pinned_output_is_delivered_by_the_kernel(b2d, oracle):
     caps = [caps[i] for i in order]
     ref = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32)
     total = sum(caps)
+    # page-locked input alone (copied to the device like pageable input, but asynchronously), and with a pinned output
+    got = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32, pinned_in=True)
+    assert got[0] == ref[0]
+    for k in range(1, 5):
+        assert np.array_equal(got[k], ref[k]), k
     for phase in (0, 3, 77):                                                 # the slots start at odd host addresses too
         buf = b2d.PinnedBuffer(total + 256)
         buf.array[:] = 0xEE
-        got = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32, out=buf.array[phase:phase + max(total, 1)])
+        got = b2d.inflate_batch(members, caps, b2d.INFLATE_CRC32, out=buf.array[phase:phase + max(total, 1)],
+                                pinned_in=phase != 3)
         assert got[0] == ref[0]
         for k in range(1, 5):
             assert np.array_equal(got[k], ref[k]), k
