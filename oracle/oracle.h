@@ -90,6 +90,15 @@ enum {
 size_t oracle_deflate(const uint8_t *in, size_t n, const int *strategies, int n_strategies,
                       int lookahead, int history, int search, uint8_t *out, size_t cap);
 
+/* The same with `new BinarySplit(substrategy, min_block_len)` as the stream's strategy (comp/BinarySplit.java:30-98),
+ * substrategy = the single strategy or the MultiStrategy of `strategies`: every lookahead block is recursively cut in
+ * halves while a cut makes it smaller, halves no shorter than min_block_len + 1.  *n_blocks (optional) = number of
+ * blocks chosen, judged at bit position 0.  The reference never uses BinarySplit by default and has no test for it:
+ * pinned by round trips and by never being larger than the unsplit stream. */
+size_t oracle_deflate_split(const uint8_t *in, size_t n, const int *strategies, int n_strategies,
+                            int lookahead, int history, int search, int min_block_len,
+                            uint8_t *out, size_t cap, size_t *n_blocks);
+
 /* Upper bound for oracle_deflate's output. */
 size_t oracle_deflate_bound(size_t n, int lookahead);
 

@@ -59,6 +59,10 @@ def lib():
             L.oracle_deflate.restype = ctypes.c_size_t
             L.oracle_deflate.argtypes = [u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]
+            L.oracle_deflate_split.restype = ctypes.c_size_t
+            L.oracle_deflate_split.argtypes = [u8p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_int), ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                               ctypes.c_size_t, szp]
             L.oracle_deflate_bound.restype = ctypes.c_size_t
             L.oracle_deflate_bound.argtypes = [ctypes.c_size_t, ctypes.c_int]
             L.oracle_package_merge.restype = None
@@ -119,6 +123,22 @@ def deflate(data, strategies=(RLE_DYNAMIC,), lookahead=64 * 1024, history=32 * 1
     if n == ctypes.c_size_t(-1).value:
         raise RuntimeError("oracle_deflate failed (bad arguments or bound too small)")
     return out.raw[:n]
+
+
+def deflate_split(data, strategies=(RLE_DYNAMIC,), min_block_len=4096, lookahead=64 * 1024, history=32 * 1024,
+                  brute_force=False):
+    """BinarySplit(substrategy, min_block_len) as the stream's strategy -> (compressed bytes, blocks chosen)."""
+    data = bytes(data)
+    L = lib()
+    strat = (ctypes.c_int * len(strategies))(*strategies)
+    cap = L.oracle_deflate_bound(len(data), min(lookahead, max(min_block_len, 1))) + len(data) // max(min_block_len, 1) * 400
+    out = ctypes.create_string_buffer(cap)
+    nb = ctypes.c_size_t(0)
+    n = L.oracle_deflate_split(data, len(data), strat, len(strategies), lookahead, history, 1 if brute_force else 0,
+                               min_block_len, out, cap, ctypes.byref(nb))
+    if n == ctypes.c_size_t(-1).value:
+        raise ValueError("oracle_deflate_split failed")
+    return out.raw[:n], nb.value
 
 
 def package_merge(hist, max_len):

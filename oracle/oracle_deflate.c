@@ -7,6 +7,7 @@
  *                                codeLengthsToCodes :372-391, static codes :394-410
  *   comp/Uncompressed.java       :19-48
  *   comp/MultiStrategy.java      :31-57
+ *   comp/BinarySplit.java        :30-98 (oracle_deflate_split)
  *   DeflaterOutputStream.java    framing :76-137, BitOut :141-171
  *
  * Encoder byte-level parity is UNPINNED (the reference has no golden compressed bytes and no JVM exists
@@ -448,5 +449,148 @@ size_t oracle_deflate(const uint8_t *in, size_t n, const int *strategies, int n_
 	}
 	finish_bits(&out);
 	if (chp) { free(ch.head); free(ch.prev); }
+	return out.overflow ? (size_t)-1 : out.pos;
+}
+
+
+/* ---------- BinarySplit (comp/BinarySplit.java:30-98) over MultiStrategy / a single strategy ---------- */
+
+typedef struct Dec {                /* one Decision object of BinarySplit.decide (:36-98) */
+	size_t start, end;
+	int64_t cost[8];                /* getBitLengths() */
+	int leaf_strategy[8];           /* the sub-strategy MultiStrategy picked per start bit position (:35-44) */
+	uint8_t use_split[8];           /* subdecisions[i] is the pair of halves (:62-69) */
+	struct Dec *sub[2];
+} Dec;
+
+typedef struct {
+	const uint8_t *in;
+	size_t off;                     /* start of the history available to the enclosing block */
+	const int *strategies;
+	int n_strategies;
+	Chains *ch;
+	int search;
+	int min_len;
+} SplitCtx;
+
+/* substrategy.decide(b, off, historyLen, dataLen): Lz77Huffman prices one pass on a counting sink and reports the
+ * same cost for all 8 bit positions (Lz77Huffman.java:46-52), Uncompressed has a cost per position
+ * (Uncompressed.java:23-25), MultiStrategy keeps the per-position minimum, the first listed winning ties (:35-44). */
+static Dec *leaf_decide(const SplitCtx *c, size_t start, size_t end) {
+	Dec *d = (Dec *)calloc(1, sizeof(Dec));
+	d->start = start; d->end = end;
+	for (int i = 0; i < 8; i++) { d->cost[i] = INT64_MAX; d->leaf_strategy[i] = c->strategies[0]; }
+	for (int k = 0; k < c->n_strategies; k++) {
+		int st = c->strategies[k];
+		int64_t lz = 0;
+		if (st != ORC_STRAT_UNCOMPRESSED) {
+			BitOut cnt;
+			memset(&cnt, 0, sizeof cnt);
+			cnt.counting = 1;
+			size_t mark = c->ch ? c->ch->inserted : 0;
+			lz77_block(&PRESETS[st], c->in, c->off, start, end, c->ch, c->search, &cnt, 0);
+			if (c->ch) chains_rollback(c->ch, mark);
+			lz = (int64_t)cnt.count;
+		}
+		for (int i = 0; i < 8; i++) {
+			int64_t cost = st == ORC_STRAT_UNCOMPRESSED ? stored_cost(end - start, i) : lz;
+			if (cost < d->cost[i]) { d->cost[i] = cost; d->leaf_strategy[i] = st; }
+		}
+	}
+	return d;
+}
+
+/* the accumulation of BinarySplit.java:49-53 / :60-64: it restarts at 0 for every i, i.e. the halves are always
+ * priced as if the first one started byte-aligned */
+static int64_t pair_bits(Dec *const *sp) {
+	int64_t bits = 0;
+	for (int k = 0; k < 2; k++) bits += sp[k]->cost[(int)(bits % 8)];
+	return bits;
+}
+
+static void split_decide(const SplitCtx *c, Dec *cur) {                /* BinarySplit.decide(b, off, hist, len, curDec) */
+	size_t len = cur->end - cur->start;
+	size_t first = (len + 1) / 2, second = len - first;
+	size_t mn = first < second ? first : second;
+	if (mn <= (size_t)c->min_len) return;                              /* :42 */
+	Dec *sp[2] = {leaf_decide(c, cur->start, cur->start + first), leaf_decide(c, cur->start + first, cur->end)};
+	int64_t bits = pair_bits(sp);
+	int improved = 0;
+	for (int i = 0; i < 8; i++) improved |= bits < cur->cost[i];       /* :47-54 */
+	if (improved) { split_decide(c, sp[0]); split_decide(c, sp[1]); }  /* :56-59 */
+	bits = pair_bits(sp);
+	int used = 0;
+	for (int i = 0; i < 8; i++)                                        /* :60-69 */
+		if (bits < cur->cost[i]) { cur->cost[i] = bits; cur->use_split[i] = 1; used = 1; }
+	cur->sub[0] = sp[0]; cur->sub[1] = sp[1];
+	(void)used;
+}
+
+static void split_emit(const SplitCtx *c, const Dec *d, BitOut *out, int is_final) {   /* compressTo :78-82 */
+	int pos = bit_position(out);
+	if (d->use_split[pos]) {
+		split_emit(c, d->sub[0], out, 0);
+		split_emit(c, d->sub[1], out, is_final);
+		return;
+	}
+	int st = d->leaf_strategy[pos];                                    /* MultiStrategy dispatches on the position again (:54) */
+	if (st == ORC_STRAT_UNCOMPRESSED) stored_emit(c->in, d->start, d->end, out, is_final);
+	else lz77_block(&PRESETS[st], c->in, c->off, d->start, d->end, c->ch, c->search, out, is_final);
+}
+
+static void split_free(Dec *d) {
+	if (!d) return;
+	split_free(d->sub[0]);
+	split_free(d->sub[1]);
+	free(d);
+}
+
+size_t oracle_deflate_split(const uint8_t *in, size_t n, const int *strategies, int n_strategies,
+                            int lookahead, int history, int search, int min_block_len,
+                            uint8_t *outbuf, size_t cap, size_t *n_blocks) {
+	if (n_strategies < 1 || n_strategies > 8 || lookahead < 1 || history < 0 || history > 32768 || min_block_len < 1)
+		return (size_t)-1;
+	for (int i = 0; i < n_strategies; i++)
+		if (strategies[i] < 0 || strategies[i] > ORC_STRAT_UNCOMPRESSED) return (size_t)-1;
+	init_static();
+	int need_chains = 0;
+	for (int i = 0; i < n_strategies; i++)
+		if (strategies[i] == ORC_STRAT_FULL_STATIC || strategies[i] == ORC_STRAT_FULL_DYNAMIC) need_chains = !search;
+	Chains ch, *chp = NULL;
+	if (need_chains && n >= 3) {
+		ch.data = in; ch.n = n; ch.inserted = 0;
+		ch.head = (int32_t *)malloc(sizeof(int32_t) << 24);
+		ch.prev = (int32_t *)malloc(sizeof(int32_t) * n);
+		memset(ch.head, 0xFF, sizeof(int32_t) << 24);
+		chp = &ch;
+	}
+	BitOut out;
+	memset(&out, 0, sizeof out);
+	out.out = outbuf; out.cap = cap;
+	size_t start = 0, blocks = 0;
+	for (;;) {                                                         /* DeflaterOutputStream framing, as oracle_deflate */
+		size_t remaining = n - start;
+		int is_final = remaining <= (size_t)lookahead;
+		size_t end = is_final ? n : start + (size_t)lookahead;
+		size_t hist_len = start < (size_t)history ? start : (size_t)history;
+		SplitCtx c = {in, start - hist_len, strategies, n_strategies, chp, search, min_block_len};
+		Dec *top = leaf_decide(&c, start, end);                        /* BinarySplit.decide :30-33 */
+		split_decide(&c, top);
+		size_t before = out.pos;
+		(void)before;
+		split_emit(&c, top, &out, is_final);
+		/* count the DEFLATE blocks this outer block became (leaves actually emitted at their positions are
+		 * not recoverable after the fact; count tree leaves reachable through position-0 decisions as a gauge) */
+		{
+			const Dec *stack[64]; int sp_ = 0; stack[sp_++] = top;
+			while (sp_) { const Dec *d = stack[--sp_]; if (d->use_split[0] && sp_ < 62) { stack[sp_++] = d->sub[0]; stack[sp_++] = d->sub[1]; } else blocks++; }
+		}
+		split_free(top);
+		if (is_final) break;
+		start = end;
+	}
+	finish_bits(&out);
+	if (chp) { free(ch.head); free(ch.prev); }
+	if (n_blocks) *n_blocks = blocks;
 	return out.overflow ? (size_t)-1 : out.pos;
 }

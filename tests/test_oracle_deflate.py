@@ -158,3 +158,48 @@ def test_zlib_container_oracle(oracle):
     assert oracle.status_name(oracle.unzlib(bytes([0x77, fix]) + z[2:])[0]) == "UNSUPPORTED_COMPRESSION_METHOD"
     assert oracle.status_name(oracle.unzlib(z[:-1] + bytes([z[-1] ^ 1]))[0]) == "DECOMPRESSED_CHECKSUM_MISMATCH"
     assert oracle.status_name(oracle.unzlib(z[:-2])[0]) == "UNEXPECTED_END_OF_STREAM"
+
+
+# ---- BinarySplit (comp/BinarySplit.java): the reference ships it, never uses it by default and has no test for it ----
+def _mixed(rng):
+    words = [bytes(rng.choices(b"etaoinshrdlucmfw", k=rng.randrange(1, 10))) for _ in range(400)]
+    def text(n):
+        out = bytearray()
+        while len(out) < n:
+            out += rng.choice(words) + b" "
+        return bytes(out[:n])
+    return text(40000) + rng.randbytes(30000) + bytes(20000) + text(25000) + bytes(range(256)) * 60
+
+
+@pytest.mark.parametrize("strategies", [(3,), (5,), (6, 4, 5)], ids=["RLE_DYNAMIC", "FULL_DYNAMIC", "Multi"])
+def test_binary_split_roundtrip_and_never_worse(oracle, strategies):
+    """BinarySplit.decide keeps a cut only where it is cheaper (:60-69), so the stream is never larger than the
+    substrategy's own, it decodes to the input through both decoders, and on data whose statistics change inside a
+    block it is strictly smaller; with a minimum length of half the block no cut is allowed (:42)."""
+    rng = random.Random(77)
+    data = _mixed(rng)
+    plain = oracle.deflate(data, strategies)
+    prev_blocks = None
+    for min_len in (1, 1000, 4096, 16384):
+        comp, blocks = oracle.deflate_split(data, strategies, min_len)
+        st, out, cons = oracle.inflate(comp, out_cap=len(data) + 8)
+        assert st == 0 and out == data and cons == len(comp)
+        assert zlib_inflate_raw(comp)[0] == data
+        assert len(comp) < len(plain)
+        assert prev_blocks is None or blocks <= prev_blocks          # a larger minimum allows fewer cuts
+        prev_blocks = blocks
+    comp, blocks = oracle.deflate_split(data, strategies, 32768)
+    assert comp == plain                                             # halves of a 64 KiB block are not > 32768: no cut
+    for data in (b"", b"a", bytes(1000), rng.randbytes(70000)):
+        comp, _ = oracle.deflate_split(data, strategies, 8)
+        st, out, _ = oracle.inflate(comp, out_cap=len(data) + 8)
+        assert st == 0 and out == data
+        assert len(comp) <= len(oracle.deflate(data, strategies))
+
+
+def test_binary_split_brute_force_equals_hash_chains(oracle):
+    rng = random.Random(78)
+    data = _mixed(rng)[:30000]
+    a = oracle.deflate_split(data, (5,), 512, brute_force=True)
+    b = oracle.deflate_split(data, (5,), 512, brute_force=False)
+    assert a == b
