@@ -55,7 +55,8 @@ class B2dError(RuntimeError):
 class DeflateOpts(ctypes.Structure):
     _fields_ = [("chunk_bytes", ctypes.c_uint32), ("block_bytes", ctypes.c_uint32), ("mode", ctypes.c_int32),
                 ("search", ctypes.c_int32), ("chain_depth", ctypes.c_int32), ("lazy", ctypes.c_int32),
-                ("is_last", ctypes.c_int32), ("framing", ctypes.c_int32), ("checksum", ctypes.c_int32)]
+                ("is_last", ctypes.c_int32), ("framing", ctypes.c_int32), ("checksum", ctypes.c_int32),
+                ("split_min_bytes", ctypes.c_uint32)]
 
 
 _lib = None
@@ -155,8 +156,9 @@ def _ptr(a):
 
 
 def make_opts(chunk_bytes=0, block_bytes=0, mode=MODE_AUTO, search=SEARCH_DEFAULT, chain_depth=0, lazy=-1, is_last=1,
-              framing=FRAMING_CHUNKED, checksum=0):
-    return DeflateOpts(chunk_bytes, block_bytes, mode, search, chain_depth, lazy, is_last, framing, checksum)
+              framing=FRAMING_CHUNKED, checksum=0, split_min_bytes=0):
+    return DeflateOpts(chunk_bytes, block_bytes, mode, search, chain_depth, lazy, is_last, framing, checksum,
+                       split_min_bytes)
 
 
 # ---- corpora (host) ----

@@ -122,6 +122,14 @@ int normalise_opts(const b2d_deflate_opts *o, uint64_t in_len, DeflateParams &p)
 	p.is_last = d.is_last ? 1 : 0;
 	p.checksum = d.checksum;
 	if (p.checksum != B2D_CHECKSUM_CRC32 && p.checksum != B2D_CHECKSUM_ADLER32) return B2D_ERR_BAD_ARGUMENT;
+	p.leaf_bytes = 0;
+	if (d.split_min_bytes && d.split_min_bytes < p.block_bytes) {
+		const uint32_t l = d.split_min_bytes;
+		if (l < 4096 || (l & (l - 1)) || p.block_bytes % l != 0 || p.block_bytes / l > 16 ||
+		    ((p.block_bytes / l) & (p.block_bytes / l - 1)))
+			return B2D_ERR_BAD_ARGUMENT;
+		p.leaf_bytes = l;
+	}
 	return 0;
 }
 

@@ -53,7 +53,32 @@ struct BlockRec {
 	u32 mode;               // set by layout: 1 stored, 2 fixed, 3 dynamic
 	u32 bfinal;
 	u64 out_bit;            // bit offset of the block inside its chunk's output
+	u64 tok_bit;            // adaptive splitting, piece records: bit offset of the piece's first token
+	// adaptive splitting (split_decide_kernel): for piece (leaf) records
+	u32 owner;              // heap index of the node that is emitted as the block holding this piece
+	u32 first_last;         // bit 0: first piece of that block, bit 1: last piece
+	u32 body_dyn, body_fixed;   // bits of this piece's tokens (without end-of-block) under the block's dynamic / the fixed code
+	u32 best_cost;          // any node: cheapest cost in bits of its span (one block, or the best split below it)
 };
+
+// Adaptive splitting keeps the records of one block_bytes span as a complete binary tree in heap order: node 0 is the
+// whole span, nodes 2h+1 / 2h+2 are the halves of node h, the K = block_bytes / leaf_bytes pieces are the leaves
+// K-1 .. 2K-2.  Without splitting K = 1 and the tree is the single record there has always been.
+struct Heap {
+	u32 K, H;               // leaves and nodes per span (H = 2K - 1)
+	u32 block_bytes, leaf_bytes;
+};
+__device__ __host__ __forceinline__ u32 heap_level(u32 h) { u32 l = 0; for (u32 v = h + 1; v > 1; v >>= 1) l++; return l; }
+// byte range of node h of span `root`
+__device__ __forceinline__ void heap_range(const Heap &hp, u32 root, u32 h, u64 n, u64 &start, u64 &len) {
+	const u32 lvl = heap_level(h), idx = h + 1 - (1u << lvl), size = hp.block_bytes >> lvl;
+	const u64 s0 = (u64)root * hp.block_bytes + (u64)idx * size;
+	start = min(n, s0);
+	len = min(n, s0 + size) - start;
+}
+__device__ __forceinline__ u32 leaf_slot(const Heap &hp, u32 leaf) {       // record index of piece number `leaf`
+	return (leaf / hp.K) * hp.H + hp.K - 1 + leaf % hp.K;
+}
 
 // ---------------------------------------------------------------- helpers
 __device__ __forceinline__ u32 load4_global(const u8 *in, u64 p, u64 n_words) {   // unaligned LE 4-byte read
@@ -304,7 +329,7 @@ __device__ __forceinline__ void hist_token(u32 *hist, u32 tok) {
 
 __global__ void __launch_bounds__(PARSE_WARPS * 32)
 parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks, int lazy,
-             u32 *__restrict__ tokens, BlockRec *__restrict__ recs) {
+             u32 *__restrict__ tokens, BlockRec *__restrict__ recs, Heap hp) {
 	__shared__ u32 hist_sm[PARSE_WARPS][320];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 g = blockIdx.x * PARSE_WARPS + warp;
@@ -374,10 +399,11 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 		hist_token(hist, my_tok);
 	}
 	__syncwarp();
-	if (lane == 0) { hist[256] += 1; recs[g].n_tokens = ntok; }   // end-of-block (Lz77Huffman.java:131-132)
+	BlockRec *rec = &recs[leaf_slot(hp, g)];
+	if (lane == 0) { hist[256] += 1; rec->n_tokens = ntok; }      // end-of-block (Lz77Huffman.java:131-132)
 	__syncwarp();
-	for (int k = lane; k < 288; k += 32) recs[g].hist_ll[k] = hist[k];
-	recs[g].hist_d[lane] = hist[288 + lane];
+	for (int k = lane; k < 288; k += 32) rec->hist_ll[k] = hist[k];
+	rec->hist_d[lane] = hist[288 + lane];
 }
 #undef LOADM
 
@@ -529,15 +555,17 @@ __device__ __forceinline__ void bw_put(BitW &b, u32 v, int n) {      // single w
 }
 
 __global__ void __launch_bounds__(HUFF_WARPS * 32)
-huffman_kernel(BlockRec *__restrict__ recs, u32 n_blocks, u64 n, u32 block_bytes) {
+huffman_kernel(BlockRec *__restrict__ recs, u32 n_recs, u64 n, Heap hp) {
 	__shared__ HuffSmem hs[HUFF_WARPS];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 g = blockIdx.x * HUFF_WARPS + warp;
-	if (g >= n_blocks) return;
+	if (g >= n_recs) return;
 	HuffSmem *s = &hs[warp];
 	BlockRec *rec = &recs[g];
-	const u64 bs = (u64)g * block_bytes;
-	const u32 data_len = (u32)(min(n, bs + block_bytes) - min(n, bs));
+	u64 bs, dl64;
+	heap_range(hp, g / hp.H, g % hp.H, n, bs, dl64);
+	const u32 data_len = (u32)dl64;
+	if (data_len == 0 && n != 0 && hp.K > 1) return;                       // a node past the end of the input
 	for (int i = lane; i < 288; i += 32) s->hist[i] = rec->hist_ll[i];
 	s->hist[288 + lane] = rec->hist_d[lane];
 	__syncwarp();
@@ -648,39 +676,161 @@ huffman_kernel(BlockRec *__restrict__ recs, u32 n_blocks, u64 n, u32 block_bytes
 	}
 }
 
+// ---------------------------------------------------------------- adaptive block splitting (comp/BinarySplit.java)
+// The reference cuts a block in halves top-down and keeps a cut where the two halves, priced by the sub-strategy,
+// are cheaper (BinarySplit.java:36-98).  Here every node of the span's binary tree gets its real codes and costs
+// (huffman_kernel runs on all of them), and the cheapest partition is found bottom-up: at least as good as the
+// top-down rule, which stops at the first level that does not pay.  The pieces were parsed once, at the leaf size;
+// a block made of several pieces is emitted by its pieces' CTAs with the block's codes.
+
+// K3a': histograms of the inner nodes = sums of their halves; one warp per span
+__global__ void __launch_bounds__(128)
+node_hist_kernel(BlockRec *__restrict__ recs, u32 n_roots, u64 n, Heap hp) {
+	const u32 lane = threadIdx.x & 31;
+	const u32 root = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (root >= n_roots) return;
+	BlockRec *base = recs + (size_t)root * hp.H;
+	for (int h = (int)hp.K - 2; h >= 0; h--) {
+		u64 s0, l0, s1, l1;
+		heap_range(hp, root, 2 * h + 1, n, s0, l0);
+		heap_range(hp, root, 2 * h + 2, n, s1, l1);
+		if (l0 == 0) continue;                                              // the node lies past the end of the input
+		BlockRec *a = base + 2 * h + 1, *b = base + 2 * h + 2, *o = base + h;
+		for (int k = lane; k < 288; k += 32) o->hist_ll[k] = a->hist_ll[k] + (l1 ? b->hist_ll[k] : 0u);
+		o->hist_d[lane] = a->hist_d[lane] + (l1 ? b->hist_d[lane] : 0u);
+		__syncwarp();
+		if (lane == 0) { o->hist_ll[256] = 1; o->n_tokens = a->n_tokens + (l1 ? b->n_tokens : 0u); }   // one end-of-block
+		__syncwarp();
+	}
+}
+
+__device__ __forceinline__ u64 stored_bits(u64 dl, int i) {                  // Uncompressed.java:23-25
+	const u64 nsb = max((u64)1, (dl + 65534) / 65535);
+	return (u64)((long long)(dl * 8 + nsb * 40) + (((13 - i) % 8) - 5));
+}
+__device__ __forceinline__ u64 single_cost(const BlockRec *r, u64 dl, int i, int mode, u32 &m) {
+	const u64 sc = stored_bits(dl, i);
+	if (mode == B2D_MODE_STORED) { m = 1; return sc; }
+	if (mode == B2D_MODE_FIXED) { m = 2; return r->cost_fixed; }
+	if (mode == B2D_MODE_DYNAMIC) { m = 3; return r->cost_dyn; }
+	u64 best = sc;                                                          // first listed wins ties (MultiStrategy.java:39)
+	m = 1;
+	if (r->cost_fixed < best) { m = 2; best = r->cost_fixed; }
+	if (r->cost_dyn < best) { m = 3; best = r->cost_dyn; }
+	return best;
+}
+
+// K3a'': cheapest partition of every span, owners of the pieces, and the size of every piece's tokens under its
+// block's codes; one warp per span, lane h = node h (at most 31 nodes)
+__global__ void __launch_bounds__(128)
+split_decide_kernel(BlockRec *__restrict__ recs, u32 n_roots, u64 n, Heap hp, int mode) {
+	const u32 lane = threadIdx.x & 31;
+	const u32 root = blockIdx.x * 4 + (threadIdx.x >> 5);
+	if (root >= n_roots) return;
+	BlockRec *base = recs + (size_t)root * hp.H;
+	u64 st, dl = 0;
+	if (lane < hp.H) heap_range(hp, root, lane, n, st, dl);
+	const bool exists = lane < hp.H && dl > 0;
+	const bool leaf = lane >= hp.K - 1;
+	u32 m;
+	const u64 single = exists ? single_cost(base + lane, dl, 0, mode, m) : 0;
+	u64 best = single;
+	bool split = false;
+	for (u32 it = 0; it < 5; it++) {                                        // depth <= 4: values settle bottom-up
+		const u64 bl = __shfl_sync(FULL_MASK, best, (2 * lane + 1) & 31), br = __shfl_sync(FULL_MASK, best, (2 * lane + 2) & 31);
+		if (exists && !leaf) {
+			split = bl + br < single;                                       // a cut has to pay (BinarySplit.java:64)
+			best = split ? bl + br : single;
+		}
+	}
+	const u32 splitmask = __ballot_sync(FULL_MASK, split);
+	if (exists) base[lane].best_cost = (u32)min(best, (u64)0xFFFFFFFFu);
+	// pieces: lane j = piece j of the span
+	u64 s0, span_len;
+	heap_range(hp, root, 0, n, s0, span_len);
+	const u32 n_exist = (u32)((span_len + hp.leaf_bytes - 1) / hp.leaf_bytes);
+	u32 owner = 0, lo = 0, cnt = hp.K;
+	while ((splitmask >> owner) & 1) {
+		cnt >>= 1;
+		if (lane < lo + cnt) owner = 2 * owner + 1;
+		else { owner = 2 * owner + 2; lo += cnt; }
+	}
+	const u32 last_piece = min(lo + cnt, n_exist) - 1;
+	if (lane < n_exist) {
+		BlockRec *L = base + hp.K - 1 + lane;
+		L->owner = owner;
+		L->first_last = (lane == lo ? 1u : 0u) | (lane == last_piece ? 2u : 0u);
+	}
+	__syncwarp();
+	for (u32 j = 0; j < n_exist; j++) {
+		const u32 ow = __shfl_sync(FULL_MASK, owner, j);
+		const BlockRec *O = base + ow;
+		BlockRec *L = base + hp.K - 1 + j;
+		u32 dyn = 0, fixed = 0;
+		for (int k = lane; k < 286; k += 32) {
+			const u32 c = L->hist_ll[k] - (k == 256 ? 1u : 0u);             // the piece's own end-of-block is not emitted
+			dyn += c * ((O->code_ll[k] & 15) + ll_extra_bits(k));
+			fixed += c * (fixed_ll_len(k) + ll_extra_bits(k));
+		}
+		if (lane < 30) {
+			const u32 c = L->hist_d[lane];
+			dyn += c * ((O->code_d[lane] & 15) + d_extra_bits(lane));
+			fixed += c * (5 + d_extra_bits(lane));
+		}
+		dyn = warp_sum(dyn);
+		fixed = warp_sum(fixed);
+		if (lane == 0) { L->body_dyn = dyn; L->body_fixed = fixed; }
+	}
+}
+
 // ---------------------------------------------------------------- K3b: per-chunk layout, K3c: scan
 // Per block the cheapest of stored / fixed / dynamic for the block's actual start bit position, first listed
 // wins ties (MultiStrategy.java:35-44,54); stored cost per Uncompressed.java:23-25.
 __global__ void layout_kernel(BlockRec *__restrict__ recs, u32 n_blocks, u32 n_chunks, u64 n, u32 chunk_bytes,
                               u32 block_bytes, int mode, int is_last, int ref_framing, u64 *__restrict__ chunk_len,
-                              u64 *__restrict__ chunk_tail) {
+                              u64 *__restrict__ chunk_tail, Heap hp) {
 	u32 c = blockIdx.x * blockDim.x + threadIdx.x;
 	if (c >= n_chunks) return;
-	const u32 bpc = chunk_bytes / block_bytes;
+	const u32 bpc = chunk_bytes / block_bytes;          // block_bytes here = the parse unit (the leaf size when splitting)
 	const u32 g0 = c * bpc;
 	const u32 g1 = min(n_blocks, g0 + bpc);
 	u64 bit = 0;
-	for (u32 g = g0; g < g1; g++) {
-		BlockRec *r = &recs[g];
-		const u64 bs = (u64)g * block_bytes;
-		const u64 dl = min(n, bs + block_bytes) - min(n, bs);
-		const int i = (int)(bit & 7);
-		const u64 nsb = max((u64)1, (dl + 65534) / 65535);
-		const u64 stored_cost = (u64)((long long)(dl * 8 + nsb * 40) + (((13 - i) % 8) - 5));
-		u64 best;
-		u32 m;
-		if (mode == B2D_MODE_STORED) { m = 1; best = stored_cost; }
-		else if (mode == B2D_MODE_FIXED) { m = 2; best = r->cost_fixed; }
-		else if (mode == B2D_MODE_DYNAMIC) { m = 3; best = r->cost_dyn; }
-		else {
-			m = 1; best = stored_cost;
-			if (r->cost_fixed < best) { m = 2; best = r->cost_fixed; }
-			if (r->cost_dyn < best) { m = 3; best = r->cost_dyn; }
+	if (hp.K == 1) {
+		for (u32 g = g0; g < g1; g++) {
+			BlockRec *r = &recs[g];
+			const u64 bs = (u64)g * block_bytes;
+			const u64 dl = min(n, bs + block_bytes) - min(n, bs);
+			u32 m;
+			const u64 best = single_cost(r, dl, (int)(bit & 7), mode, m);
+			r->mode = m;
+			r->out_bit = bit;
+			r->bfinal = (ref_framing && is_last && g + 1 == n_blocks) ? 1u : 0u;
+			bit += best;
 		}
-		r->mode = m;
-		r->out_bit = bit;
-		r->bfinal = (ref_framing && is_last && g + 1 == n_blocks) ? 1u : 0u;
-		bit += best;
+	} else {
+		u64 blk_start = 0, run = 0, blk_stored = 0;
+		u32 m = 0, eob = 0;
+		for (u32 g = g0; g < g1; g++) {
+			BlockRec *L = &recs[leaf_slot(hp, g)];
+			const u32 root = g / hp.K;
+			BlockRec *O = &recs[(size_t)root * hp.H + L->owner];
+			if (L->first_last & 1) {
+				u64 os, ol;
+				heap_range(hp, root, L->owner, n, os, ol);
+				(void)single_cost(O, ol, (int)(bit & 7), mode, m);
+				blk_stored = stored_bits(ol, (int)(bit & 7));
+				const u32 pieces = hp.K >> heap_level(L->owner);
+				O->mode = m;
+				O->out_bit = bit;
+				O->bfinal = (ref_framing && is_last && min(g + pieces, n_blocks) == n_blocks) ? 1u : 0u;
+				blk_start = bit;
+				run = bit + 3 + (m == 3 ? O->hdr_bits : 0u);
+				eob = m == 3 ? (O->code_ll[256] & 15) : 7u;
+			}
+			L->tok_bit = run;
+			run += m == 3 ? L->body_dyn : m == 2 ? L->body_fixed : 0u;
+			if (L->first_last & 2) bit = m == 1 ? blk_start + blk_stored : run + eob;
+		}
 	}
 	chunk_tail[c] = bit;
 	if (!ref_framing) {
@@ -748,17 +898,23 @@ __device__ __forceinline__ void or_bits_shared(u32 *w, u32 bitpos, u64 v, int nb
 __global__ void __launch_bounds__(EMIT_THREADS)
 emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, u32 n_blocks, u32 n_chunks,
             const BlockRec *__restrict__ recs, const u32 *__restrict__ tokens, const u64 *__restrict__ chunk_off,
-            const u64 *__restrict__ chunk_tail, int is_last, int ref_framing, u8 *out) {
+            const u64 *__restrict__ chunk_tail, int is_last, int ref_framing, u8 *out, Heap hp) {
 	__shared__ u32 code_ll[288];
 	__shared__ u32 code_d[32];
 	__shared__ u32 stage[EMIT_STAGE_WORDS];
 	__shared__ u32 warp_tot[EMIT_THREADS / 32];
+	// One CTA per parse unit (block_bytes here: the leaf size when splitting).  `r` is the record of the DEFLATE block
+	// the unit belongs to -- its own without splitting -- and `piece` the unit's own record: the block's first unit
+	// writes the block header (a stored block: everything), every unit its own tokens with the block's codes, the
+	// last one the end-of-block symbol.
 	const u32 g = blockIdx.x;
 	const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-	const BlockRec *r = &recs[g];
+	const BlockRec *piece = &recs[leaf_slot(hp, g)];
+	const BlockRec *r = hp.K == 1 ? piece : &recs[(size_t)(g / hp.K) * hp.H + piece->owner];
+	const bool first = hp.K == 1 || (piece->first_last & 1), last = hp.K == 1 || (piece->first_last & 2);
 	const u32 c = g / (chunk_bytes / block_bytes);
-	const u64 bs = (u64)g * block_bytes;
-	const u64 dl = min(n, bs + block_bytes) - bs;
+	u64 bs = (u64)g * block_bytes;
+	u64 dl = min(n, bs + block_bytes) - bs;
 	u32 *outw = (u32 *)out;
 	u64 bit = chunk_off[c] * 8 + r->out_bit;
 	const u32 mode = r->mode;
@@ -773,6 +929,8 @@ emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, 
 	}
 
 	if (mode == 1) {                                   // stored (Uncompressed.java:35-45)
+		if (!first) return;
+		if (hp.K > 1) heap_range(hp, g / hp.K, piece->owner, n, bs, dl);   // the whole block's bytes
 		u64 pos = bs, end = bs + dl;
 		do {
 			u64 nb = min((u64)65535, end - pos);
@@ -810,26 +968,28 @@ emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, 
 		: ((__brev((u32)(i < 144 ? 0x30 + i : i < 256 ? 0x190 + i - 144 : i < 280 ? i - 256 : 0xC0 + i - 280)) >> (32 - fixed_ll_len(i))) << 4 | (u32)fixed_ll_len(i));
 	if (tid < 32) code_d[tid] = mode == 3 ? r->code_d[tid] : ((__brev(tid) >> 27) << 4 | 5u);
 	for (int i = tid; i < EMIT_STAGE_WORDS; i += EMIT_THREADS) stage[i] = 0;
-	if (tid == 0) or_bits_global(outw, bit, (r->bfinal ? 1u : 0u) | (mode == 3 ? 2u : 1u) << 1, 3);
+	if (first && tid == 0) or_bits_global(outw, bit, (r->bfinal ? 1u : 0u) | (mode == 3 ? 2u : 1u) << 1, 3);
 	bit += 3;
 	if (mode == 3) {                                   // dynamic header
 		const u32 hb = r->hdr_bits;
-		for (u32 w = tid; w * 32 < hb; w += EMIT_THREADS) {
-			int nb = (int)min(32u, hb - w * 32);
-			or_bits_global(outw, bit + (u64)w * 32, r->hdr[w], nb);
-		}
+		if (first)
+			for (u32 w = tid; w * 32 < hb; w += EMIT_THREADS) {
+				int nb = (int)min(32u, hb - w * 32);
+				or_bits_global(outw, bit + (u64)w * 32, r->hdr[w], nb);
+			}
 		bit += hb;
 	}
+	if (hp.K > 1) bit = chunk_off[c] * 8 + piece->tok_bit;    // this piece's tokens start where layout_kernel put them
 	__syncthreads();
 
-	const u32 ntok = r->n_tokens + 1;                  // + end-of-block
+	const u32 ntok = piece->n_tokens + (last ? 1u : 0u);      // + end-of-block
 	const u32 *tk = tokens + bs;
 	for (u32 base = 0; base < ntok; base += EMIT_THREADS) {
 		const u32 t = base + tid;
 		u64 bits = 0;
 		int nb = 0;
 		if (t < ntok) {
-			if (t + 1 == ntok) { u32 p = code_ll[256]; bits = p >> 4; nb = p & 15; }
+			if (last && t + 1 == ntok) { u32 p = code_ll[256]; bits = p >> 4; nb = p & 15; }
 			else {
 				u32 e = tk[t];
 				int len = (int)tok_len(e);
@@ -871,9 +1031,12 @@ emit_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes, 
 }
 
 // ---------------------------------------------------------------- block index for the block-parallel decoder
-__global__ void block_bits_kernel(const BlockRec *__restrict__ recs, u32 n_blocks, u32 *__restrict__ out) {
+__global__ void block_bits_kernel(const BlockRec *__restrict__ recs, u32 n_roots, u32 *__restrict__ out, Heap hp) {
 	const u32 g = blockIdx.x * blockDim.x + threadIdx.x;
-	if (g < n_blocks) out[g] = (u32)recs[g].out_bit;       // bit offset of the block inside its chunk's output
+	if (g >= n_roots) return;
+	// bit offset, inside its chunk's output, of the (first) block of every block_bytes span
+	const BlockRec *base = recs + (size_t)g * hp.H;
+	out[g] = (u32)(hp.K == 1 ? base->out_bit : base[base[hp.K - 1].owner].out_bit);
 }
 
 // ---------------------------------------------------------------- host side
@@ -888,6 +1051,7 @@ uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t blo
 }
 size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p) {
 	u64 n_blocks = (in_len + p.block_bytes - 1) / p.block_bytes;
+	if (p.leaf_bytes) n_blocks *= 2 * (p.block_bytes / p.leaf_bytes) - 1;     // the spans' binary trees
 	u64 n_chunks = (in_len + p.chunk_bytes - 1) / p.chunk_bytes;
 	size_t s = 0;
 	s += ((in_len * 2 + 255) & ~(u64)255) + 256;          // prevdist u16
@@ -915,16 +1079,25 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	}
 	const int ref_framing = p.framing == 1;
 	const int is_last = p.is_last;
-	u32 n_blocks = (u32)((n + p.block_bytes - 1) / p.block_bytes);
+	// parse unit: the block, or the piece of adaptive splitting (then a block_bytes span owns a heap of records)
+	Heap hp;
+	hp.block_bytes = p.block_bytes;
+	hp.leaf_bytes = (p.leaf_bytes && n) ? p.leaf_bytes : p.block_bytes;
+	hp.K = hp.block_bytes / hp.leaf_bytes;
+	hp.H = 2 * hp.K - 1;
+	const u32 unit = hp.leaf_bytes;
+	u32 n_blocks = (u32)((n + unit - 1) / unit);                 // parse units
+	u32 n_roots = (u32)((n + p.block_bytes - 1) / p.block_bytes);
 	u32 n_chunks = (u32)((n + p.chunk_bytes - 1) / p.chunk_bytes);
-	if (ref_framing && n == 0) { n_blocks = 1; n_chunks = 1; }   // the reference writes one (empty) final block
+	if (ref_framing && n == 0) { n_blocks = 1; n_roots = 1; n_chunks = 1; }   // the reference writes one (empty) final block
+	const u32 n_recs = n_roots * hp.H;
 	// carve scratch
 	u8 *sp = (u8 *)d_scratch;
 	auto carve = [&](size_t bytes) { u8 *r = sp; sp += (bytes + 255) & ~(size_t)255; return r; };
 	u16 *prevdist = (u16 *)carve(n * 2 + 256);
 	u32 *match = (u32 *)carve(n * 4 + 256);
 	u32 *tokens = (u32 *)carve(n * 4 + 256);
-	BlockRec *recs = (BlockRec *)carve((size_t)n_blocks * sizeof(BlockRec) + 256);
+	BlockRec *recs = (BlockRec *)carve((size_t)n_recs * sizeof(BlockRec) + 256);
 	u64 *chunk_len = (u64 *)carve((size_t)(n_chunks + 2) * 8);
 	u64 *chunk_off = (u64 *)carve((size_t)(n_chunks + 2) * 8);
 	u64 *chunk_tail = (u64 *)carve((size_t)(n_chunks + 2) * 8);
@@ -951,17 +1124,19 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 			chains_kernel<<<n_segs, 32, 2 << HASH_BITS, st>>>(d_in, n, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist);
 		}
 		const u32 n_tiles = (u32)((n + TILE - 1) / TILE);
-		if (n_tiles) match_kernel<<<n_tiles, MATCH_THREADS, MATCH_SMEM, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, mp, prevdist, match);
+		if (n_tiles) match_kernel<<<n_tiles, MATCH_THREADS, MATCH_SMEM, st>>>(d_in, n, p.chunk_bytes, unit, mp, prevdist, match);
 		parse_kernel<<<(n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st>>>(
-			match, n, p.block_bytes, n_blocks, p.lazy, tokens, recs);
-		huffman_kernel<<<(n_blocks + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_blocks, n, p.block_bytes);
+			match, n, unit, n_blocks, p.lazy, tokens, recs, hp);
+		if (hp.K > 1) node_hist_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp);
+		huffman_kernel<<<(n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_recs, n, hp);
 	}
-	layout_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(recs, n_blocks, n_chunks, n, p.chunk_bytes, p.block_bytes,
-	                                                     p.mode, is_last, ref_framing, chunk_len, chunk_tail);
+	if (hp.K > 1) split_decide_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp, p.mode);
+	layout_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(recs, n_blocks, n_chunks, n, p.chunk_bytes, unit,
+	                                                     p.mode, is_last, ref_framing, chunk_len, chunk_tail, hp);
 	scan_kernel<<<1, 1024, 0, st>>>(chunk_len, n_chunks, chunk_off, d_out_len_total, d_chunk_out_len);
-	emit_kernel<<<n_blocks, EMIT_THREADS, 0, st>>>(d_in, n, p.chunk_bytes, p.block_bytes, n_blocks, n_chunks, recs,
-	                                               tokens, chunk_off, chunk_tail, is_last, ref_framing, d_out);
-	if (d_block_bits) block_bits_kernel<<<(n_blocks + 255) / 256, 256, 0, st>>>(recs, n_blocks, d_block_bits);
+	emit_kernel<<<n_blocks, EMIT_THREADS, 0, st>>>(d_in, n, p.chunk_bytes, unit, n_blocks, n_chunks, recs,
+	                                               tokens, chunk_off, chunk_tail, is_last, ref_framing, d_out, hp);
+	if (d_block_bits) block_bits_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(recs, n_roots, d_block_bits, hp);
 	return cudaGetLastError();
 }
 

@@ -46,6 +46,7 @@ struct DeflateParams {
 	int mode, search, depth, lazy, is_last;
 	int checksum;     // B2D_CHECKSUM_*: what the per-chunk checksum array holds
 	int framing;      // 0 = chunks closed by empty stored blocks; 1 = reference framing (one chunk, BFINAL on the last block)
+	uint32_t leaf_bytes;   // 0 = no splitting; else the piece size of adaptive splitting (divides block_bytes)
 };
 uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t block_bytes);
 size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p);

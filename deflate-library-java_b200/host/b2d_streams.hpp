@@ -356,6 +356,7 @@ struct DeflaterOptions {                     // the GPU build's counterpart of (
 	int lazy = -1;
 	uint64_t batch_bytes = 256ull << 20;     // input buffered per GPU call
 	int checksum = B2D_CHECKSUM_CRC32;       // which checksum of the input rides the GPU call (gzip: CRC-32, zlib: Adler-32)
+	uint32_t split_min_bytes = 0;            // != 0: `new BinarySplit(strategy, n)`-style adaptive blocks (comp/BinarySplit.java)
 };
 
 class DeflaterOutputStream : public OutputStream {
@@ -415,6 +416,7 @@ private:
 		o.chunk_bytes = opt.chunk_bytes; o.block_bytes = opt.block_bytes; o.mode = opt.mode; o.search = opt.search;
 		o.chain_depth = opt.chain_depth; o.lazy = opt.lazy; o.is_last = last ? 1 : 0; o.framing = B2D_FRAMING_CHUNKED;
 		o.checksum = opt.checksum;
+		o.split_min_bytes = opt.split_min_bytes;
 		const uint64_t bound = b2d_deflate_bound(fill, opt.chunk_bytes);
 		comp.reserve(bound);
 		stage.reserve(1);

@@ -25,7 +25,8 @@ public final class B2Deflate {
 	public static final StructLayout DEFLATE_OPTS = MemoryLayout.structLayout(
 		JAVA_INT.withName("chunk_bytes"), JAVA_INT.withName("block_bytes"), JAVA_INT.withName("mode"),
 		JAVA_INT.withName("search"), JAVA_INT.withName("chain_depth"), JAVA_INT.withName("lazy"),
-		JAVA_INT.withName("is_last"), JAVA_INT.withName("framing"), JAVA_INT.withName("checksum"));
+		JAVA_INT.withName("is_last"), JAVA_INT.withName("framing"), JAVA_INT.withName("checksum"),
+		JAVA_INT.withName("split_min_bytes"));
 
 	public static final int INFLATE_CRC32 = 1, INFLATE_CHUNK_INDEXED = 2;
 	public static final int ERR_OUTPUT_OVERFLOW = -1;

@@ -163,6 +163,12 @@ typedef struct b2d_deflate_opts {
 	int32_t is_last;        /* 1: the stream ends after this call (final block emitted) */
 	int32_t framing;        /* B2D_FRAMING_* */
 	int32_t checksum;       /* B2D_CHECKSUM_*: which checksum of the input crc32_inout / d_chunk_crc32 carry */
+	uint32_t split_min_bytes; /* 0 = one block per block_bytes.  Otherwise adaptive block splitting, the counterpart of
+	                           comp/BinarySplit.java:30-98: the input is parsed in pieces of this many bytes (a power of
+	                           two >= 4096 dividing block_bytes, at most 16 pieces per block_bytes) and every
+	                           block_bytes span becomes the cheapest partition of its binary tree of pieces -- a piece,
+	                           a pair, ... or the whole span as one block -- priced with the real codes of every node.
+	                           The block index then has one entry per block_bytes span (its first block). */
 } b2d_deflate_opts;
 
 /* Worst-case output size of b2d_deflate_chunks for in_len bytes (any mode, any framing). */

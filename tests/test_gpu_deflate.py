@@ -210,3 +210,58 @@ def test_block_indexed_failures_fall_back_to_the_sequential_outcome(b2d, oracle)
         assert int(st[1]) != 0
         if ost > 0:
             assert int(st[1]) == ost
+
+
+# ---- adaptive block splitting (the GPU counterpart of comp/BinarySplit.java) ----
+def _mixed_local(rng, n):
+    parts, total = [], 0
+    while total < n:
+        k = rng.choice((3000, 9000, 20000, 50000, 90000))
+        kind = rng.randrange(4)
+        p = _text(rng, k) if kind == 0 else rng.randbytes(k) if kind == 1 else bytes(k) if kind == 2 else bytes(range(256)) * (k // 256)
+        parts.append(p)
+        total += len(p)
+    return b"".join(parts)[:n]
+
+
+@pytest.mark.parametrize("leaf", [4096, 8192, 16384, 32768])
+@pytest.mark.parametrize("mode", [0, 3])
+def test_adaptive_split_roundtrip_and_gain(b2d, oracle, leaf, mode):
+    """Every block_bytes span becomes the cheapest partition of its tree of pieces: the stream still decodes through the
+    reference decoder and zlib, the block index still works (one entry per span), and on data whose statistics change
+    inside 64 KiB it is smaller than one block per span."""
+    rng = random.Random(leaf + mode)
+    data = _mixed_local(rng, 3 * (1 << 20) + 70001)                          # ragged tail: partial span, partial piece
+    plain = b2d.deflate_chunks(data, b2d.make_opts(mode=mode))
+    opts = b2d.make_opts(mode=mode, split_min_bytes=leaf)
+    comp, sizes, bits = _indexed_roundtrip(b2d, data, opts)
+    assert _decode_both(oracle, comp, len(data)) == data
+    assert len(comp) < len(plain) * 0.995, (len(comp), len(plain))
+    # homogeneous text: nothing to gain, and nothing to lose beyond the matches cut at piece boundaries
+    text = _text(rng, (1 << 20) + 5)
+    a = b2d.deflate_chunks(text, b2d.make_opts(mode=mode))
+    b = b2d.deflate_chunks(text, opts)
+    assert _decode_both(oracle, b, len(text)) == text
+    assert len(b) <= len(a) * 1.004, (len(b), len(a))
+
+
+def test_adaptive_split_small_and_framings(b2d, oracle):
+    rng = random.Random(5)
+    for n in (0, 1, 4095, 4096, 4097, 16384, 65536, 65537, 100000, 200000):
+        data = _mixed_local(rng, n)
+        for framing in (0, 1):
+            opts = b2d.make_opts(split_min_bytes=4096, framing=framing, chunk_bytes=1 << 17)
+            comp = b2d.deflate_chunks(data, opts)
+            assert _decode_both(oracle, comp, n) == data, (n, framing)
+    # forced modes, greedy reference searches, small chunks
+    data = _mixed_local(rng, 300000)
+    for mode in (1, 2, 3):
+        for search in (0, 2, 3):
+            opts = b2d.make_opts(mode=mode, search=search, split_min_bytes=8192, chunk_bytes=1 << 17)
+            assert _decode_both(oracle, b2d.deflate_chunks(data, opts), len(data)) == data, (mode, search)
+    # invalid piece sizes are refused
+    for bad in (1000, 4097, 12288, 2048):
+        with pytest.raises(Exception):
+            b2d.deflate_chunks(data, b2d.make_opts(split_min_bytes=bad))
+    with pytest.raises(Exception):
+        b2d.deflate_chunks(data, b2d.make_opts(split_min_bytes=4096, block_bytes=1 << 17))   # 32 pieces per span
