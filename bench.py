@@ -510,6 +510,34 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
     total_in = sum_over_ranks(float(n_bytes))
     value = total_in / step_s / 1e9
 
+    # the same input with adaptive block splitting (pieces of 16 KiB, the GPU counterpart of BinarySplit)
+    opts_split = b2d.make_opts(chunk_bytes=CHUNK_BYTES, block_bytes=65536, mode=b2d.MODE_AUTO, is_last=int(rank == world - 1),
+                               split_min_bytes=16384)
+    d_total_s = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def deflate_split_dev():
+        r = L.b2d_deflate_chunks_dev(d_in.data_ptr(), n_bytes, ctypes.byref(opts_split), d_out.data_ptr(), bound,
+                                     d_total_s.data_ptr(), d_clen.data_ptr(), d_ccrc.data_ptr(), sp)
+        if r != 0:
+            raise RuntimeError(f"b2d_deflate_chunks_dev (split): {b2d.status_name(r)}")
+    split_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        deflate_split_dev()
+    split_s = timed(deflate_split_dev, split_steps) / split_steps
+    split_len = int(d_total_s.item())
+    clen_s = d_clen.cpu().numpy()
+    h_split = d_out[:split_len].cpu().numpy()
+    o = 0
+    for c in range(n_chunks):                                # zlib-decode a sample of the split stream's chunks
+        if c % max(1, n_chunks // 16) == 0:
+            got = zlib.decompressobj(-15).decompress(h_split[o:o + int(clen_s[c])].tobytes())
+            assert got == data[c * CHUNK_BYTES:(c + 1) * CHUNK_BYTES].tobytes(), f"deflate (split): zlib decode of chunk {c} differs"
+        o += int(clen_s[c])
+    assert o == split_len
+    del h_split
+    deflate_dev()                                            # d_out / d_clen hold the unsplit stream again for what follows
+    torch.cuda.synchronize()
+
     # multi-GPU: the one exchange step of the path -- chunk sizes all-gathered, payloads sent to GPU 0 (NCCL over NVLink)
     gather_ms = None
     if world > 1:
@@ -562,7 +590,8 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         # chains, match, parse, huffman, layout, scan, emit, block_bits, crc32 (+ one cudaMemsetAsync, not ours) per call
         "gpu_launches_per_step": 9,
         # deflate steps (+ block_bits_kernel), chunk-indexed decode (inflate + crc32), block-indexed decode (units + resolve + crc32), e2e
-        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 512)) * e2e_steps,
+        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 512)) * e2e_steps
+                        + 10 * (split_steps + 2) + 9,
         "roofline": {"bound": "hbm", "achieved": round((n_bytes + comp_len) / step_s / 1e9, 2), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round((n_bytes + comp_len) / step_s / 1e9 / hbm_peak, 5),
                      "note": "whole pipeline (8 kernels + memset); algorithmic bytes = input read + compressed written"},
@@ -573,6 +602,11 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         "inflate_block_indexed": {"value": round(sum_over_ranks(float(n_bytes)) / unblock_s / 1e9, 3), "unit": "GB/s",
                                   "ms_per_step": round(unblock_s * 1e3, 3),
                                   "note": "b2d_inflate_chunks_dev: one warp per 64 KiB block (Huffman decode), then one warp per chunk replays the back-references"},
+        "adaptive_split": {"value": round(sum_over_ranks(float(n_bytes)) / split_s / 1e9, 3), "unit": "GB/s",
+                           "ms_per_step": round(split_s * 1e3, 3), "compressed_bytes_per_gpu": split_len,
+                           "ratio": round(n_bytes / split_len, 4), "bytes_vs_unsplit": round(split_len / comp_len, 5),
+                           "note": "split_min_bytes = 16 KiB: every 64 KiB span becomes the cheapest partition of its tree of "
+                                   "pieces (SURVEY 8f N3, comp/BinarySplit.java); 10 launches per call"},
     }
 
     def cpu(O, cores):

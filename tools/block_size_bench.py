@@ -20,8 +20,8 @@ for kind in ('mixed', 'text'):
     d_total = torch.zeros(1, dtype=torch.int64, device=dev)
     nc = n // CH
     d_clen = torch.zeros(nc, dtype=torch.int64, device=dev); d_crc = torch.zeros(nc, dtype=torch.int32, device=dev)
-    for bb in (65536, 32768, 16384, 8192):
-        opts = b2d.make_opts(chunk_bytes=CH, block_bytes=bb)
+    for bb, leaf in ((65536, 0), (32768, 0), (16384, 0), (8192, 0), (65536, 32768), (65536, 16384), (65536, 8192), (65536, 4096)):
+        opts = b2d.make_opts(chunk_bytes=CH, block_bytes=bb, split_min_bytes=leaf)
         d_bits = torch.zeros(n // bb, dtype=torch.int32, device=dev)
         def deflate():
             r = L.b2d_deflate_chunks_indexed_dev(d_in.data_ptr(), n, ctypes.byref(opts), d_out.data_ptr(), bound, d_total.data_ptr(), d_clen.data_ptr(), d_crc.data_ptr(), d_bits.data_ptr(), sp)
@@ -42,4 +42,4 @@ for kind in ('mixed', 'text'):
         assert int(cst.abs().sum()) == 0 and torch.equal(d_dec, d_in) and torch.equal(c2, d_crc)
         e0.record(); [inflate_blocks() for _ in range(3)]; e1.record(); torch.cuda.synchronize()
         tb = e0.elapsed_time(e1) / 3
-        print(f"{kind:6s} block {bb >> 10:3d} KiB: {comp:11d} bytes, ratio {n / comp:7.4f}  deflate {td:7.2f} ms = {n / td / 1e6:6.2f} GB/s   block-parallel inflate {tb:7.2f} ms = {n / tb / 1e6:6.2f} GB/s", flush=True)
+        print(f"{kind:6s} block {bb >> 10:3d} KiB{f' split to {leaf >> 10:2d} KiB' if leaf else '                ':s}: {comp:11d} bytes, ratio {n / comp:7.4f}  deflate {td:7.2f} ms = {n / td / 1e6:6.2f} GB/s   block-parallel inflate {tb:7.2f} ms = {n / tb / 1e6:6.2f} GB/s", flush=True)
