@@ -30,6 +30,8 @@ static std::optional<std::string> submain(int argc, char **argv) {
 	                  std::nullopt, baseName(inPath), std::nullopt, true);
 	const char *ix = getenv("B2D_GZIP_INDEX");
 	const bool withIndex = !(ix && ix[0] == '0');
+	DeflaterOptions dopt;                                  // B2D_GZIP_SPLIT=<bytes>: BinarySplit-style adaptive blocks
+	if (const char *sp = getenv("B2D_GZIP_SPLIT")) dopt.split_min_bytes = (uint32_t)strtoul(sp, nullptr, 10);
 
 	auto t0 = std::chrono::steady_clock::now();
 	uint64_t outBytes = 0;
@@ -38,12 +40,12 @@ static std::optional<std::string> submain(int argc, char **argv) {
 		FileOutputStream fout(outPath);
 		std::vector<uint8_t> buf(8 << 20);
 		if (!withIndex) {
-			GzipOutputStream out(fout, meta);
+			GzipOutputStream out(fout, meta, dopt);
 			for (long r; (r = in.read(buf.data(), 0, buf.size())) > 0;) out.write(buf.data(), 0, (size_t)r);   // in.transferTo(out)
 			out.close();
 		} else {
 			ByteArrayOutputStream body;
-			DeflaterOutputStream def(body);
+			DeflaterOutputStream def(body, dopt);
 			for (long r; (r = in.read(buf.data(), 0, buf.size())) > 0;) def.write(buf.data(), 0, (size_t)r);
 			def.finish();
 			meta.extraField = GzipMetadata::encodeChunkIndex(def.chunkIndex());      // absent if it does not fit 64 KiB

@@ -23,12 +23,16 @@ def run(*args, env=None):
 
 
 @pytest.mark.parametrize("kind,n", [("text", 0), ("text", 1), ("text", 70000), ("mixed", (5 << 20) + 12345), ("random", 3 << 20)])
-@pytest.mark.parametrize("index", ["1", "0"])
+@pytest.mark.parametrize("index", ["1", "0", "split"])
 def test_cli_roundtrip_and_interop(b2d, oracle, tmp_path, kind, n, index):
     data = b2d.corpus(kind, 0xDEF1A7E, n).tobytes()
     src, gz, back = tmp_path / "in.bin", tmp_path / "out.gz", tmp_path / "back.bin"
     src.write_bytes(data)
-    r = run(GZIP, str(src), str(gz), env={"B2D_GZIP_INDEX": index})
+    env = {"B2D_GZIP_INDEX": index}
+    if index == "split":                                         # adaptive block splitting, with the index
+        env = {"B2D_GZIP_INDEX": "1", "B2D_GZIP_SPLIT": "8192"}
+        index = "1"
+    r = run(GZIP, str(src), str(gz), env=env)
     assert r.returncode == 0, r.stderr
     assert "Input  speed:" in r.stderr and "Output speed:" in r.stderr              # gzip.java:73-74
     member = gz.read_bytes()
