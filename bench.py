@@ -590,7 +590,7 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         # chains, match, parse, huffman, layout, scan, emit, block_bits, crc32 (+ one cudaMemsetAsync, not ours) per call
         "gpu_launches_per_step": 9,
         # deflate steps (+ block_bits_kernel), chunk-indexed decode (inflate + crc32), block-indexed decode (units + resolve + crc32), e2e
-        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 512)) * e2e_steps
+        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 256)) * e2e_steps
                         + 10 * (split_steps + 2) + 9,
         "roofline": {"bound": "hbm", "achieved": round((n_bytes + comp_len) / step_s / 1e9, 2), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round((n_bytes + comp_len) / step_s / 1e9 / hbm_peak, 5),

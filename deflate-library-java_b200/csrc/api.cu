@@ -32,7 +32,7 @@ struct Ctx {
 	int sm_count = 0;
 	cudaStream_t st[16] = {};                                    // pipeline streams (one per slice)
 	cudaEvent_t ev[24] = {};
-	DevBuf in, out, meta, scratch, crc, scratch2, bits;
+	DevBuf in, out, meta, scratch, crc, scratch2, bits, scratch3;
 	void *pinned_meta = nullptr;
 	size_t pinned_meta_cap = 0;
 	char last_error[256] = "";
@@ -79,7 +79,7 @@ int ensure_pinned_meta(size_t bytes) {
 }
 
 void release_all() {
-	for (DevBuf *b : {&g.in, &g.out, &g.meta, &g.scratch, &g.crc, &g.scratch2, &g.bits}) {
+	for (DevBuf *b : {&g.in, &g.out, &g.meta, &g.scratch, &g.crc, &g.scratch2, &g.bits, &g.scratch3}) {
 		if (b->p) cudaFree(b->p);
 		b->p = nullptr;
 		b->cap = 0;
@@ -147,11 +147,12 @@ int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n
 
 int deflate_dev_locked(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out, uint64_t out_cap,
                        uint64_t *d_total, uint64_t *d_chunk_len, uint32_t *d_chunk_crc, cudaStream_t st,
-                       uint32_t *d_block_bits = nullptr) {
+                       uint32_t *d_block_bits = nullptr, DevBuf *scratch = nullptr) {
+	if (!scratch) scratch = &g.scratch;
 	size_t sb = deflate_scratch_bytes(in_len, p);
-	int r = ensure(g.scratch, sb);
+	int r = ensure(*scratch, sb);
 	if (r) return r;
-	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, g.scratch.p, g.scratch.cap, st, d_block_bits));
+	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, scratch->p, scratch->cap, st, d_block_bits));
 	if (d_chunk_crc) {
 		uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
 		if (p.checksum == B2D_CHECKSUM_ADLER32) CK(launch_adler32_pieces(d_in, in_len, p.chunk_bytes, n_chunks, d_chunk_crc, st));
@@ -417,11 +418,20 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 	if ((r = ensure_pinned_meta(m_total))) return r;
 	uint8_t *dm = (uint8_t *)g.meta.p, *hm = (uint8_t *)g.pinned_meta;
 	cudaStream_t st = g.st[0];
-	if (p.framing == B2D_FRAMING_CHUNKED && n_chunks >= 512) {
-		// Pipelined: the chunks are cut into up to 4 slices of >= 512 chunks (smaller launches lose more to tail effects than the overlap wins); slice k+1's H2D (stream A) runs under slice k's kernels
-		// (stream B) and slice k-1's D2H (stream C).  The slices are ordinary calls (is_last only on the final one), so
-		// the bytes are the same as one big call.
-		const uint32_t per = std::max<uint32_t>(512, (n_chunks + 3) / 4);
+	if (p.framing == B2D_FRAMING_CHUNKED && n_chunks >= 256) {
+		// Pipelined: the chunks are cut into up to 4 slices of >= 256 chunks.  Slice k+1's H2D (stream A) runs under
+		// slice k's kernels and slice k-1's D2H (stream C); the slices' kernels alternate between two streams with a
+		// scratch area each, so the latency-bound kernels of one slice (chains: one warp per 256 KiB segment, the
+		// same few milliseconds whatever the slice size) run under the issue-bound ones of its neighbour.  The slices
+		// are ordinary calls (is_last only on the final one), so the bytes are the same as one big call.
+		uint32_t max_slices = 4, min_per = 256;          // measured at 1 GiB: 2 slices 50.4 ms, 4: 48.1, 8: 56.2, 1: 62.5
+		if (const char *sl_ = getenv("B2D_DEFLATE_SLICES")) {      // diagnostic: "slices[,chunks per slice at least]"
+			unsigned a_ = 0, b_ = 0;
+			int got = sscanf(sl_, "%u,%u", &a_, &b_);
+			if (got >= 1 && a_ >= 1 && a_ <= 8) max_slices = a_;
+			if (got >= 2 && b_ >= 1) min_per = b_;
+		}
+		const uint32_t per = std::max<uint32_t>(min_per, (n_chunks + max_slices - 1) / max_slices);
 		const uint32_t n_slices = (n_chunks + per - 1) / per;
 		const uint64_t slice_in = (uint64_t)per * p.chunk_bytes;
 		const uint64_t slice_bound = (deflate_bound_bytes(slice_in, p.chunk_bytes, p.block_bytes) + 255) & ~(uint64_t)255;
@@ -431,8 +441,11 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 		if ((r = ensure_pinned_meta(ms_total * n_slices))) return r;
 		DeflateParams ps = p;
 		if ((r = ensure(g.scratch, deflate_scratch_bytes(slice_in, ps)))) return r;
+		if (n_slices > 1 && (r = ensure(g.scratch3, deflate_scratch_bytes(slice_in, ps)))) return r;
 		dm = (uint8_t *)g.meta.p; hm = (uint8_t *)g.pinned_meta;
-		cudaStream_t sA = g.st[1], sB = g.st[0], sC = g.st[2];
+		cudaStream_t sA = g.st[1], sC = g.st[2];
+		cudaStream_t sK[2] = {g.st[0], g.st[3]};
+		DevBuf *scr[2] = {&g.scratch, &g.scratch3};
 		for (uint32_t k = 0; k < n_slices; k++) {
 			const uint64_t a = (uint64_t)k * slice_in, len = std::min<uint64_t>(slice_in, in_len - a);
 			CK(cudaMemcpyAsync((uint8_t *)g.in.p + a, in + a, len, cudaMemcpyHostToDevice, sA));
@@ -442,9 +455,11 @@ B2D_API int64_t b2d_deflate_chunks(const uint8_t *in, uint64_t in_len, const b2d
 			const uint64_t a = (uint64_t)k * slice_in, len = std::min<uint64_t>(slice_in, in_len - a);
 			ps.is_last = (p.is_last && k + 1 == n_slices) ? 1 : 0;
 			uint8_t *dmk = dm + ms_total * k;
+			cudaStream_t sB = sK[k & 1];
 			CK(cudaStreamWaitEvent(sB, g.ev[k], 0));
 			r = deflate_dev_locked((const uint8_t *)g.in.p + a, len, ps, (uint8_t *)g.out.p + slice_bound * k, slice_bound,
-			                       (uint64_t *)dmk, (uint64_t *)(dmk + ms_clen), crc32_inout ? (uint32_t *)(dmk + ms_ccrc) : nullptr, sB);
+			                       (uint64_t *)dmk, (uint64_t *)(dmk + ms_clen), crc32_inout ? (uint32_t *)(dmk + ms_ccrc) : nullptr, sB,
+			                       nullptr, scr[k & 1]);
 			if (r) return r;
 			CK(cudaMemcpyAsync(hm + ms_total * k, dmk, ms_total, cudaMemcpyDeviceToHost, sB));
 			CK(cudaEventRecord(g.ev[8 + k], sB));
