@@ -59,40 +59,53 @@ struct Canon {                            // canonical-code description for the 
 
 struct __align__(16) WarpSmem {
 	u8 tile[TILE];                        // output staging: tile[i] <-> global byte tile_g[i]
-	uint2 mq[32];                         // pending back-references: x = shared-window address of the tile byte
-	                                      // | length << 16, y = distance
-	Canon ll_canon, d_canon;
-	u16 ll_sorted[288];
-	u16 d_sorted[32];
-	u16 cl_lut[128];
+	union {                               // the code-length code's LUT is dead once the lengths are read, before
+		u16 cl_lut[128];                  // build_code() fills ll_sorted
+		u16 ll_sorted[288];
+	};
 	u8 lens[320];
 	// host mirror (see mirror_progress): the member's output base and how many of its bytes are mirrored already.
 	// Kept here, reachable from the tile pointer, rather than in the Member.
 	u8 *m_out;
 	u64 m_done;
 };
-// Shared memory of a CTA.  The LUTs are placed so that each lit/len LUT is 4 KiB-aligned and each distance LUT 1 KiB-
-// aligned IN THE SHARED WINDOW: an entry's address is then (index bits << 2) OR-ed into the table address, one LOP3.
-// On sm_100 the static shared segment of a CTA starts at window address 0x400 (the first KiB is the system's), so the
-// 3 KiB up to 0x1000 hold three of the four distance LUTs, the lit/len LUTs follow at 0x1000..0x4FFF, then the fourth
-// distance LUT and the small per-warp state.  Kernels check the segment address once and trap if it ever differs.
+struct __align__(16) SideSmem {           // slow-path description of the two codes
+	Canon ll_canon, d_canon;
+	u16 d_sorted[32];
+};
+// Shared memory of a CTA, by shared-WINDOW address (on sm_100 the static segment of a CTA starts at 0x400, the first
+// KiB being the system's; kernels check that once and trap if it ever differs):
+//   0x0400  4 x reference queue, 256 B each        -> "queue full" is `(next slot & 0xFF) == 0`
+//   0x0800  4 x distance LUT, 1 KiB each
+//   0x1800  4 x SideSmem
+//   0x2000  4 x lit/len LUT, 4 KiB each
+//   0x6000  4 x WarpSmem
+// Every LUT is naturally aligned in the window, so an entry's address is (index bits << 2) OR-ed into the table
+// address, one LOP3; and warp w's distance LUT sits at a quarter of its lit/len LUT's address, so the hot loop keeps
+// one table address in a register, not two.
 static_assert(WARPS_PER_CTA == 4 && LL_TB == 10 && D_TB == 8, "shared-memory layout below is written for these");
+static_assert(sizeof(SideSmem) * 4 <= 0x800, "SideSmem area");
 constexpr u32 SM_WINDOW_BASE = 0x400;
-constexpr int SM_LL_OFF = 0xC00;                         // window 0x1000
-constexpr int SM_D3_OFF = SM_LL_OFF + 4 * 4096;          // window 0x5000
-constexpr int SM_W_OFF = SM_D3_OFF + 1024;
+constexpr int SM_MQ_OFF = 0x400 - 0x400, SM_D_OFF = 0x800 - 0x400, SM_SIDE_OFF = 0x1800 - 0x400, SM_LL_OFF = 0x2000 - 0x400,
+              SM_W_OFF = 0x6000 - 0x400;
 constexpr int SM_BYTES = SM_W_OFF + WARPS_PER_CTA * (int)sizeof(WarpSmem);
+static_assert(7 * (SM_BYTES + 1024) <= 233472, "seven CTAs per SM");
 struct Sm {                               // one warp's view, in registers
 	WarpSmem *w;
 	u32 *ll;                              // 1 << LL_TB entries
 	u32 *dl;                              // 1 << D_TB entries
+	uint2 *mq;                            // pending back-references: x = shared-window address of the tile byte
+	                                      // | length << 16, y = distance
+	SideSmem *side;
 	__device__ __forceinline__ WarpSmem *operator->() const { return w; }
 };
 __device__ __forceinline__ Sm warp_smem(u8 *raw, u32 warp) {
 	if ((u32)__cvta_generic_to_shared(raw) != SM_WINDOW_BASE) __trap();
 	Sm s;
 	s.ll = (u32 *)(raw + SM_LL_OFF) + (warp << LL_TB);
-	s.dl = (u32 *)(raw + (warp < 3 ? warp * 1024 : SM_D3_OFF));
+	s.dl = (u32 *)(raw + SM_D_OFF) + (warp << D_TB);
+	s.mq = (uint2 *)(raw + SM_MQ_OFF) + warp * 32;
+	s.side = (SideSmem *)(raw + SM_SIDE_OFF) + warp;
 	s.w = (WarpSmem *)(raw + SM_W_OFF) + warp;
 	return s;
 }
@@ -304,6 +317,13 @@ __device__ __forceinline__ u32 lds_u32(u32 a) {
 	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a) : "memory");
 	return v;
 }
+// llb >> 2, kept out of the optimiser's sight so that it is recomputed (one shift) where it is used instead of being
+// carried, and spilled, as a second loop invariant
+__device__ __forceinline__ u32 quarter(u32 a) {
+	u32 r;
+	asm volatile("shr.u32 %0, %1, 2;" : "=r"(r) : "r"(a));
+	return r;
+}
 __device__ __forceinline__ void sts_u8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_v2(u32 a, u32 x, u32 y) {
 	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
@@ -391,7 +411,7 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 }
 
 __device__ __forceinline__ void resolve(Member &m, const Sm &sm, u32 lane) {
-	resolve_pending(sm->tile, sm->mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
+	resolve_pending(sm->tile, sm.mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
 	m.nm = 0;
 }
 
@@ -475,15 +495,14 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 	// The output position is kept as the shared-window ADDRESS of the next tile byte (tp = tile_s + tpos), so a
 	// literal store needs no address arithmetic; limits and the queued references are in the same terms.
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile);
-	const u32 mq_s = (u32)__cvta_generic_to_shared(sm->mq);
-	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);       // 4 KiB-aligned
-	const u32 dlb = (u32)__cvta_generic_to_shared(sm.dl);       // 1 KiB-aligned
+	const u32 mq_s = (u32)__cvta_generic_to_shared(sm.mq);
+	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);       // 4 KiB-aligned; the distance LUT sits at llb >> 2
 	u32 tp = tile_s + m.tpos;
 	u32 tend = tile_s + m.tlimit;                    // end of the usable tile
 	int tguard = (int)tend - (int)LIT_GUARD;         // tp <= tguard at every word boundary (see NEXT_SYMBOL)
 	int pos_off = m.pos_base - (int)tile_s;          // output position of the byte at tp = pos_off + tp
-	u32 qp = mq_s + m.nm * 8;                        // next free slot of the reference queue
-	const u32 qend = mq_s + 32 * 8;
+	u32 qp = mq_s + m.nm * 8;                        // next free slot of the reference queue (256 B, 256-aligned:
+	                                                 // full when the next slot's address wraps to 0 mod 256)
 	const u32 fast_last = b.n_full - 3;
 	const u32 *const words = b.words;
 	u64 *gp = DEFER ? m.glist + m.gcount : nullptr;  // DEFER: next free record, end of the list, unit offset of tile[0]
@@ -496,7 +515,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
                          if (DEFER) ubase = (u32)(m.tile_g - m.out) - tile_s; } while (0)
 	// LUT entry addresses: (bits << 2) masked and OR-ed into the aligned table address
 #define LL_AT(bits) lds_u32(llb | (((bits) << 2) & ((4u << LL_TB) - 4)))
-#define DL_AT(bits) lds_u32(dlb | (((bits) << 2) & ((4u << D_TB) - 4)))
+#define DL_AT(bits) lds_u32(quarter(llb) | (((bits) << 2) & ((4u << D_TB) - 4)))
 	// Window refill at a symbol boundary.  The three buffered words must stay real input, so the word about to be
 	// loaded (widx + 3) has to be a full one; otherwise the hot loop is left with the window untouched (the checked
 	// path advances by itself).  A length/distance pair can cross two words: then the loop runs twice.  Literals are
@@ -547,7 +566,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			} else {
 				sts_v2(qp, qx, dist);                        // same value from every lane: one broadcast write
 				qp += 8;
-				if (qp == qend) { ev = EV_QFULL; break; }
+				if ((qp & 0xFF) == 0) { ev = EV_QFULL; break; }
 			}
 			NEXT_SYMBOL();
 		}
@@ -556,7 +575,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			if (e & K_LENX) { e = lenx_resolve(e, lo); continue; }
 			u32 v = e & 0xFFFF;
 			if (v == V_LONG) {
-				e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted);
+				e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
 				if (!(e & K_OTHER)) continue;
 				v = e & 0xFFFF;
 			}
@@ -568,7 +587,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 		if (ev == EV_DSPECIAL) {
 			u32 v = d >> 16;
 			if (v == 0) {
-				d = slow_decode<D_TB, true>(lo2, &sm->d_canon, sm->d_sorted);
+				d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted);
 				v = (d & KD_SPECIAL) ? d >> 16 : 0;
 			}
 			if (v) {
@@ -603,7 +622,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 					tp += take;
 					len -= take;
 				}
-				if (len == 0 && qp != qend) break;
+				if (len == 0 && (DEFER || (qp & 0xFF) != 0)) break;
 				SAVE_STATE();
 				if (len == 0) { resolve(m, sm, lane); qp = mq_s; break; }
 				flush_tile(m, sm, lane);
@@ -707,7 +726,7 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 		if (!(e & K_LEN)) {                                  // rare kinds
 			if (e & K_LENX) { e = lenx_resolve(e, lo); goto dispatch; }
 			const u32 v = e & 0xFFFF;
-			if (v == V_LONG) { e = slow_decode<LL_TB, false>(lo, &sm->ll_canon, sm->ll_sorted); goto dispatch; }
+			if (v == V_LONG) { e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted); goto dispatch; }
 			if (CAREFUL && (int)(e >> 27) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			if (v == V_EOB) { sh += e >> 27; ret = R_EOB; break; }
 			ret = B2D_RESERVED_LENGTH_SYMBOL;
@@ -727,7 +746,7 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 		if (d & KD_SPECIAL) {
 			const u32 v = d >> 16;
 			if (v == V_NODIST) { ret = B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE; break; }
-			if (v == 0) { d = slow_decode<D_TB, true>(lo2, &sm->d_canon, sm->d_sorted); goto dispatch_d; }
+			if (v == 0) { d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted); goto dispatch_d; }
 			if (CAREFUL && (int)((d >> 8) & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			ret = B2D_RESERVED_DISTANCE_SYMBOL;
 			break;
@@ -747,7 +766,7 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 				tpos += len;
 				continue;
 			}
-			sm->mq[nm] = make_uint2(tile_s + tpos + (len << 16), dist);   // same value from every lane: one broadcast write
+			sm.mq[nm] = make_uint2(tile_s + tpos + (len << 16), dist);   // same value from every lane: one broadcast write
 			tpos += len;
 			if (++nm == 32) {
 				SAVE_STATE();
@@ -769,7 +788,7 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 					const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
 					m.glist[m.gcount++] = upos | (u64)take << 24 | (u64)dist << 40;
 				} else {
-					if (lane == 0) sm->mq[nm] = make_uint2((tile_s + tpos) | take << 16, dist);
+					if (lane == 0) sm.mq[nm] = make_uint2((tile_s + tpos) | take << 16, dist);
 					nm++;
 				}
 				tpos += take;
@@ -923,7 +942,7 @@ __device__ int dynamic_header(Member &m, const Sm &sm, int &avail, u32 lane) {
 	}
 	__syncwarp();
 	if (sm->lens[256] == 0) return B2D_END_OF_BLOCK_CODE_ZERO_LENGTH;               // :383-384
-	int e = build_code<LL_TB, false>(sm->lens, num_ll, sm.ll, sm->ll_sorted, &sm->ll_canon, lane);   // :385
+	int e = build_code<LL_TB, false>(sm->lens, num_ll, sm.ll, sm->ll_sorted, &sm.side->ll_canon, lane);   // :385
 	if (e) return e;
 	// distance code special cases (:396-428)
 	u8 *dl = sm->lens + num_ll;
@@ -942,7 +961,7 @@ __device__ int dynamic_header(Member &m, const Sm &sm, int &avail, u32 lane) {
 			num_d = 32;
 			__syncwarp();
 		}
-		e = build_code<D_TB, true>(dl, num_d, sm.dl, sm->d_sorted, &sm->d_canon, lane);   // :426
+		e = build_code<D_TB, true>(dl, num_d, sm.dl, sm.side->d_sorted, &sm.side->d_canon, lane);   // :426
 		if (e) return e;
 	}
 	m.tables = 0;
@@ -954,8 +973,8 @@ __device__ void fixed_tables(Member &m, const Sm &sm, u32 lane) {
 	for (int i = lane; i < 288; i += 32) sm->lens[i] = i < 144 ? 8 : i < 256 ? 9 : i < 280 ? 7 : 8;
 	sm->lens[288 + lane] = 5;
 	__syncwarp();
-	build_code<LL_TB, false>(sm->lens, 288, sm.ll, sm->ll_sorted, &sm->ll_canon, lane);
-	build_code<D_TB, true>(sm->lens + 288, 32, sm.dl, sm->d_sorted, &sm->d_canon, lane);
+	build_code<LL_TB, false>(sm->lens, 288, sm.ll, sm->ll_sorted, &sm.side->ll_canon, lane);
+	build_code<D_TB, true>(sm->lens + 288, 32, sm.dl, sm.side->d_sorted, &sm.side->d_canon, lane);
 	m.tables = 1;
 }
 
