@@ -383,7 +383,13 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 		const int j = __ffs(mask) - 1;
 		const int o = __shfl_sync(FULL_MASK, off, j), l = __shfl_sync(FULL_MASK, len, j), si = __shfl_sync(FULL_MASK, s, j);
 		const u8 *gs = tile_g + si;
-		for (int k = lane; k < l; k += 32) sts_u8(t_s + o + k, ldg_u8(gs + k));
+		for (int k = lane; k < l; k += 160) {            // up to five loads in flight per lane, then the stores
+			u32 v[5];
+#pragma unroll
+			for (int j = 0; j < 5; j++) v[j] = k + 32 * j < l ? ldg_u8(gs + k + 32 * j) : 0u;
+#pragma unroll
+			for (int j = 0; j < 5; j++) if (k + 32 * j < l) sts_u8(t_s + o + k + 32 * j, v[j]);
+		}
 	}
 	__syncwarp();
 	// (3) near: source overlaps the tile; strictly in stream order, from shared memory

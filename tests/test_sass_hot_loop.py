@@ -1,0 +1,45 @@
+"""CPU: the member decoder's symbol loop must not touch local memory.  ptxas allocates registers across the
+__noinline__ calls around the loop, and during development unrelated edits to those functions repeatedly spilled loop
+invariants (LUT addresses, the window limit) INTO the loop: the same source then ran between 15.6 and 24.8 ms per GiB
+(DESIGN.md 3.1).  This test disassembles the built object and looks at the loop itself."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OBJ = os.path.join(ROOT, "deflate-library-java_b200", "build", "inflate.cu.o")
+
+
+def _sass(kernel):
+    out = subprocess.run(["cuobjdump", "-sass", OBJ], capture_output=True, text=True, check=True).stdout
+    lines, on = [], False
+    for ln in out.splitlines():
+        if "Function :" in ln:
+            on = kernel in ln
+        elif on:
+            m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/\s+(.*?)\s*/\*", ln)
+            if m:
+                lines.append(m.group(2).rstrip(" ;"))
+    return lines
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(OBJ), reason="needs the built object and cuobjdump")
+def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic():
+    sass = _sass("14inflate_kernel")
+    # the literal path: `sh += e >> 27` is the only LEA.HI with a 5-bit shift; the loop body follows it
+    hits = [i for i, ins in enumerate(sass) if re.match(r"LEA\.HI R\d+, R\d+, R\d+, RZ, 0x5$", ins)]
+    assert hits, "symbol loop not found"
+    start = hits[0] - 4
+    # the loop ends where its exits store the state (the first STL after the queue store of a reference)
+    sts64 = next(i for i in range(start, len(sass)) if sass[i].startswith("STS.64"))
+    end = next(i for i in range(sts64, len(sass)) if sass[i].startswith("STL"))
+    body = sass[start:end]
+    assert 60 < len(body) < 200, len(body)
+    # two table lookups and the literal store are there ...
+    assert sum(ins.startswith("LDS R") for ins in body) >= 2 and any(ins.startswith("STS.U8") for ins in body)
+    # ... and nothing goes through local memory, except in the window refill's leave-the-loop path
+    local = [ins for ins in body if "LDL" in ins or "STL" in ins]
+    assert len(local) <= 1, local
