@@ -247,6 +247,10 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	for (u32 round = 0; round < TILE / (MATCH_THREADS * RUN); round++) {
 	const u32 k0 = (round * MATCH_THREADS + threadIdx.x) * RUN;
 	if (k0 >= n_pos) break;
+	// positions relative to the chunk start fit 32 bits; the end of the current block is found once per run and moved
+	// on when a position reaches it (no 64-bit division per position)
+	const u32 rel0 = (u32)(ts + k0 - cs), ce_rel = (u32)(ce - cs);
+	u32 be_rel = (rel0 / block_bytes + 1) * block_bytes;
 	u32 res[RUN];
 	int prev_len = 0, prev_dist = 0;
 	int run_len = 0, since = 1 << 20;                 // length of / positions since the last searched long match
@@ -255,20 +259,20 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	for (u32 j = 0; j < RUN; j++) {
 		const u32 k = k0 + j;
 		if (k >= n_pos) { res[j] = 0; continue; }
-		const u64 p = ts + k;
+		const u32 rel = rel0 + j;                                  // p - cs
 		const u32 o = woff + k;
 		const u32 cur = sm_load4(W, o);
-		const u64 blk_end = min(ce, (p / block_bytes + 1) * block_bytes);
-		const int maxlen = (int)min((u64)MAX_MATCH, blk_end - p);   // runs stop at the block end (Lz77Huffman.java:75)
+		if (rel >= be_rel) be_rel += block_bytes;
+		const int maxlen = (int)min((u32)MAX_MATCH, min(ce_rel, be_rel) - rel);   // runs stop at the block end (Lz77Huffman.java:75)
 		int best_len = 0, best_dist = 0;
 		if (mp.search == B2D_SEARCH_RLE) {
-			if (p > cs && maxlen >= 3) {                           // distance 1 only (RLE_*, Lz77Huffman.java:301-302)
+			if (rel > 0 && maxlen >= 3) {                          // distance 1 only (RLE_*, Lz77Huffman.java:301-302)
 				int len = sm_match_len(W, o - 1, o, maxlen);
 				if (len >= 3) { best_len = len; best_dist = 1; }
 			}
-		} else if (mp.search != B2D_SEARCH_LITERAL && maxlen >= mp.hb && p + mp.hb <= ce) {
+		} else if (mp.search != B2D_SEARCH_LITERAL && maxlen >= mp.hb && rel + mp.hb <= ce_rel) {
 			const u32 cmask = mp.hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
-			const u32 max_dist = (u32)min((u64)WINDOW, p - cs);
+			const u32 max_dist = min(WINDOW, rel);
 			int depth = mp.depth;
 			best_len = mp.hb - 1;
 			if (inherit && prev_len > mp.hb) {                     // same source, shifted by one
