@@ -587,14 +587,15 @@ def deflate_leg(args, b2d, L, torch, dist, dev, rank, world, pool, timed, barrie
         "compressed_bytes_per_gpu": comp_len, "ratio": round(n_bytes / comp_len, 4),
         "e2e": {"value": round(total_in / e2e_s / 1e9, 3), "unit": "GB/s", "h2d_bytes_per_step": n_bytes,
                 "d2h_bytes_per_step": comp_len + n_chunks * 12 + 8, "ms_per_step": round(e2e_s * 1e3, 3)},
-        # chains, match, parse, huffman, layout, scan, emit, block_bits, crc32 (+ one cudaMemsetAsync, not ours) per call
-        "gpu_launches_per_step": 9,
+        # chains, match, parse, node_hist, huffman, split_decide, layout, scan, emit, block_bits, crc32 (+ one
+        # cudaMemsetAsync, not ours) per call
+        "gpu_launches_per_step": 11,
         # deflate steps (+ block_bits_kernel), chunk-indexed decode (inflate + crc32), block-indexed decode (units + resolve + crc32), e2e
-        "gpu_launches": 9 * args.steps + (2 + 3) * max(3, args.steps // 2) + 8 * max(1, min(4, n_chunks // 256)) * e2e_steps
-                        + 10 * (split_steps + 2) + 9,
+        "gpu_launches": 11 * args.steps + (2 + 3) * max(3, args.steps // 2) + 10 * max(1, min(4, n_chunks // 256)) * e2e_steps
+                        + 10 * (split_steps + 2) + 11,
         "roofline": {"bound": "hbm", "achieved": round((n_bytes + comp_len) / step_s / 1e9, 2), "peak": hbm_peak,
                      "unit": "GB/s", "frac": round((n_bytes + comp_len) / step_s / 1e9 / hbm_peak, 5),
-                     "note": "whole pipeline (8 kernels + memset); algorithmic bytes = input read + compressed written"},
+                     "note": "whole pipeline (10 kernels + memset); algorithmic bytes = input read + compressed written"},
         "gather_to_gpu0_ms": gather_ms,
         "inflate_chunk_indexed": {"value": round(sum_over_ranks(float(n_bytes)) / unchunk_s / 1e9, 3), "unit": "GB/s",
                                   "ms_per_step": round(unchunk_s * 1e3, 3),

@@ -67,6 +67,7 @@ struct BlockRec {
 struct Heap {
 	u32 K, H;               // leaves and nodes per span (H = 2K - 1)
 	u32 block_bytes, leaf_bytes;
+	u32 roots_only;         // pieces are only a parse unit: every span is emitted as ONE block (see heap_for)
 };
 __device__ __host__ __forceinline__ u32 heap_level(u32 h) { u32 l = 0; for (u32 v = h + 1; v > 1; v >>= 1) l++; return l; }
 // byte range of node h of span `root`
@@ -559,11 +560,12 @@ __device__ __forceinline__ void bw_put(BitW &b, u32 v, int n) {      // single w
 }
 
 __global__ void __launch_bounds__(HUFF_WARPS * 32)
-huffman_kernel(BlockRec *__restrict__ recs, u32 n_recs, u64 n, Heap hp) {
+huffman_kernel(BlockRec *__restrict__ recs, u32 n_items, u32 item_stride, u64 n, Heap hp) {
 	__shared__ HuffSmem hs[HUFF_WARPS];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const u32 g = blockIdx.x * HUFF_WARPS + warp;
-	if (g >= n_recs) return;
+	const u32 item = blockIdx.x * HUFF_WARPS + warp;
+	if (item >= n_items) return;
+	const u32 g = item * item_stride;                   // stride H: only the roots of the spans
 	HuffSmem *s = &hs[warp];
 	BlockRec *rec = &recs[g];
 	u64 bs, dl64;
@@ -742,7 +744,7 @@ split_decide_kernel(BlockRec *__restrict__ recs, u32 n_roots, u64 n, Heap hp, in
 	bool split = false;
 	for (u32 it = 0; it < 5; it++) {                                        // depth <= 4: values settle bottom-up
 		const u64 bl = __shfl_sync(FULL_MASK, best, (2 * lane + 1) & 31), br = __shfl_sync(FULL_MASK, best, (2 * lane + 2) & 31);
-		if (exists && !leaf) {
+		if (exists && !leaf && !hp.roots_only) {
 			split = bl + br < single;                                       // a cut has to pay (BinarySplit.java:64)
 			best = split ? bl + br : single;
 		}
@@ -1053,9 +1055,31 @@ uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t blo
 	uint64_t n_chunks = (in_len + chunk_bytes - 1) / chunk_bytes + 1;
 	return in_len + in_len / 8 + n_blocks * 384 + n_chunks * 16 + 1024;
 }
+// The parse unit.  With adaptive splitting it is the piece the caller asked for.  Without, the default search on
+// chunked framing still parses in pieces of 16 KiB and emits every block_bytes span as one block with the summed
+// histogram: parse_kernel is one warp per unit, and 64 KiB units are only 1.7 waves of warps per GiB (8.9 ms against
+// 6.4 ms for the same bytes in 16 KiB units); the price is a match cut every 16 KiB (< 0.05 % of the output).  The
+// reference framing and the reference's own searches keep the block as the unit: their bytes are compared with the
+// restated reference encoder's.
+static Heap heap_for(const DeflateParams &p, u64 n) {
+	Heap hp;
+	hp.block_bytes = p.block_bytes;
+	hp.leaf_bytes = p.block_bytes;
+	hp.roots_only = 0;
+	if (p.leaf_bytes && n) hp.leaf_bytes = p.leaf_bytes;
+	else if (n && p.framing == 0 && p.search == B2D_SEARCH_DEFAULT && p.mode != B2D_MODE_STORED && p.block_bytes >= 65536 &&
+	         p.block_bytes <= 262144 && (p.block_bytes & (p.block_bytes - 1)) == 0) {
+		hp.leaf_bytes = 16384;
+		hp.roots_only = 1;
+	}
+	hp.K = hp.block_bytes / hp.leaf_bytes;
+	hp.H = 2 * hp.K - 1;
+	return hp;
+}
+
 size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p) {
 	u64 n_blocks = (in_len + p.block_bytes - 1) / p.block_bytes;
-	if (p.leaf_bytes) n_blocks *= 2 * (p.block_bytes / p.leaf_bytes) - 1;     // the spans' binary trees
+	n_blocks *= heap_for(p, in_len ? in_len : 1).H;                             // the spans' binary trees
 	u64 n_chunks = (in_len + p.chunk_bytes - 1) / p.chunk_bytes;
 	size_t s = 0;
 	s += ((in_len * 2 + 255) & ~(u64)255) + 256;          // prevdist u16
@@ -1084,11 +1108,7 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	const int ref_framing = p.framing == 1;
 	const int is_last = p.is_last;
 	// parse unit: the block, or the piece of adaptive splitting (then a block_bytes span owns a heap of records)
-	Heap hp;
-	hp.block_bytes = p.block_bytes;
-	hp.leaf_bytes = (p.leaf_bytes && n) ? p.leaf_bytes : p.block_bytes;
-	hp.K = hp.block_bytes / hp.leaf_bytes;
-	hp.H = 2 * hp.K - 1;
+	const Heap hp = heap_for(p, n);
 	const u32 unit = hp.leaf_bytes;
 	u32 n_blocks = (u32)((n + unit - 1) / unit);                 // parse units
 	u32 n_roots = (u32)((n + p.block_bytes - 1) / p.block_bytes);
@@ -1132,7 +1152,8 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 		parse_kernel<<<(n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st>>>(
 			match, n, unit, n_blocks, p.lazy, tokens, recs, hp);
 		if (hp.K > 1) node_hist_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp);
-		huffman_kernel<<<(n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_recs, n, hp);
+		if (hp.roots_only) huffman_kernel<<<(n_roots + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_roots, hp.H, n, hp);
+		else huffman_kernel<<<(n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_recs, 1, n, hp);
 	}
 	if (hp.K > 1) split_decide_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp, p.mode);
 	layout_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(recs, n_blocks, n_chunks, n, p.chunk_bytes, unit,
