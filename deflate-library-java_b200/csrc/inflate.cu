@@ -1,17 +1,18 @@
 // inflate.cu -- batched DEFLATE decoder for sm_100a: one warp per independent member / chunk.
 //
 // Replaces the decode loops of the reference (paths relative to src/io/nayuki/deflate/):
-//   decomp/Open.java:83-110   block loop            -> inflate_member()
+//   decomp/Open.java:83-110   block loop            -> inflate_kernel()
 //   decomp/Open.java:137-170  bit reader            -> BitIn (three words in registers, funnel-shift peek)
 //   decomp/Open.java:227-306  stored block          -> stored_block()  (warp-wide coalesced copy)
 //   decomp/Open.java:336-431  dynamic header        -> dynamic_header()
 //   decomp/Open.java:705-789  code tree + 9-bit LUT -> build_code(): canonical codes built by the whole warp
 //                                                      into a 10-bit (lit/len) / 8-bit (distance) LUT in shared
 //                                                      memory, longer codes resolved canonically (no tree walk)
-//   decomp/Open.java:438-620  symbol loop + copy    -> decode_block(): every lane decodes the same symbol from
-//                                                      shared tables (no divergence, no broadcast needed); output is
-//                                                      staged in a shared-memory tile, back-references are queued
-//                                                      and resolved 32 at a time by resolve()
+//   decomp/Open.java:438-620  symbol loop + copy    -> decode_block_fast() / decode_block_careful(): every lane decodes
+//                                                      the same symbol from shared tables (no divergence, no
+//                                                      broadcast needed); output is staged in a shared-memory tile,
+//                                                      back-references are queued and resolved 32 at a time by
+//                                                      resolve_pending()
 // Results (bytes, out_len, consumed input, status) are identical to the reference's; the validation ORDER of
 // Open.java is kept (first failing check wins).  Not a translation: no dictionary ring (the output buffer plus
 // the staging tile are the window), no code tree, no per-block allocation.
@@ -26,7 +27,7 @@ constexpr int D_TB = 8;                   // distance LUT index bits
 constexpr int WARPS_PER_CTA = 4;
 constexpr int CTAS_PER_SM = 7;            // 28 resident warps per SM: 4096 members fit one wave on 148 SMs
 constexpr int TILE = 1024;                // bytes of output staged per warp in shared memory
-constexpr u32 LIT_GUARD = 80;             // see decode_block<false>
+constexpr u32 LIT_GUARD = 80;             // see decode_block_fast (NEXT_SYMBOL)
 
 // lit/len LUT entry:  [31:27] bits this entry consumes   [19:16] kind   [15:0] value
 //   K_LIT    value = the literal byte (a byte store takes it from the low bits as it is)
