@@ -20,6 +20,7 @@ public final class GpuDeflaterOutputStream extends OutputStream {
 
 	private OutputStream output;
 	private final int chunkBytes, blockBytes;
+	private int splitMinBytes = 0;
 	private final long batchBytes;
 	private final MemorySegment stage, comp;
 	private long fill, totalIn;
@@ -43,6 +44,14 @@ public final class GpuDeflaterOutputStream extends OutputStream {
 
 	public int crc32() { return crc32; }          // CRC-32 of everything compressed so far (GzipOutputStream.java:57,67)
 	public long totalIn() { return totalIn; }
+
+	/** Counterpart of wrapping the strategy in {@code new BinarySplit(strategy, n)}: adaptive blocks with pieces of n bytes
+	 *  (a power of two >= 4096 dividing the block size, at most 16 per block); 0 switches it off. */
+	public void setSplitMinBytes(int n) {
+		if (n != 0 && (n < 4096 || (n & (n - 1)) != 0 || blockBytes % n != 0 || blockBytes / n > 16))
+			throw new IllegalArgumentException("Invalid piece size");
+		splitMinBytes = n;
+	}
 
 	@Override public void write(int b) throws IOException {
 		write(new byte[]{(byte)b}, 0, 1);
@@ -86,6 +95,7 @@ public final class GpuDeflaterOutputStream extends OutputStream {
 			o.set(JAVA_INT, 24, last ? 1 : 0);
 			o.set(JAVA_INT, 28, 0);      // chunked framing
 			o.set(JAVA_INT, 32, 0);      // CRC-32 alongside
+			o.set(JAVA_INT, 36, splitMinBytes);   // 0, or BinarySplit-style adaptive blocks (comp/BinarySplit.java)
 			MemorySegment crc = a.allocate(JAVA_INT);
 			crc.set(JAVA_INT, 0, crc32);
 			long n = B2Deflate.deflateChunks(stage, fill, o, comp, comp.byteSize(), crc, MemorySegment.NULL);
