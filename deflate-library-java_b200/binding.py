@@ -273,8 +273,9 @@ def crc32_combine(a, b, len_b):
     return int(lib().b2d_crc32_combine(a, b, len_b))
 
 
-def gunzip_batch(members, out_caps=None):
-    """members: list of complete gzip members.  out_caps: capacities (default: each member's ISIZE).
+def gunzip_batch(members, out_caps=None, pinned_out=False):
+    """members: list of complete gzip members.  out_caps: capacities (default: each member's ISIZE).  pinned_out: decode
+    into page-locked memory (the kernel then delivers the bytes itself, no D2H copy).
     -> (outputs list[bytes], out_len, in_consumed, status)."""
     n = len(members)
     in_off = np.zeros(n + 1, dtype=np.uint64)
@@ -290,7 +291,8 @@ def gunzip_batch(members, out_caps=None):
     out_off = np.zeros(n + 1, dtype=np.uint64)
     for i in range(n):
         out_off[i + 1] = out_off[i] + np.uint64(out_caps[i])
-    out = np.zeros(max(int(out_off[n]), 1), dtype=np.uint8)
+    keep = PinnedBuffer(max(int(out_off[n]), 1)) if pinned_out else None
+    out = keep.array if pinned_out else np.zeros(max(int(out_off[n]), 1), dtype=np.uint8)
     out_len = np.zeros(max(n, 1), dtype=np.uint64)
     consumed = np.zeros(max(n, 1), dtype=np.uint64)
     status = np.zeros(max(n, 1), dtype=np.int32)

@@ -222,6 +222,10 @@ def test_gunzip_batch_matches_reference_gzip_reader(b2d, oracle):
             assert outs[i] == out and int(consumed[i]) == cons, i
     outs2, _, _, status2 = b2d.gunzip_batch(members[:18])     # capacities from ISIZE
     assert not status2.any() and outs2 == outs[:18]
+    # the same batch into page-locked memory (bytes delivered by the decoding warps): identical in every respect
+    outs3, out_len3, consumed3, status3 = b2d.gunzip_batch(members, caps, pinned_out=True)
+    assert outs3 == outs and np.array_equal(out_len3, out_len) and np.array_equal(consumed3, consumed)
+    assert np.array_equal(status3, status)
 
 
 def test_random_garbage_members(b2d, oracle):
