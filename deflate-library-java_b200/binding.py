@@ -34,6 +34,7 @@ EXPORTS = [
     "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
     "b2d_adler32", "b2d_adler32_combine", "b2d_crc32_update", "b2d_adler32_update",
     "b2d_deflate_chunks_indexed", "b2d_deflate_chunks_indexed_dev", "b2d_inflate_chunks", "b2d_inflate_chunks_dev",
+    "b2d_init_devices", "b2d_device_count", "b2d_kernel_launches",
 ]
 
 
@@ -75,6 +76,10 @@ def lib():
     L.b2d_init.restype = i32
     L.b2d_init.argtypes = [i32]
     L.b2d_shutdown.restype = None
+    L.b2d_init_devices.restype = i32
+    L.b2d_init_devices.argtypes = [vp, i32]
+    L.b2d_device_count.restype = i32
+    L.b2d_kernel_launches.restype = u64
     L.b2d_strerror.restype = ctypes.c_char_p
     L.b2d_strerror.argtypes = [i32]
     L.b2d_last_error.restype = ctypes.c_char_p
@@ -136,6 +141,20 @@ def _check(code, what):
 
 def init(device=0):
     _check(lib().b2d_init(device), "b2d_init")
+
+
+def init_devices(devices=None):
+    """Binds several GPUs (list of CUDA ordinals; None = all of the box); the host entry points then shard over them."""
+    if not devices:
+        _check(lib().b2d_init_devices(None, 0), "b2d_init_devices")
+    else:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        _check(lib().b2d_init_devices(arr, len(devices)), "b2d_init_devices")
+    return int(lib().b2d_device_count())
+
+
+def kernel_launches():
+    return int(lib().b2d_kernel_launches())
 
 
 def shutdown():

@@ -163,11 +163,12 @@ __global__ void crc32_fold_kernel(const u32 *__restrict__ piece_crc, u32 n_piece
 }
 
 static cudaError_t upload_tables() {
-	static bool uploaded = false;
-	if (uploaded) return cudaSuccess;
+	static bool uploaded[MAX_DEVICES] = {};             // __constant__ memory is per device
+	const int slot = current_device_slot();
+	if (uploaded[slot]) return cudaSuccess;
 	host_init_tables();
 	cudaError_t e = cudaMemcpyToSymbol(X2N, h_x2n, sizeof(h_x2n));
-	if (e == cudaSuccess) uploaded = true;
+	if (e == cudaSuccess) uploaded[slot] = true;
 	return e;
 }
 
@@ -176,7 +177,7 @@ cudaError_t launch_crc32_segments(const uint8_t *d_data, const uint64_t *d_off, 
 	if (n_seg == 0) return cudaSuccess;
 	cudaError_t e = upload_tables();
 	if (e != cudaSuccess) return e;
-	crc32_kernel<<<n_seg, CRC_THREADS, 0, st>>>(d_data, d_off, d_len, 0, 0, d_crc);
+	B2D_LAUNCH(crc32_kernel, n_seg, CRC_THREADS, 0, st)(d_data, d_off, d_len, 0, 0, d_crc);
 	return cudaGetLastError();
 }
 
@@ -185,7 +186,7 @@ cudaError_t launch_crc32_pieces(const uint8_t *d_data, uint64_t total, uint64_t 
 	if (n_pieces == 0) return cudaSuccess;
 	cudaError_t e = upload_tables();
 	if (e != cudaSuccess) return e;
-	crc32_kernel<<<n_pieces, CRC_THREADS, 0, st>>>(d_data, nullptr, nullptr, total, piece, d_crc);
+	B2D_LAUNCH(crc32_kernel, n_pieces, CRC_THREADS, 0, st)(d_data, nullptr, nullptr, total, piece, d_crc);
 	return cudaGetLastError();
 }
 
@@ -193,7 +194,7 @@ cudaError_t launch_crc32_fold(const uint32_t *d_piece_crc, uint32_t n_pieces, ui
                               uint32_t *d_crc_out, cudaStream_t st) {
 	cudaError_t e = upload_tables();
 	if (e != cudaSuccess) return e;
-	crc32_fold_kernel<<<1, 32, 0, st>>>(d_piece_crc, n_pieces, piece, total, d_crc_out);
+	B2D_LAUNCH(crc32_fold_kernel, 1, 32, 0, st)(d_piece_crc, n_pieces, piece, total, d_crc_out);
 	return cudaGetLastError();
 }
 
@@ -271,14 +272,14 @@ uint32_t host_adler32_combine(uint32_t ad1, uint32_t ad2, uint64_t len2) {    //
 cudaError_t launch_adler32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
                                     uint32_t n_seg, uint32_t *d_out, cudaStream_t st) {
 	if (n_seg == 0) return cudaSuccess;
-	adler32_kernel<<<n_seg, CRC_THREADS, 0, st>>>(d_data, d_off, d_len, 0, 0, d_out);
+	B2D_LAUNCH(adler32_kernel, n_seg, CRC_THREADS, 0, st)(d_data, d_off, d_len, 0, 0, d_out);
 	return cudaGetLastError();
 }
 
 cudaError_t launch_adler32_pieces(const uint8_t *d_data, uint64_t total, uint64_t piece, uint32_t n_pieces,
                                   uint32_t *d_out, cudaStream_t st) {
 	if (n_pieces == 0) return cudaSuccess;
-	adler32_kernel<<<n_pieces, CRC_THREADS, 0, st>>>(d_data, nullptr, nullptr, total, piece, d_out);
+	B2D_LAUNCH(adler32_kernel, n_pieces, CRC_THREADS, 0, st)(d_data, nullptr, nullptr, total, piece, d_out);
 	return cudaGetLastError();
 }
 

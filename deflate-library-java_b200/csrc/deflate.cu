@@ -1092,18 +1092,19 @@ size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p) {
 	return s + sizeof(BlockRec) + 2048;
 }
 
-static bool g_attr_set = false;
+static bool g_attr_set[MAX_DEVICES] = {};
 
 cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams &p, uint8_t *d_out,
                            uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
                            void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits) {
 	cudaError_t e;
-	if (!g_attr_set) {
+	const int slot = current_device_slot();
+	if (!g_attr_set[slot]) {
 		e = cudaFuncSetAttribute(chains_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 << HASH_BITS);
 		if (e != cudaSuccess) return e;
 		e = cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MATCH_SMEM);
 		if (e != cudaSuccess) return e;
-		g_attr_set = true;
+		g_attr_set[slot] = true;
 	}
 	const int ref_framing = p.framing == 1;
 	const int is_last = p.is_last;
@@ -1145,23 +1146,23 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	if (need_search) {
 		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3)) {
 			const u32 n_segs = n_chunks * ((p.chunk_bytes + CHAIN_SEG - 1) / CHAIN_SEG);
-			chains_kernel<<<n_segs, 32, 2 << HASH_BITS, st>>>(d_in, n, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist);
+			B2D_LAUNCH(chains_kernel, n_segs, 32, 2 << HASH_BITS, st)(d_in, n, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist);
 		}
 		const u32 n_tiles = (u32)((n + TILE - 1) / TILE);
-		if (n_tiles) match_kernel<<<n_tiles, MATCH_THREADS, MATCH_SMEM, st>>>(d_in, n, p.chunk_bytes, unit, mp, prevdist, match);
-		parse_kernel<<<(n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st>>>(
+		if (n_tiles) B2D_LAUNCH(match_kernel, n_tiles, MATCH_THREADS, MATCH_SMEM, st)(d_in, n, p.chunk_bytes, unit, mp, prevdist, match);
+		B2D_LAUNCH(parse_kernel, (n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st)(
 			match, n, unit, n_blocks, p.lazy, tokens, recs, hp);
-		if (hp.K > 1) node_hist_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp);
-		if (hp.roots_only) huffman_kernel<<<(n_roots + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_roots, hp.H, n, hp);
-		else huffman_kernel<<<(n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st>>>(recs, n_recs, 1, n, hp);
+		if (hp.K > 1) B2D_LAUNCH(node_hist_kernel, (n_roots + 3) / 4, 128, 0, st)(recs, n_roots, n, hp);
+		if (hp.roots_only) B2D_LAUNCH(huffman_kernel, (n_roots + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st)(recs, n_roots, hp.H, n, hp);
+		else B2D_LAUNCH(huffman_kernel, (n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st)(recs, n_recs, 1, n, hp);
 	}
-	if (hp.K > 1) split_decide_kernel<<<(n_roots + 3) / 4, 128, 0, st>>>(recs, n_roots, n, hp, p.mode);
-	layout_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(recs, n_blocks, n_chunks, n, p.chunk_bytes, unit,
+	if (hp.K > 1) B2D_LAUNCH(split_decide_kernel, (n_roots + 3) / 4, 128, 0, st)(recs, n_roots, n, hp, p.mode);
+	B2D_LAUNCH(layout_kernel, (n_chunks + 127) / 128, 128, 0, st)(recs, n_blocks, n_chunks, n, p.chunk_bytes, unit,
 	                                                     p.mode, is_last, ref_framing, chunk_len, chunk_tail, hp);
-	scan_kernel<<<1, 1024, 0, st>>>(chunk_len, n_chunks, chunk_off, d_out_len_total, d_chunk_out_len);
-	emit_kernel<<<n_blocks, EMIT_THREADS, 0, st>>>(d_in, n, p.chunk_bytes, unit, n_blocks, n_chunks, recs,
+	B2D_LAUNCH(scan_kernel, 1, 1024, 0, st)(chunk_len, n_chunks, chunk_off, d_out_len_total, d_chunk_out_len);
+	B2D_LAUNCH(emit_kernel, n_blocks, EMIT_THREADS, 0, st)(d_in, n, p.chunk_bytes, unit, n_blocks, n_chunks, recs,
 	                                               tokens, chunk_off, chunk_tail, is_last, ref_framing, d_out, hp);
-	if (d_block_bits) block_bits_kernel<<<(n_roots + 255) / 256, 256, 0, st>>>(recs, n_roots, d_block_bits, hp);
+	if (d_block_bits) B2D_LAUNCH(block_bits_kernel, (n_roots + 255) / 256, 256, 0, st)(recs, n_roots, d_block_bits, hp);
 	return cudaGetLastError();
 }
 

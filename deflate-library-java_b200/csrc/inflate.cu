@@ -75,7 +75,8 @@ struct __align__(16) SideSmem {           // slow-path description of the two co
 	u16 d_sorted[32];
 };
 // Shared memory of a CTA, by shared-WINDOW address (on sm_100 the static segment of a CTA starts at 0x400, the first
-// KiB being the system's; kernels check that once and trap if it ever differs):
+// KiB being the system's; b2d_init runs smem_base_probe_kernel once per device and refuses the device with
+// B2D_ERR_CUDA if that ever differs):
 //   0x0400  4 x reference queue, 256 B each        -> "queue full" is `(next slot & 0xFF) == 0`
 //   0x0800  4 x distance LUT, 1 KiB each
 //   0x1800  4 x SideSmem
@@ -86,7 +87,7 @@ struct __align__(16) SideSmem {           // slow-path description of the two co
 // one table address in a register, not two.
 static_assert(WARPS_PER_CTA == 4 && LL_TB == 10 && D_TB == 8, "shared-memory layout below is written for these");
 static_assert(sizeof(SideSmem) * 4 <= 0x800, "SideSmem area");
-constexpr u32 SM_WINDOW_BASE = 0x400;
+constexpr u32 SM_WINDOW_BASE = INFLATE_SMEM_WINDOW_BASE;
 constexpr int SM_MQ_OFF = 0x400 - 0x400, SM_D_OFF = 0x800 - 0x400, SM_SIDE_OFF = 0x1800 - 0x400, SM_LL_OFF = 0x2000 - 0x400,
               SM_W_OFF = 0x6000 - 0x400;
 constexpr int SM_BYTES = SM_W_OFF + WARPS_PER_CTA * (int)sizeof(WarpSmem);
@@ -101,8 +102,7 @@ struct Sm {                               // one warp's view, in registers
 	__device__ __forceinline__ WarpSmem *operator->() const { return w; }
 };
 __device__ __forceinline__ Sm warp_smem(u8 *raw, u32 warp) {
-	if ((u32)__cvta_generic_to_shared(raw) != SM_WINDOW_BASE) __trap();
-	Sm s;
+	Sm s;                                 // (raw sits at SM_WINDOW_BASE: checked once per device by b2d_init, see the probe below)
 	s.ll = (u32 *)(raw + SM_LL_OFF) + (warp << LL_TB);
 	s.dl = (u32 *)(raw + SM_D_OFF) + (warp << D_TB);
 	s.mq = (uint2 *)(raw + SM_MQ_OFF) + warp * 32;
@@ -986,7 +986,7 @@ __device__ void fixed_tables(Member &m, const Sm &sm, u32 lane) {
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
-inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_members,
+inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const u64 *__restrict__ in_end, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
                u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags,
                long long mdelta) {
@@ -997,11 +997,11 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, u32 n_
 	const Sm sm = warp_smem(smem_raw, warp);
 
 	Member m;
-	u64 i0 = in_off[mi], i1 = in_off[mi + 1];
+	u64 i0 = in_off[mi], i1 = in_end ? in_end[mi] : in_off[mi + 1];     // in_end: members need not be back to back
 	u64 o0 = out_off[mi], o1 = out_off[mi + 1];
 	const u8 *src = in + i0;
 	u32 lead = (u32)((uintptr_t)src & 3);
-	u64 in_len = i1 - i0;
+	u64 in_len = i1 > i0 ? i1 - i0 : 0;
 	m.in.words = (const u32 *)(src - lead);
 	m.in.lead8 = lead * 8;
 	m.in.total_bits = in_len * 8;
@@ -1198,12 +1198,13 @@ cudaError_t launch_inflate_units(const u8 *d_in, const u64 *d_chunk_in_off, u32 
                                  u32 chunk_bytes, u32 block_bytes, u64 out_total, u8 *d_out, int *d_chunk_status,
                                  void *d_scratch, cudaStream_t st) {
 	if (n_chunks == 0) return cudaSuccess;
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[MAX_DEVICES] = {};
+	const int slot = current_device_slot();
+	if (!attr_set[slot]) {
 		cudaError_t e = cudaFuncSetAttribute(inflate_units_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
 		                                     cudaSharedmemCarveoutMaxShared);
 		if (e != cudaSuccess) return e;
-		attr_set = true;
+		attr_set[slot] = true;
 	}
 	const u32 bpc = chunk_bytes / block_bytes;
 	const u32 n_units = n_chunks * bpc;
@@ -1211,28 +1212,49 @@ cudaError_t launch_inflate_units(const u8 *d_in, const u64 *d_chunk_in_off, u32 
 	u64 *glist = (u64 *)d_scratch;
 	u32 *gcount = (u32 *)(glist + (u64)n_units * gcap);
 	int *ustatus = (int *)(gcount + n_units);
-	inflate_units_kernel<<<(n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st>>>(
+	B2D_LAUNCH(inflate_units_kernel, (n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st)(
 		d_in, d_chunk_in_off, d_block_bits, n_units, bpc, chunk_bytes, block_bytes, out_total, d_out, glist, gcap, gcount, ustatus);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return e;
-	resolve_units_kernel<<<(n_chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st>>>(
+	B2D_LAUNCH(resolve_units_kernel, (n_chunks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, WARPS_PER_CTA * 32, 0, st)(
 		d_out, glist, gcap, gcount, ustatus, n_chunks, bpc, chunk_bytes, block_bytes, out_total, d_chunk_status);
 	return cudaGetLastError();
 }
 
+// The static shared segment must start at SM_WINDOW_BASE for the LUT addressing above; this kernel has the decoder's
+// declaration and reports where it landed.
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) smem_base_probe_kernel(u32 *out) {
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
+	smem_raw[threadIdx.x] = (u8)threadIdx.x;          // keep the array alive
+	__syncthreads();
+	if (threadIdx.x == 0) out[0] = (u32)__cvta_generic_to_shared(smem_raw) + (smem_raw[1] == 1 ? 0u : 1u);
+}
+cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st) {
+	u32 *d = nullptr;
+	cudaError_t e = cudaMalloc(&d, 4);
+	if (e != cudaSuccess) return e;
+	B2D_LAUNCH(smem_base_probe_kernel, 1, WARPS_PER_CTA * 32, 0, st)(d);
+	e = cudaGetLastError();
+	if (e == cudaSuccess) e = cudaMemcpyAsync(base_out, d, 4, cudaMemcpyDeviceToHost, st);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+	cudaFree(d);
+	return e;
+}
+
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,
                            u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st,
-                           uint8_t *out_mirror) {
+                           uint8_t *out_mirror, const u64 *d_in_end) {
 	if (n == 0) return cudaSuccess;
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[MAX_DEVICES] = {};
+	const int slot = current_device_slot();
+	if (!attr_set[slot]) {
 		cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
 		                                     cudaSharedmemCarveoutMaxShared);
 		if (e != cudaSuccess) return e;
-		attr_set = true;
+		attr_set[slot] = true;
 	}
 	u32 grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	inflate_kernel<<<grid, WARPS_PER_CTA * 32, 0, st>>>(d_in, d_in_off, n, d_out, d_out_off, d_out_len,
+	B2D_LAUNCH(inflate_kernel, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len,
 	                                                     d_in_consumed, d_status, flags,
 	                                                     out_mirror ? (long long)(out_mirror - d_out) : 0ll);
 	return cudaGetLastError();

@@ -6,10 +6,28 @@
 
 namespace b2d {
 
+// Every kernel launch of the library goes through B2D_LAUNCH, which counts it (b2d_kernel_launches(): bench.py's
+// gpu_launches is read from here, not derived by hand).  Device-dependent one-time state (cudaFuncSetAttribute,
+// __constant__ uploads) is kept per CUDA ordinal, so b2d_init on another device or several devices at once is fine.
+constexpr int MAX_DEVICES = 16;
+void count_launch();
+#define B2D_LAUNCH(kernel, grid, block, smem, stream) ::b2d::count_launch(), kernel<<<(grid), (block), (smem), (stream)>>>
+inline int current_device_slot() {
+	int d = 0;
+	if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= MAX_DEVICES) d = 0;
+	return d;
+}
+
 // inflate.cu
+// runs a one-warp kernel with the decoder's static shared-memory declaration and reports where the segment starts in the
+// shared window; the decoder's LUT addressing (see inflate.cu) needs it at INFLATE_SMEM_WINDOW_BASE
+constexpr uint32_t INFLATE_SMEM_WINDOW_BASE = 0x400;
+cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st);
 cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
-                           int *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr);
+                           int *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr,
+                           const uint64_t *d_in_end = nullptr);
+// d_in_end (optional): member i occupies d_in[d_in_off[i], d_in_end[i]) instead of [d_in_off[i], d_in_off[i + 1])
 // out_mirror (optional): a mapped host address for d_out[0] with (out_mirror - d_out) % 128 == 0; every output byte is
 // then delivered there as well by the kernel itself (no device-to-host copy afterwards)
 

@@ -20,6 +20,42 @@ def unit_range(n_units, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def slice_ranges(n_units, rank, world, n_slices):
+    """Slice-major partition for a pipelined gather: the stream is cut into `n_slices` contiguous slices, and inside
+    slice k rank r takes the contiguous sub-range unit_range(len(slice k), r, world).  A rank thus owns n_slices
+    contiguous ranges instead of one; in return everything before slice k's payloads is known once slice k's sizes are
+    all-gathered, so slice k can travel to its final place on GPU 0 while slice k + 1 is still being compressed.
+    -> [(lo, hi)] per slice."""
+    out = []
+    for k in range(n_slices):
+        lo, hi = unit_range(n_units, k, n_slices)
+        a, b = unit_range(hi - lo, rank, world)
+        out.append((lo + a, lo + b))
+    return out
+
+
+def gather_slice(local_payload, local_total, all_totals, stream, base, group=None, dst=0):
+    """One exchange step of the pipelined gather: every rank's payload of this slice goes to rank `dst`, in rank order,
+    starting at stream[base].  all_totals: the slice's compressed byte count of every rank (host ints, from the size
+    all-gather).  All transfers of the step are posted as ONE batch (ncclGroupStart/End underneath), so they run side
+    by side instead of one after the other.  -> bytes the slice occupies in the stream."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    offs = [0]
+    for t in all_totals:
+        offs.append(offs[-1] + int(t))
+    if rank == dst:
+        if local_total:
+            stream[base + offs[rank]:base + offs[rank + 1]].copy_(local_payload[:local_total], non_blocking=True)
+        ops = [dist.P2POp(dist.irecv, stream[base + offs[r]:base + offs[r + 1]], r, group)
+               for r in range(world) if r != dst and all_totals[r]]
+    else:
+        ops = [dist.P2POp(dist.isend, local_payload[:local_total], dst, group)] if local_total else []
+    if ops:
+        for q in dist.batch_isend_irecv(ops):
+            q.wait()
+    return offs[-1]
+
+
 def all_gather_sizes(local_sizes, group=None):
     """local_sizes: 1-D int64 tensor (per-chunk compressed sizes of this rank; lengths may differ per rank).
     -> list of 1-D int64 CPU tensors, one per rank."""
@@ -54,12 +90,14 @@ def gather_stream(local_payload, local_sizes, group=None, dst=0):
         for t in totals:
             offs.append(offs[-1] + t)
         stream[offs[rank]:offs[rank + 1]] = local_payload[:totals[rank]]
-        reqs = [dist.irecv(stream[offs[r]:offs[r + 1]], src=r, group=group) for r in range(world) if r != dst and totals[r]]
-        for q in reqs:
-            q.wait()
+        ops = [dist.P2POp(dist.irecv, stream[offs[r]:offs[r + 1]], r, group) for r in range(world) if r != dst and totals[r]]
+        if ops:                                      # one batch: the transfers run side by side, not serialised
+            for q in dist.batch_isend_irecv(ops):
+                q.wait()
         return stream, all_sizes
     if totals[rank]:
-        dist.send(local_payload[:totals[rank]].contiguous(), dst=dst, group=group)
+        for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, local_payload[:totals[rank]].contiguous(), dst, group)]):
+            q.wait()
     return None, all_sizes
 
 

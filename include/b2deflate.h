@@ -7,9 +7,11 @@
  * maintainer of the reference would add.  Plain pointers and sizes only -- no CUDA or torch types.
  *
  * Conventions
- *   - One process drives one GPU (b2d_init(device)); calls are blocking and serialised by an
- *     internal mutex, so they may arrive from any thread (the reference classes are not thread-safe
- *     and spawn no threads; FFM downcalls may come from any JVM thread).
+ *   - One process drives one GPU (b2d_init(device)) or several GPUs of the box (b2d_init_devices): the host
+ *     entry points then partition the independent units (gzip members, chunks) into contiguous ranges, one per
+ *     GPU, and join the results.  Calls are blocking and serialised per GPU by an internal mutex,
+ *     so they may arrive from any thread (the reference classes are not thread-safe and spawn no threads; FFM
+ *     downcalls may come from any JVM thread).
  *   - Host entry points take HOST pointers and include the host<->device copies.  The *_dev entry
  *     points take DEVICE pointers (e.g. torch tensor data_ptr()) and run on the given CUDA stream
  *     (a cudaStream_t passed as void*; NULL = the CUDA legacy default stream, which is what
@@ -66,7 +68,18 @@ enum {
  * Idempotent for the same device.  Reference objects "only use memory and no OS resources"
  * (InflaterInputStream.java:22-23), so nothing below requires per-stream teardown. */
 int b2d_init(int device);
+/* Binds the process to n GPUs (CUDA ordinals, distinct); devices[0] is "GPU 0", the one single-device work runs on and
+ * the gather target.  n <= 0: every GPU of the box.  The host entry points (b2d_inflate_batch, b2d_gunzip_batch,
+ * b2d_deflate_chunks[_indexed], b2d_inflate_chunks) then shard their units over the GPUs, one host thread per GPU,
+ * with the same results byte for byte as on one GPU; the *_dev entry points run on the GPU their output pointer
+ * lives on.  Compressed payloads are joined at the scanned offsets: straight into the caller's host buffer over every
+ * GPU's own PCIe link, or -- environment B2D_MULTI_GATHER=peer -- with one cudaMemcpyPeerAsync per GPU into GPU 0's
+ * memory (NVLink) and one copy from there.  The reference has no counterpart (DeflaterOutputStream.java:119-137 and
+ * Open.java:83-110 are sequential). */
+int b2d_init_devices(const int *devices, int n);
+int b2d_device_count(void);                  /* GPUs bound by b2d_init / b2d_init_devices */
 void b2d_shutdown(void);
+uint64_t b2d_kernel_launches(void);          /* kernels this library has launched so far (process-wide counter) */
 const char *b2d_strerror(int status);        /* message strings of Open.java / GzipInputStream.java */
 const char *b2d_last_error(void);            /* last CUDA error text for B2D_ERR_CUDA */
 int b2d_device_sm_count(void);

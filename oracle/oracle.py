@@ -38,7 +38,8 @@ def status_name(st):
 
 def build(force=False):
     """Compile oracle/build/liboracle.so with gcc (a few seconds)."""
-    srcs = [os.path.join(_HERE, f) for f in ("oracle_inflate.c", "oracle_deflate.c", "oracle_misc.c", "oracle.h")]
+    srcs = [os.path.join(_HERE, f) for f in ("oracle_inflate.c", "oracle_deflate.c", "oracle_misc.c", "oracle.h", "Makefile",
+                                             os.path.join("..", "deflate-library-java_b200", "csrc", "corpus.c"))]
     if not force and os.path.exists(_SO) and all(os.path.getmtime(_SO) >= os.path.getmtime(s) for s in srcs):
         return _SO
     subprocess.check_call(["make", "-C", _HERE, "-s", "-B" if force else "-s"])
@@ -76,6 +77,10 @@ def lib():
                                              ctypes.c_char_p, ctypes.c_size_t]
             L.oracle_gzip_parse_header.restype = ctypes.c_int
             L.oracle_gzip_parse_header.argtypes = [u8p, ctypes.c_size_t, szp]
+            for name in ("b2d_corpus_random", "b2d_corpus_text", "b2d_corpus_mixed"):   # SURVEY Appendix D generators
+                f = getattr(L, name)
+                f.restype = None
+                f.argtypes = [ctypes.c_uint64, ctypes.c_void_p, ctypes.c_size_t]
             _lib = L
     return _lib
 

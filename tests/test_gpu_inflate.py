@@ -218,14 +218,45 @@ def test_gunzip_batch_matches_reference_gzip_reader(b2d, oracle):
     for i, m in enumerate(members):
         st, out, cons = oracle.gunzip(m, out_cap=caps[i])
         assert int(status[i]) == st, (i, b2d.status_name(int(status[i])), oracle.status_name(st))
+        assert outs[i] == out, (i, len(outs[i]), len(out))        # also on failure: the bytes delivered before it
         if st == 0:
-            assert outs[i] == out and int(consumed[i]) == cons, i
+            assert int(consumed[i]) == cons, i
     outs2, _, _, status2 = b2d.gunzip_batch(members[:18])     # capacities from ISIZE
     assert not status2.any() and outs2 == outs[:18]
     # the same batch into page-locked memory (bytes delivered by the decoding warps): identical in every respect
     outs3, out_len3, consumed3, status3 = b2d.gunzip_batch(members, caps, pinned_out=True)
     assert outs3 == outs and np.array_equal(out_len3, out_len) and np.array_equal(consumed3, consumed)
     assert np.array_equal(status3, status)
+
+
+def test_gunzip_batch_member_never_reads_its_neighbour(b2d, oracle):
+    """A truncated or corrupt member must end where ITS bytes end (GzipInputStream reading that member alone), not run
+    on into the next member's header and body: status, out_len and the delivered bytes equal the oracle's for the
+    member on its own, whatever follows it in the batch."""
+    import gzip as pygzip
+    rng = random.Random(77)
+    a, b = _text(rng, 120000), _text(rng, 90000)
+    ga, gb = pygzip.compress(a, 6, mtime=0), pygzip.compress(b, 6, mtime=0)
+    raw_a = zlib_raw(a, 6)
+    cases = [ga[:len(ga) // 2], ga[:-9], ga[:-8], ga[:-4], ga[:10 + len(raw_a) - 1], ga[:10 + 3], ga[:10]]
+    for pinned in (False, True):
+        members = []
+        for c in cases:
+            members += [c, gb]                                   # every damaged member is followed by a valid one
+        outs, out_len, consumed, status = b2d.gunzip_batch(members, [200000] * len(members), pinned_out=pinned)
+        for i, m in enumerate(members):
+            st, out, cons = oracle.gunzip(m, out_cap=200000)
+            assert int(status[i]) == st, (i, b2d.status_name(int(status[i])), oracle.status_name(st))
+            assert int(out_len[i]) == len(out) and outs[i] == out, (i, int(out_len[i]), len(out))
+            assert int(consumed[i]) <= len(m), (i, int(consumed[i]), len(m))
+            if st == 0:
+                assert int(consumed[i]) == cons
+    # raw members through b2d_inflate_batch: a truncated member's range ends at the next member's start
+    members = [raw_a[:len(raw_a) // 3], zlib_raw(b, 6), raw_a[:-1], zlib_raw(b, 1)]
+    outs, out_len, consumed, crc, status = b2d.inflate_batch(members, 200000)
+    for i, m in enumerate(members):
+        st, out, cons = oracle.inflate(m, out_cap=200000)
+        assert int(status[i]) == st and outs[i] == out and int(consumed[i]) <= len(m), i
 
 
 def test_random_garbage_members(b2d, oracle):
