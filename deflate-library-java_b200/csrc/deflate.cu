@@ -122,8 +122,7 @@ __device__ __forceinline__ u32 warp_sum(u32 v) {
 // One warp per segment of the input (SEG bytes, never crossing a chunk).  The warp first re-inserts up to 32 KiB
 // before its segment so the head table is what a sequential insert would have left, then links every position of
 // the segment.  32 positions per step: match.any finds equal hashes inside the step, the shared head table (low 16
-// bits of the chunk-relative position per hash) gives the link to earlier steps.  Input words for step i + 2 are
-// requested while step i is processed, so the global-load latency is off the serial chain.
+// bits of the chunk-relative position per hash) gives the link to earlier steps.
 constexpr u32 CHAIN_SEG = 256u << 10;
 
 __global__ void __launch_bounds__(32)
@@ -149,39 +148,51 @@ chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 seg_bytes, 
 	const u32 ws_rel = (u32)(ws - cs);
 	u16 *__restrict__ pd = prevdist + org;
 	const u32 cmask = hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
-#define LOADW(i) ((i) < n_words ? __ldg(words + (i)) : 0u)
-	u32 o = o_ws + lane;
-	u32 a0 = LOADW(o >> 2), a1 = LOADW((o >> 2) + 1);
-	u32 b0 = LOADW((o + 32) >> 2), b1 = LOADW(((o + 32) >> 2) + 1);
-	for (u32 base = o_ws; base < o_se; base += 32) {
-		o = base + lane;
-		const u32 c0 = LOADW((o + 64) >> 2), c1 = LOADW(((o + 64) >> 2) + 1);    // for step + 2
-		const bool valid = o < o_se && o + (u32)hb <= o_ce;
-		const u32 v = __funnelshift_r(a0, a1, (o & 3) * 8) & cmask;
-		const u32 h = (v * 2654435761u) >> (32 - HASH_BITS);
-		const u32 prel = rel0 + o;
-		u32 dist = 0;
-		if (valid) {                                            // link to the newest position of earlier steps
-			u32 d = (prel - head[h]) & 0xFFFFu;
-			if (d == 0) d = 65536;
-			if (d <= WINDOW && d <= prel - ws_rel) dist = d;
-		}
-		__syncwarp();
-		if (valid) head[h] = (u16)prel;                         // equal hashes in this step: one of them wins ...
-		__syncwarp();
-		const bool lost = valid && head[h] != (u16)prel;
-		if (__any_sync(FULL_MASK, lost)) {                      // ... then (rare) sort the step out exactly
-			const u32 grp = __match_any_sync(FULL_MASK, valid ? h : (0x80000000u | lane));
-			const u32 lower = grp & lanemask_lt();
-			if (valid && lower) dist = lane - (31 - __clz(lower));    // same hash earlier in this step
+	// Input: one coalesced load brings 32 consecutive words = the bytes of FOUR steps; the four bytes of a lane's
+	// position are taken from the lanes that hold them with shuffles.  Three more groups are in flight (16 steps of
+	// lookahead), so the global-load latency is off the serial chain of head-table updates.
+#define LOADG(g) (((g) * 32u + lane) < n_words ? __ldg(words + (g) * 32u + lane) : 0u)
+	const u32 g_first = o_ws >> 7;                             // group = 128 bytes; positions before o_ws are skipped
+	u32 G0 = LOADG(g_first), G1 = LOADG(g_first + 1), G2 = LOADG(g_first + 2), G3 = LOADG(g_first + 3);
+	for (u32 g = g_first; g * 128u < o_se; g++) {
+		const u32 G4 = LOADG(g + 4);
+#pragma unroll
+		for (u32 s = 0; s < 4; s++) {
+			const u32 o = g * 128u + s * 32u + lane;
+			const u32 w0 = __shfl_sync(FULL_MASK, G0, 8 * s + (lane >> 2));
+			u32 w1 = __shfl_sync(FULL_MASK, G0, (8 * s + (lane >> 2) + 1) & 31);
+			if (s == 3) { const u32 wn = __shfl_sync(FULL_MASK, G1, 0); if (lane >= 28) w1 = wn; }
+			const bool valid = o >= o_ws && o < o_se && o + (u32)hb <= o_ce;
+			const u32 v = __funnelshift_r(w0, w1, (lane & 3) * 8) & cmask;
+			const u32 h = (v * 2654435761u) >> (32 - HASH_BITS);
+			const u32 prel = rel0 + o;
+			u32 dist = 0;
+			if (valid) {                                            // link to the newest position of earlier steps
+				u32 d = (prel - head[h]) & 0xFFFFu;
+				if (d == 0) d = 65536;
+				if (d <= WINDOW && d <= prel - ws_rel) dist = d;
+			}
 			__syncwarp();
-			if (valid && (grp >> lane) == 1u) head[h] = (u16)prel;    // the highest lane of each group stays
+			if (valid) head[h] = (u16)prel;                         // equal hashes in this step: one of them wins ...
 			__syncwarp();
+			// ... then the step is sorted out exactly, one colliding hash at a time (match.any would loop over every
+			// DISTINCT hash of the step, about 30 rounds for a single collision; this loops over the colliding ones)
+			u32 lostmask = __ballot_sync(FULL_MASK, valid && head[h] != (u16)prel);
+			while (lostmask) {
+				const u32 hl = __shfl_sync(FULL_MASK, h, __ffs(lostmask) - 1);
+				const bool mine = valid && h == hl;
+				const u32 grp = __ballot_sync(FULL_MASK, mine);
+				const u32 lower = grp & lanemask_lt();
+				if (mine && lower) dist = lane - (31 - __clz(lower));     // same hash earlier in this step
+				if (mine && (grp >> lane) == 1u) head[h] = (u16)prel;     // the highest lane of the group stays
+				lostmask &= ~grp;
+			}
+			__syncwarp();
+			if (o >= o_ss && o < o_se) pd[o] = (u16)dist;
 		}
-		if (o >= o_ss && o < o_se) pd[o] = (u16)dist;
-		a0 = b0; a1 = b1; b0 = c0; b1 = c1;
+		G0 = G1; G1 = G2; G2 = G3; G3 = G4;
 	}
-#undef LOADW
+#undef LOADG
 }
 
 // ---------------------------------------------------------------- K1b: match search
@@ -245,6 +256,7 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	const u32 n_pos = (u32)(te - ts);
 	const bool inherit = mp.search == B2D_SEARCH_DEFAULT;
 	constexpr u32 RUN = 16;                           // consecutive positions per thread and round: four 16-byte stores per lane
+	const u32 cmask = mp.hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
 	for (u32 round = 0; round < TILE / (MATCH_THREADS * RUN); round++) {
 	const u32 k0 = (round * MATCH_THREADS + threadIdx.x) * RUN;
 	if (k0 >= n_pos) break;
@@ -252,17 +264,33 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	// on when a position reaches it (no 64-bit division per position)
 	const u32 rel0 = (u32)(ts + k0 - cs), ce_rel = (u32)(ce - cs);
 	u32 be_rel = (rel0 / block_bytes + 1) * block_bytes;
-	u32 res[RUN];
 	int prev_len = 0, prev_dist = 0;
 	int run_len = 0, since = 1 << 20;                 // length of / positions since the last searched long match
 	constexpr int SKIP_MIN = 8;
+	// The run's own bytes (16 + 3) and links (16) are read ONCE, with three 128-bit loads and a word, and kept in
+	// registers: inside the run the position's four bytes and its link are the low ends of two 64-bit windows that
+	// slide by a byte / a link per position.  (Read per position they were 3 shared-memory loads at 4- and 8-way bank
+	// conflicts -- runs of 16 positions put the lanes 16 bytes apart -- and half of the kernel's shared wavefronts.)
+	const u32 o0 = woff + k0;                        // multiple of 16
+	const uint4 own_w = *(const uint4 *)(W + (o0 >> 2));
+	const u32 own_w4 = W[(o0 >> 2) + 4];
+	const uint4 own_pa = *(const uint4 *)(P + o0), own_pb = *(const uint4 *)(P + o0 + 8);
+	const u32 ow[5] = {own_w.x, own_w.y, own_w.z, own_w.w, own_w4};
+	const u32 pl[8] = {own_pa.x, own_pa.y, own_pa.z, own_pa.w, own_pb.x, own_pb.y, own_pb.z, own_pb.w};
+	uint4 *dst = (uint4 *)(match + ts + k0);        // ts is a multiple of TILE and k0 of RUN: 16-byte aligned; padded past n
+#pragma unroll
+	for (u32 q = 0; q < RUN / 4; q++) {
+	u64 win = (u64)ow[q] | (u64)ow[q + 1] << 32;
+	u64 lwin = (u64)pl[2 * q] | (u64)pl[2 * q + 1] << 32;
+	u32 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
 #pragma unroll 1
-	for (u32 j = 0; j < RUN; j++) {
+	for (u32 r = 0; r < 4; r++, win >>= 8, lwin >>= 16) {
+		const u32 j = 4 * q + r;
 		const u32 k = k0 + j;
-		if (k >= n_pos) { res[j] = 0; continue; }
+		if (k >= n_pos) break;
 		const u32 rel = rel0 + j;                                  // p - cs
-		const u32 o = woff + k;
-		const u32 cur = sm_load4(W, o);
+		const u32 o = o0 + j;
+		const u32 cur = (u32)win;
 		if (rel >= be_rel) be_rel += block_bytes;
 		const int maxlen = (int)min((u32)MAX_MATCH, min(ce_rel, be_rel) - rel);   // runs stop at the block end (Lz77Huffman.java:75)
 		int best_len = 0, best_dist = 0;
@@ -272,7 +300,6 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 				if (len >= 3) { best_len = len; best_dist = 1; }
 			}
 		} else if (mp.search != B2D_SEARCH_LITERAL && maxlen >= mp.hb && rel + mp.hb <= ce_rel) {
-			const u32 cmask = mp.hb == 3 ? 0xFFFFFFu : 0xFFFFFFFFu;
 			const u32 max_dist = min(WINDOW, rel);
 			int depth = mp.depth;
 			best_len = mp.hb - 1;
@@ -287,8 +314,10 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 				// (Position 1 is searched: the parser's lazy step compares it with the match before it.)
 				if (since >= 2 && since < run_len) depth = 0;
 			}
-			u32 d = P[o];
+			u32 d = (u32)lwin & 0xFFFFu;
 			u32 dist = 0;
+			u32 end_own = 0;                                       // own bytes at best_len - 3 .. best_len, read when best_len changes
+			int end_for = -1;
 			while (d != 0 && depth-- > 0) {
 				dist += d;
 				if (dist > max_dist) break;
@@ -296,7 +325,10 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 				d = P[c];
 				if ((int)dist == best_dist) continue;
 				// a candidate can only win if it also matches the byte that would make it longer
-				if (best_len >= 4 && sm_load4(W, c + best_len - 3) != sm_load4(W, o + best_len - 3)) continue;
+				if (best_len >= 4) {
+					if (end_for != best_len) { end_own = sm_load4(W, o + best_len - 3); end_for = best_len; }
+					if (sm_load4(W, c + best_len - 3) != end_own) continue;
+				}
 				if (((sm_load4(W, c) ^ cur) & cmask) == 0) {
 					int len = mp.hb + sm_match_len(W, c + mp.hb, o + mp.hb, maxlen - mp.hb);
 					if (len > best_len) {                          // strict: ties keep the smaller distance (:80)
@@ -312,12 +344,11 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 		since++;
 		prev_len = best_len;
 		prev_dist = best_dist;
-		res[j] = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
+		const u32 v = (cur << 24) | ((u32)best_len << 15) | (u32)(best_dist > 0 ? best_dist - 1 : 0);
+		if (r == 0) r0 = v; else if (r == 1) r1 = v; else if (r == 2) r2 = v; else r3 = v;
 	}
-	// ts is a multiple of TILE and k0 of RUN, so the stores are 16-byte aligned; the scratch array is padded past n
-	uint4 *dst = (uint4 *)(match + ts + k0);
-#pragma unroll
-	for (u32 q = 0; q < RUN / 4; q++) dst[q] = make_uint4(res[4 * q], res[4 * q + 1], res[4 * q + 2], res[4 * q + 3]);
+	dst[q] = make_uint4(r0, r1, r2, r3);
+	}
 	}
 }
 

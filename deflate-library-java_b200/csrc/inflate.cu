@@ -69,6 +69,9 @@ struct __align__(16) WarpSmem {
 	// Kept here, reachable from the tile pointer, rather than in the Member.
 	u8 *m_out;
 	u64 m_done;
+	// progress reports (b2d_inflate_batch delivering a pinned, uniformly strided output with the copy engine): the mapped
+	// host word that receives how many PROGRESS_PIECE-sized pieces of this member are final in device memory
+	u32 *m_prog;
 };
 struct __align__(16) SideSmem {           // slow-path description of the two codes
 	Canon ll_canon, d_canon;
@@ -445,8 +448,22 @@ __device__ __forceinline__ void mirror_copy(const u8 *dev, long long mdelta, u64
 	for (; i < nv; i += 32) d4[i] = __ldcg(s4 + i);
 	for (u64 k = head + (nv << 4) + lane; k < n; k += 32) h[k] = dev[k];
 }
+// Progress reports instead of a mirror (mdelta == MDELTA_PROGRESS): the output stays in device memory and the HOST
+// moves it, piece by piece across all members of the batch, with strided copy-engine transfers while the decode goes
+// on (api.cu, inflate_host).  A warp tells the host how many whole pieces of its member are final: its stores are
+// fenced to system scope first, then one lane writes the count to the member's word in mapped host memory.
+constexpr long long MDELTA_PROGRESS = 1;       // (a real mirror delta is a multiple of 128)
+__device__ __forceinline__ void report_progress(WarpSmem *w, const u8 *end, bool final, u32 lane) {
+	const u32 pieces = final ? 0x7FFFFFFFu : (u32)((u64)(end - w->m_out) >> INFLATE_PROGRESS_SHIFT);
+	if (pieces <= (u32)w->m_done) return;
+	__threadfence_system();
+	__syncwarp();
+	if (lane == 0) { *(volatile u32 *)w->m_prog = pieces; w->m_done = pieces; }
+	__syncwarp();
+}
 // end = device address just past the member's bytes that are final in device memory
 __device__ __forceinline__ void mirror_progress(WarpSmem *w, const u8 *end, long long mdelta, bool final, u32 lane) {
+	if (mdelta == MDELTA_PROGRESS) { report_progress(w, end, final, lane); return; }
 	const u8 *base = w->m_out;
 	const u64 done = w->m_done, pos = (u64)(end - base);
 	u64 upto = pos;
@@ -989,7 +1006,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const u64 *__restrict__ in_end, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
                u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags,
-               long long mdelta) {
+               long long mdelta, u32 *progress) {
 	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	u32 mi = blockIdx.x * WARPS_PER_CTA + warp;
@@ -1014,7 +1031,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	m.glist = nullptr;
 	m.gcount = m.gcap = m.hist_base = 0;
 	m.mdelta = mdelta;
-	if (lane == 0) { sm->m_out = m.out; sm->m_done = 0; }
+	if (lane == 0) { sm->m_out = m.out; sm->m_done = 0; sm->m_prog = progress ? progress + mi : nullptr; }
 	__syncwarp();
 	set_tile_origin(m, 0);
 	m.tables = 0;
@@ -1243,7 +1260,7 @@ cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st) {
 
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,
                            u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st,
-                           uint8_t *out_mirror, const u64 *d_in_end) {
+                           uint8_t *out_mirror, const u64 *d_in_end, uint32_t *progress) {
 	if (n == 0) return cudaSuccess;
 	static bool attr_set[MAX_DEVICES] = {};
 	const int slot = current_device_slot();
@@ -1256,7 +1273,8 @@ cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out
 	u32 grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
 	B2D_LAUNCH(inflate_kernel, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len,
 	                                                     d_in_consumed, d_status, flags,
-	                                                     out_mirror ? (long long)(out_mirror - d_out) : 0ll);
+	                                                     progress ? MDELTA_PROGRESS : out_mirror ? (long long)(out_mirror - d_out) : 0ll,
+	                                                     progress);
 	return cudaGetLastError();
 }
 

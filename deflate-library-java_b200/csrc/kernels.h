@@ -22,11 +22,14 @@ inline int current_device_slot() {
 // runs a one-warp kernel with the decoder's static shared-memory declaration and reports where the segment starts in the
 // shared window; the decoder's LUT addressing (see inflate.cu) needs it at INFLATE_SMEM_WINDOW_BASE
 constexpr uint32_t INFLATE_SMEM_WINDOW_BASE = 0x400;
+constexpr uint32_t INFLATE_PROGRESS_SHIFT = 15;          // 32 KiB pieces
 cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st);
 cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
                            int *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr,
-                           const uint64_t *d_in_end = nullptr);
+                           const uint64_t *d_in_end = nullptr, uint32_t *progress = nullptr);
+// progress (optional, instead of out_mirror): mapped host words, one per member; member i's word receives the number of
+// whole (1 << INFLATE_PROGRESS_SHIFT)-byte pieces of its output that are final in d_out (0x7FFFFFFF when it is done)
 // d_in_end (optional): member i occupies d_in[d_in_off[i], d_in_end[i]) instead of [d_in_off[i], d_in_off[i + 1])
 // out_mirror (optional): a mapped host address for d_out[0] with (out_mirror - d_out) % 128 == 0; every output byte is
 // then delivered there as well by the kernel itself (no device-to-host copy afterwards)

@@ -1,5 +1,6 @@
 """GPU parity: b2d_inflate_batch (through the C ABI, host pointers) against the oracle restating
 decomp/Open.java, the reference's golden vectors, and zlib."""
+import os
 import random
 import zlib
 
@@ -329,3 +330,52 @@ def test_pinned_output_is_delivered_by_the_kernel(b2d, oracle):
             assert (buf.array[off + n:off + c] == 0xEE).all(), i
             off += c
     _check_against_oracle(b2d, oracle, members, caps, flags=b2d.INFLATE_CRC32)
+
+
+def test_pinned_uniform_slots_are_delivered_by_the_copy_engine(b2d, oracle):
+    """Slots of one size in a page-locked buffer: the decoding warps only REPORT progress (32 KiB pieces) and the host
+    moves finished pieces of all members with strided copy-engine transfers while the decode runs.  Same bytes, lengths,
+    consumed counts, checksums and statuses as the pageable path and as the oracle, for members that fill the slot, stop
+    short, overflow it, fail, are stored-only, or are empty; and B2D_INFLATE_D2H picks the other paths for the same call."""
+    rng = random.Random(31337)
+    cap = 100000                                          # not a multiple of the piece size
+    members = []
+    for i in range(300):
+        kind = i % 10
+        if kind == 0:
+            members.append(zlib_raw(rng.randbytes(cap), 0))                       # stored blocks only, fills the slot
+        elif kind == 1:
+            members.append(zlib_raw(_text(rng, rng.randrange(0, 3000)), 6))       # far short of the slot
+        elif kind == 2:
+            members.append(zlib_raw(_text(rng, cap + 5000), 6))                   # overflows the slot
+        elif kind == 3:
+            members.append(zlib_raw(_text(rng, 60000), 6)[:rng.randrange(1, 9000)])   # truncated
+        elif kind == 4:
+            members.append(zlib_raw(bytes(cap), 9))                               # length 258 / distance 1
+        elif kind == 5:
+            members.append(b"")
+        else:
+            members.append(zlib_raw(_text(rng, cap - rng.randrange(0, 40000)), rng.choice([1, 6, 9])))
+    ref = b2d.inflate_batch(members, cap, b2d.INFLATE_CRC32)
+    for i in (0, 1, 2, 3, 4, 5, 6, 17, 299):
+        st, out, cons = oracle.inflate(members[i], out_cap=cap)
+        assert int(ref[4][i]) == st and ref[0][i] == out, i
+    for mode in ("", "ce", "mirror", "copy"):
+        if mode:
+            os.environ["B2D_INFLATE_D2H"] = mode
+        try:
+            buf = b2d.PinnedBuffer(cap * len(members) + 64)
+            buf.array[:] = 0xEE
+            got = b2d.inflate_batch(members, cap, b2d.INFLATE_CRC32, out=buf.array[7:7 + cap * len(members)], pinned_in=True)
+        finally:
+            os.environ.pop("B2D_INFLATE_D2H", None)
+        assert got[0] == ref[0], mode
+        for k in range(1, 5):
+            assert np.array_equal(got[k], ref[k]), (mode, k)
+        assert (buf.array[:7] == 0xEE).all() and (buf.array[7 + cap * len(members):] == 0xEE).all(), mode
+    # gzip members through the same path (b2d_gunzip_batch, the bench's end-to-end call)
+    import gzip as pygzip
+    datas = [_text(rng, 65536 - (i % 7) * 1000) for i in range(130)]
+    gz = [pygzip.compress(d, 6, mtime=0) for d in datas]
+    outs, out_len, consumed, status = b2d.gunzip_batch(gz, 65536, pinned_out=True)
+    assert not status.any() and outs == datas and [int(c) for c in consumed] == [len(g) for g in gz]
