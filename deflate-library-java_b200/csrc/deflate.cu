@@ -20,6 +20,7 @@
 //   layout : one thread per chunk picks stored / fixed / dynamic per block and assigns bit offsets;
 //            scan_kernel turns chunk sizes into byte offsets
 //   emit   : one CTA per block: prefix sum of code lengths, bits OR-ed into a shared staging tile, coalesced out
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -156,15 +157,21 @@ chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 seg_bytes, 
 	u32 G0 = LOADG(g_first), G1 = LOADG(g_first + 1), G2 = LOADG(g_first + 2), G3 = LOADG(g_first + 3);
 	for (u32 g = g_first; g * 128u < o_se; g++) {
 		const u32 G4 = LOADG(g + 4);
+		// the four steps' hashes first (independent of the head table), then the serial part of each step
+		u32 hs[4];
 #pragma unroll
 		for (u32 s = 0; s < 4; s++) {
-			const u32 o = g * 128u + s * 32u + lane;
 			const u32 w0 = __shfl_sync(FULL_MASK, G0, 8 * s + (lane >> 2));
 			u32 w1 = __shfl_sync(FULL_MASK, G0, (8 * s + (lane >> 2) + 1) & 31);
 			if (s == 3) { const u32 wn = __shfl_sync(FULL_MASK, G1, 0); if (lane >= 28) w1 = wn; }
-			const bool valid = o >= o_ws && o < o_se && o + (u32)hb <= o_ce;
 			const u32 v = __funnelshift_r(w0, w1, (lane & 3) * 8) & cmask;
-			const u32 h = (v * 2654435761u) >> (32 - HASH_BITS);
+			hs[s] = (v * 2654435761u) >> (32 - HASH_BITS);
+		}
+#pragma unroll
+		for (u32 s = 0; s < 4; s++) {
+			const u32 o = g * 128u + s * 32u + lane;
+			const bool valid = o >= o_ws && o < o_se && o + (u32)hb <= o_ce;
+			const u32 h = hs[s];
 			const u32 prel = rel0 + o;
 			u32 dist = 0;
 			if (valid) {                                            // link to the newest position of earlier steps
@@ -198,6 +205,8 @@ chains_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 seg_bytes, 
 // ---------------------------------------------------------------- K1b: match search
 struct MatchParams {
 	int search, hb, depth, nice;
+	int skip_min;      // positions 2 .. L-1 behind the start of a searched match of length L >= skip_min are not searched
+	int good_len;      // an inherited match at least this long quarters the chain depth (zlib's good_length idea)
 };
 
 __device__ __forceinline__ u32 sm_load4(const u32 *W, u32 o) {
@@ -266,31 +275,31 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 	u32 be_rel = (rel0 / block_bytes + 1) * block_bytes;
 	int prev_len = 0, prev_dist = 0;
 	int run_len = 0, since = 1 << 20;                 // length of / positions since the last searched long match
-	constexpr int SKIP_MIN = 8;
-	// The run's own bytes (16 + 3) and links (16) are read ONCE, with three 128-bit loads and a word, and kept in
-	// registers: inside the run the position's four bytes and its link are the low ends of two 64-bit windows that
-	// slide by a byte / a link per position.  (Read per position they were 3 shared-memory loads at 4- and 8-way bank
+	const int SKIP_MIN = mp.skip_min;
+	// The run's own bytes (16 + 11: every position's first 12 bytes) and links (16) are read ONCE, with four 128-bit
+	// loads, and kept in registers: a position's bytes are funnel shifts of them, its link the low end of a 64-bit
+	// window that slides by a link per position.  (Read per position they were 3 shared-memory loads at 4- and 8-way bank
 	// conflicts -- runs of 16 positions put the lanes 16 bytes apart -- and half of the kernel's shared wavefronts.)
 	const u32 o0 = woff + k0;                        // multiple of 16
-	const uint4 own_w = *(const uint4 *)(W + (o0 >> 2));
-	const u32 own_w4 = W[(o0 >> 2) + 4];
+	const uint4 own_wa = *(const uint4 *)(W + (o0 >> 2)), own_wb = *(const uint4 *)(W + (o0 >> 2) + 4);
 	const uint4 own_pa = *(const uint4 *)(P + o0), own_pb = *(const uint4 *)(P + o0 + 8);
-	const u32 ow[5] = {own_w.x, own_w.y, own_w.z, own_w.w, own_w4};
+	const u32 ow[8] = {own_wa.x, own_wa.y, own_wa.z, own_wa.w, own_wb.x, own_wb.y, own_wb.z, own_wb.w};
 	const u32 pl[8] = {own_pa.x, own_pa.y, own_pa.z, own_pa.w, own_pb.x, own_pb.y, own_pb.z, own_pb.w};
 	uint4 *dst = (uint4 *)(match + ts + k0);        // ts is a multiple of TILE and k0 of RUN: 16-byte aligned; padded past n
 #pragma unroll
 	for (u32 q = 0; q < RUN / 4; q++) {
-	u64 win = (u64)ow[q] | (u64)ow[q + 1] << 32;
 	u64 lwin = (u64)pl[2 * q] | (u64)pl[2 * q + 1] << 32;
 	u32 r0 = 0, r1 = 0, r2 = 0, r3 = 0;
 #pragma unroll 1
-	for (u32 r = 0; r < 4; r++, win >>= 8, lwin >>= 16) {
+	for (u32 r = 0; r < 4; r++, lwin >>= 16) {
 		const u32 j = 4 * q + r;
 		const u32 k = k0 + j;
 		if (k >= n_pos) break;
 		const u32 rel = rel0 + j;                                  // p - cs
 		const u32 o = o0 + j;
-		const u32 cur = (u32)win;
+		// the position's first 12 bytes, from the run's registers
+		const u32 cur = __funnelshift_r(ow[q], ow[q + 1], r * 8), own1 = __funnelshift_r(ow[q + 1], ow[q + 2], r * 8),
+		          own2 = __funnelshift_r(ow[q + 2], ow[q + 3], r * 8);
 		if (rel >= be_rel) be_rel += block_bytes;
 		const int maxlen = (int)min((u32)MAX_MATCH, min(ce_rel, be_rel) - rel);   // runs stop at the block end (Lz77Huffman.java:75)
 		int best_len = 0, best_dist = 0;
@@ -305,15 +314,17 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 			best_len = mp.hb - 1;
 			if (inherit && prev_len > mp.hb) {                     // same source, shifted by one
 				int len = min(prev_len - 1, maxlen);
-				if (len < maxlen) len += sm_match_len(W, o - prev_dist + len, o + len, maxlen - len);
+				// (a match that ended at a mismatch cannot grow when it is shifted; only one cut at 258 can)
+				if (len < maxlen && prev_len >= MAX_MATCH) len += sm_match_len(W, o - prev_dist + len, o + len, maxlen - len);
 				best_len = len;
 				best_dist = prev_dist;
 				if (len >= 32) depth = len >= maxlen ? 0 : 1;       // already good: barely look further
-				// Positions 2 .. L-1 behind the start of a searched match of length L >= SKIP_MIN are only reached by
-				// the parser when it arrives sideways; they keep the inherited match and are not searched again.
-				// (Position 1 is searched: the parser's lazy step compares it with the match before it.)
-				if (since >= 2 && since < run_len) depth = 0;
+				else if (len >= mp.good_len) depth = (depth + 3) >> 2;
 			}
+			// Positions 2 .. L-1 behind the start of a searched match of length L >= SKIP_MIN are only reached by
+			// the parser when it arrives sideways; they keep what they inherit and are not searched.
+			// (Position 1 is searched: the parser's lazy step compares it with the match before it.)
+			if (inherit && since >= 2 && since < run_len) depth = 0;
 			u32 d = (u32)lwin & 0xFFFFu;
 			u32 dist = 0;
 			u32 end_own = 0;                                       // own bytes at best_len - 3 .. best_len, read when best_len changes
@@ -324,18 +335,25 @@ match_kernel(const u8 *__restrict__ in, u64 n, u32 chunk_bytes, u32 block_bytes,
 				const u32 c = o - dist;
 				d = P[c];
 				if ((int)dist == best_dist) continue;
-				// a candidate can only win if it also matches the byte that would make it longer
-				if (best_len >= 4) {
+				// a candidate can only win if it also matches the byte that would make it longer; below 12 bytes the
+				// comparison that follows says so by itself
+				if (best_len >= 12) {
 					if (end_for != best_len) { end_own = sm_load4(W, o + best_len - 3); end_for = best_len; }
 					if (sm_load4(W, c + best_len - 3) != end_own) continue;
 				}
-				if (((sm_load4(W, c) ^ cur) & cmask) == 0) {
-					int len = mp.hb + sm_match_len(W, c + mp.hb, o + mp.hb, maxlen - mp.hb);
-					if (len > best_len) {                          // strict: ties keep the smaller distance (:80)
-						best_len = len;
-						best_dist = (int)dist;
-						if (len >= mp.nice || len >= maxlen) break;
-					}
+				// the candidate's first 12 bytes against the position's, every lane alike: four aligned words, no loop
+				const u32 ci = c >> 2, sc = (c & 3) * 8;
+				const u32 c0 = W[ci], c1 = W[ci + 1], c2 = W[ci + 2], c3 = W[ci + 3];
+				const u32 x0 = __funnelshift_r(c0, c1, sc) ^ cur;
+				if (x0 & cmask) continue;                          // not even the hashed bytes
+				const u32 x1 = __funnelshift_r(c1, c2, sc) ^ own1, x2 = __funnelshift_r(c2, c3, sc) ^ own2;
+				int len = x0 ? 3 : x1 ? 4 + ((__ffs(x1) - 1) >> 3) : x2 ? 8 + ((__ffs(x2) - 1) >> 3) : 12;
+				if (len >= 12 && maxlen > 12) len = 12 + sm_match_len(W, c + 12, o + 12, maxlen - 12);
+				len = min(len, maxlen);
+				if (len > best_len) {                              // strict: ties keep the smaller distance (:80)
+					best_len = len;
+					best_dist = (int)dist;
+					if (len >= mp.nice || len >= maxlen) break;
 				}
 			}
 			if (best_dist == 0) best_len = 0;
@@ -384,8 +402,12 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 	u32 base = 0;
 #define LOADM(k) (base + (k) * 32 + lane < lim ? __ldg(mb + base + (k) * 32 + lane) : 0u)
 	u32 w0 = LOADM(0), w1 = LOADM(1), w2 = LOADM(2), w3 = LOADM(3);    // four windows of 32 positions in flight
-	u32 lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);             // positions of window 0 without a match
-	u32 ntok = 0, nbuf = 0, my_tok = 0, my_idx = 0;
+	u32 ntok = 0;
+	// The parse is a chain -- the position after a token depends on the token -- but only its LINKS are serial: what a
+	// position would emit if the parse came by (a literal, or its match unless the next position's is longer) is
+	// known for all 32 positions of a window at once.  So per window: every lane works out its own step, the warp
+	// follows the chain through the window with one shuffle per match (literal runs are skipped with a bit scan), and
+	// the positions the chain visited write their tokens and count their symbols together.
 	while (i < be) {
 		u32 o = i - base;
 		if (o >= 32) {
@@ -400,39 +422,34 @@ parse_kernel(const u32 *__restrict__ match, u64 n, u32 block_bytes, u32 n_blocks
 				} while (i - base >= 32);
 			}
 			o = i - base;
-			lit0 = __ballot_sync(FULL_MASK, tok_len(w0) == 0);
 		}
-		// a run of positions without a match becomes that many literal tokens in one step
-		u32 run = __ffs(~(lit0 >> o)) - 1;                 // ones from bit o upwards (lit0 >> o has zeros on top)
-		run = min(run, min(32 - o, be - i));
-		if (run) {
-			if (lane >= o && lane < o + run) {
-				tk[ntok + lane - o] = w0 & 0xFF000000u;
-				atomicAdd(&hist[w0 >> 24], 1u);
-			}
-			ntok += run;
-			i += run;
-			continue;
+		const u32 len = tok_len(w0);
+		u32 len_next = __shfl_down_sync(FULL_MASK, len, 1);
+		const u32 len_w1 = __shfl_sync(FULL_MASK, tok_len(w1), 0);
+		if (lane == 31) len_next = len_w1;
+		const u32 p = base + lane;
+		// greedy (Lz77Huffman.java:85-130), or defer to the next position when it matches longer (one-step lazy)
+		const bool take = len != 0 && !(lazy && p + 1 < be && len_next > len);
+		const u32 step = take ? len : 1u;
+		const u32 takemask = __ballot_sync(FULL_MASK, take);
+		const u32 wlim = min(32u, be - base);
+		u32 visited = 0, cur = o;
+		while (cur < wlim) {
+			const u32 ahead = takemask >> cur;                 // literals up to the next position that takes a match
+			const u32 run = min(ahead ? (u32)__ffs(ahead) - 1u : 32u, wlim - cur);
+			visited |= (run >= 32 ? 0xFFFFFFFFu : (1u << run) - 1u) << cur;
+			cur += run;
+			if (cur >= wlim) break;
+			visited |= 1u << cur;
+			cur += __shfl_sync(FULL_MASK, step, cur);
 		}
-		const u32 e = __shfl_sync(FULL_MASK, w0, o);
-		u32 len = tok_len(e);
-		if (lazy) {                                        // defer when the next position matches longer
-			const u32 e1 = __shfl_sync(FULL_MASK, o < 31 ? w0 : w1, (o + 1) & 31);
-			if (i + 1 < be && tok_len(e1) > len) len = 0;
+		i = base + cur;
+		if ((visited >> lane) & 1u) {
+			const u32 tok = take ? w0 : (w0 & 0xFF000000u);
+			tk[ntok + __popc(visited & lanemask_lt())] = tok;
+			hist_token(hist, tok);
 		}
-		// single tokens are parked one per lane and written / counted 32 at a time by all lanes
-		if (lane == nbuf) { my_tok = len ? e : (e & 0xFF000000u); my_idx = ntok; }
-		ntok++;
-		i += len ? len : 1;
-		if (++nbuf == 32) {
-			tk[my_idx] = my_tok;
-			hist_token(hist, my_tok);
-			nbuf = 0;
-		}
-	}
-	if (lane < nbuf) {
-		tk[my_idx] = my_tok;
-		hist_token(hist, my_tok);
+		ntok += __popc(visited);
 	}
 	__syncwarp();
 	BlockRec *rec = &recs[leaf_slot(hp, g)];
@@ -1174,6 +1191,13 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 	mp.hb = p.search == 3 ? 3 : 4;
 	mp.depth = p.search == 3 ? 0x7FFFFFFF : p.depth;
 	mp.nice = MAX_MATCH;
+	mp.skip_min = 6;
+	mp.good_len = 1 << 20;
+	{   // diagnostics for tuning the default search (they change the parse, never the validity of the stream)
+		static const char *e_skip = getenv("B2D_MATCH_SKIP_MIN"), *e_good = getenv("B2D_MATCH_GOOD");
+		if (e_skip && atoi(e_skip) >= 3) mp.skip_min = atoi(e_skip);
+		if (e_good && atoi(e_good) >= 4) mp.good_len = atoi(e_good);
+	}
 	if (need_search) {
 		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3)) {
 			const u32 n_segs = n_chunks * ((p.chunk_bytes + CHAIN_SEG - 1) / CHAIN_SEG);

@@ -44,14 +44,36 @@ def _roundtrip_gpu(b2d, data, opts, chunk):
     return comp, crc, idx
 
 
+def _oracle_sample(oracle, data, comp, idx, chunk, n_sample=64):
+    """A strided sample of the stream's chunks through the ORACLE's decoder (the restated Open.java): status, bytes and
+    consumed input of every sampled chunk.  The last chunk of a stream carries the final marker; the others end in a
+    non-final empty stored block, after which the reference decoder asks for the next block header and reports the end
+    of input -- having delivered the whole chunk."""
+    n_chunks = len(idx)
+    off = np.zeros(n_chunks + 1, np.int64)
+    off[1:] = np.cumsum(idx)
+    picked = sorted(set(list(range(0, n_chunks, max(1, n_chunks // n_sample))) + [n_chunks - 1]))
+    for c in picked:
+        body = comp[int(off[c]):int(off[c + 1])].tobytes()
+        want = data[c * chunk:min(data.size, (c + 1) * chunk)].tobytes()
+        st, out, consumed = oracle.inflate(body, out_cap=len(want) + 8)
+        assert out == want, f"oracle decode of chunk {c} differs"
+        if c == n_chunks - 1:
+            assert st == 0 and consumed == len(body), (c, st, consumed, len(body))
+        else:
+            assert st == 1, (c, st)                        # UNEXPECTED_END_OF_STREAM after the whole chunk: no BFINAL yet
+    return len(picked)
+
+
 @pytest.mark.gpu
-def test_config3_chunked_deflate_1gib(b2d):
+def test_config3_chunked_deflate_1gib(b2d, oracle):
     """configs[2]: 1 GiB G_MIXED, 1 MiB chunks + sync-flush markers + CRC-32."""
     n = 1 << 30
     data = np.concatenate([b2d.corpus("mixed", SEED + k, 64 << 20) for k in range(16)])
     comp, crc, idx = _roundtrip_gpu(b2d, data, b2d.make_opts(), 1 << 20)
     assert crc == zlib.crc32(data.data)
     assert 2.3 < n / comp.size < 3.3
+    assert _oracle_sample(oracle, data, comp, idx, 1 << 20) >= 64
     for c in (0, 333, 1023):                                   # zlib (the java.util.zip.Inflater stand-in) reads chunks alone
         off = int(idx[:c].sum())
         d = zlib.decompressobj(-15)
@@ -59,17 +81,18 @@ def test_config3_chunked_deflate_1gib(b2d):
 
 
 @pytest.mark.gpu
-def test_config2_batch_inflate_4096_members(b2d):
+def test_config2_batch_inflate_4096_members(b2d, oracle):
     """configs[1]: 4096 independent 256 KiB members (here encoded by the GPU encoder, one stream per member)."""
     n, size = 4096, 256 * 1024
     data = np.concatenate([b2d.corpus("text", SEED + 1000 * k, 64 << 20) for k in range(16)])
-    comp, crc, idx = _roundtrip_gpu(b2d, data, b2d.make_opts(chunk_bytes=size, is_last=0), size)
+    comp, crc, idx = _roundtrip_gpu(b2d, data, b2d.make_opts(chunk_bytes=size, is_last=1), size)
     assert len(idx) == n
+    assert _oracle_sample(oracle, data, comp, idx, size) >= 64
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["random", "zeros", "fixed"])
-def test_config5_edge_stress(b2d, kind):
+def test_config5_edge_stress(b2d, oracle, kind):
     """configs[4] at 512 MiB per case: incompressible bytes -> stored blocks, zeros -> 258/distance-1 runs,
     fixed-Huffman-only streams."""
     n = 512 << 20
@@ -88,3 +111,4 @@ def test_config5_edge_stress(b2d, kind):
         for c in range(0, len(idx), 97):                      # every chunk starts with BFINAL=0, BTYPE=01
             assert comp[int(idx[:c].sum())] & 7 == 0b010
     assert crc == zlib.crc32(data.data)
+    assert _oracle_sample(oracle, data, comp, idx, 1 << 20, 32) >= 32

@@ -265,3 +265,28 @@ def test_adaptive_split_small_and_framings(b2d, oracle):
             b2d.deflate_chunks(data, b2d.make_opts(split_min_bytes=bad))
     with pytest.raises(Exception):
         b2d.deflate_chunks(data, b2d.make_opts(split_min_bytes=4096, block_bytes=1 << 17))   # 32 pieces per span
+
+
+@pytest.mark.parametrize("leaf", [4096, 8192, 16384])
+def test_adaptive_split_size_against_the_restated_binarysplit(b2d, oracle, leaf):
+    """Size parity of the GPU's adaptive splitting with the reference's own optimiser at the same minimum block length:
+    BinarySplit(FULL_DYNAMIC, minimumBlockLength = leaf) as restated in the oracle (comp/BinarySplit.java:30-98), run per
+    1 MiB chunk like the GPU stream (history reset per chunk, + the 5-byte chunk marker).  The bar is the north-star's:
+    at most 1 % larger.  (Bytes cannot be compared: different parse, bottom-up instead of top-down decisions.)"""
+    n_chunks, chunk = 4, 1 << 20
+    data = b2d.corpus("mixed", 0xDEF1A7E + 77, n_chunks * chunk).tobytes()
+    comp, crc, idx = b2d.deflate_chunks(data, b2d.make_opts(split_min_bytes=leaf, chunk_bytes=chunk), crc=0)
+    assert _decode_both(oracle, bytes(comp), len(data)) == data
+    ref_total, ref_blocks = 0, 0
+    for c in range(n_chunks):
+        piece = data[c * chunk:(c + 1) * chunk]
+        stream, nb = oracle.deflate_split(piece, (oracle.FULL_DYNAMIC,), min_block_len=leaf)
+        st, out, _ = oracle.inflate(stream, out_cap=chunk + 8)
+        assert st == 0 and out == piece
+        ref_total += len(stream) + 5
+        ref_blocks += nb
+    assert ref_blocks > n_chunks * 16, "the restated BinarySplit did not split anything: the comparison would be empty"
+    assert len(comp) <= 1.01 * ref_total, (leaf, len(comp), ref_total, len(comp) / ref_total)
+    # ... and the unsplit GPU stream against the unsplit reference strategy, for scale
+    plain = b2d.deflate_chunks(data, b2d.make_opts(chunk_bytes=chunk))
+    assert len(comp) < len(plain)

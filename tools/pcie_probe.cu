@@ -52,6 +52,25 @@ __global__ void write_pieces(const uint8_t *__restrict__ src, uint8_t *dst, size
 		done = hi;
 	}
 }
+// The other direction: every warp owns a contiguous region of HOST memory (a member's compressed bytes) and pulls it
+// into device memory front to back, `vecs` 16-byte vectors per lane and fetch (vecs * 512 bytes per warp and fetch),
+// all loads of a fetch issued before the first store; `delay` clock ticks of busy work between fetches stand for the
+// decoding that consumes the bytes.
+__global__ void read_regions(const uint4 *__restrict__ host, uint4 *dev, size_t region16, int vecs, long long delay) {
+	const size_t w = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+	const unsigned lane = threadIdx.x & 31;
+	const size_t base = w * region16;
+	for (size_t i = 0; i < region16; i += 32 * (size_t)vecs) {
+		uint4 v[8];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			if (k < vecs && i + 32 * k + lane < region16) v[k] = host[base + i + 32 * k + lane];
+#pragma unroll
+		for (int k = 0; k < 8; k++)
+			if (k < vecs && i + 32 * k + lane < region16) dev[base + i + 32 * k + lane] = v[k];
+		if (delay) { const long long t0 = clock64(); while (clock64() - t0 < delay) {} }
+	}
+}
 // grid-stride streaming copy
 __global__ void stream_copy(const uint4 *__restrict__ src, uint4 *dst, size_t n16) {
 	for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
@@ -81,6 +100,30 @@ int main() {
 			snprintf(nm, sizeof nm, "%d warps, own region each, 16 B per lane + device copy", warps); report(nm);
 			cudaEventRecord(e0); write_regions_u32<<<warps / 4, 128>>>((const uint32_t *)d, (uint32_t *)h, N / 4 / warps);
 			snprintf(nm, sizeof nm, "%d warps, own region each, 4 B per lane", warps); report(nm);
+		}
+	}
+	// SM reads of pinned host memory (the decoder pulling its own input): 4096 warps, 104 KB each = 416 MiB
+	{
+		const size_t R = 104 * 1024, warps = 4096, NB = R * warps;
+		cudaStream_t s2;
+		CK(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+		CK(cudaMemcpy(h, d, NB, cudaMemcpyDeviceToHost));
+		for (int vecs : {1, 2, 4, 8}) {
+			for (long long delay : {0ll, 20000ll, 200000ll}) {
+				for (int duplex = 0; duplex < 2; duplex++) {
+					if (duplex && delay == 20000) continue;
+					char nm[160];
+					CK(cudaDeviceSynchronize());
+					cudaEventRecord(e0);
+					if (duplex) CK(cudaMemcpyAsync(h + (N / 2), d2, N / 2, cudaMemcpyDeviceToHost, s2));
+					read_regions<<<warps / 4, 128>>>((const uint4 *)h, (uint4 *)d, R / 16, vecs, delay);
+					cudaEventRecord(e1); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+					CK(cudaDeviceSynchronize());
+					snprintf(nm, sizeof nm, "SM reads of host memory: %d B per warp and fetch, delay %lld ticks%s", vecs * 512, delay,
+					         duplex ? ", 512 MiB D2H copy at the same time" : "");
+					printf("%-96s %8.3f ms  %7.2f GB/s\n", nm, ms, NB / ms / 1e6);
+				}
+			}
 		}
 	}
 	CK(cudaDeviceSynchronize());
