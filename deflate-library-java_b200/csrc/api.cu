@@ -294,9 +294,11 @@ uint32_t combine_checksum(const DeflateParams &p, uint32_t acc, uint32_t piece, 
 int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                        const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc,
                        int32_t *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr,
-                       const uint64_t *d_in_end = nullptr, uint32_t *progress = nullptr) {
+                       const uint64_t *d_in_end = nullptr, uint32_t *progress = nullptr, const uint8_t *in_host = nullptr,
+                       const uint32_t *landed = nullptr, uint32_t group_size = 0) {
 	if (n == 0) return B2D_OK;
-	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st, out_mirror, d_in_end, progress));
+	CK(launch_inflate(d_in, d_in_off, n, d_out, d_out_off, d_out_len, d_in_consumed, d_status, flags, st, out_mirror, d_in_end, progress,
+	                  in_host, landed, group_size));
 	if ((flags & B2D_INFLATE_ADLER32) && d_crc) CK(launch_adler32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
 	else if ((flags & B2D_INFLATE_CRC32) && d_crc) CK(launch_crc32_segments(d_out, d_out_off, d_out_len, n, d_crc, st));
 	return B2D_OK;
@@ -304,13 +306,17 @@ int inflate_dev_locked(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n
 
 int deflate_dev_locked(Ctx &g, const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out, uint64_t out_cap,
                        uint64_t *d_total, uint64_t *d_chunk_len, uint32_t *d_chunk_crc, cudaStream_t st,
-                       uint32_t *d_block_bits = nullptr, DevBuf *scratch = nullptr) {
+                       uint32_t *d_block_bits = nullptr, DevBuf *scratch = nullptr, bool overlap_stages = true) {
 	if (!scratch) scratch = &g.scratch;
+	DeflateAux aux;                                               // (one call at a time per context: g.mu is held)
+	aux.stream = g.st[34];
+	for (int i = 0; i < 6; i++) aux.ev[i] = g.ev[24 + i];
 	size_t sb = deflate_scratch_bytes(in_len, p);
 	int r = ensure(*scratch, sb);
 	if (r) return r;
 	if ((r = acquire(*scratch, st))) return r;
-	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, scratch->p, scratch->cap, st, d_block_bits));
+	CK(launch_deflate(d_in, in_len, p, d_out, out_cap, d_total, d_chunk_len, scratch->p, scratch->cap, st, d_block_bits,
+	                  overlap_stages ? &aux : nullptr));
 	if ((r = release(*scratch, st))) return r;
 	if (d_chunk_crc) {
 		uint32_t n_chunks = (uint32_t)((in_len + p.chunk_bytes - 1) / p.chunk_bytes);
@@ -367,19 +373,37 @@ int inflate_host(Ctx &g, const uint8_t *in, const uint64_t *begin, const uint64_
 	if ((in_total && !in) || (out_total && !out)) return B2D_ERR_BAD_ARGUMENT;
 	CK(cudaSetDevice(g.device));
 	int r;
-	if ((r = ensure(g.in, in_total + 64))) return r;
+	if ((r = ensure(g.in, in_total + 64 + 256))) return r;
 	if ((r = ensure(g.out, out_total + 256))) return r;
 	// meta layout (device): in_begin[n] in_end[n] out_off[n+1] | out_len[n] consumed[n] crc[n] status[n]
 	const size_t m_begin = 0, m_end = (size_t)n * 8, m_off_out = m_end + (size_t)n * 8, m_len = m_off_out + (size_t)(n + 1) * 8,
 	             m_cons = m_len + (size_t)n * 8, m_crc = m_cons + (size_t)n * 8, m_stat = m_crc + (size_t)n * 4,
-	             m_total = m_stat + (size_t)n * 4;
-	if ((r = ensure(g.meta, m_total))) return r;
+	             m_total = m_stat + (size_t)n * 4, m_flags = (m_total + 15) & ~(size_t)15;      // + "group landed" words (device only)
+	if ((r = ensure(g.meta, m_flags + 4 * 512))) return r;
 	if ((r = ensure_pinned_meta(g, m_total))) return r;
 	uint8_t *hm = (uint8_t *)g.pinned_meta, *dm = (uint8_t *)g.meta.p;
 	uint64_t *h_begin = (uint64_t *)(hm + m_begin), *h_end = (uint64_t *)(hm + m_end), *h_out_off = (uint64_t *)(hm + m_off_out);
 	for (uint32_t i = 0; i < n; i++) { h_begin[i] = begin[i] - in0; h_end[i] = end[i] - in0; }
 	for (uint32_t i = 0; i <= n; i++) h_out_off[i] = out_off[i] - out0;
 	uint8_t *d_in = (uint8_t *)g.in.p, *d_out = (uint8_t *)g.out.p;
+	// A pinned INPUT buffer is not copied: the decoding warps pull their members' bytes from the mapped host address as
+	// they go (inflate.cu, stage_input), so every member starts at once instead of queueing behind the host-to-device
+	// copy of the bytes in front of it.  B2D_INFLATE_H2D=copy keeps the copy for diagnosis.
+	const uint8_t *in_host = nullptr;
+	bool hybrid = false;                                         // B2D_INFLATE_H2D=hybrid: pull AND copy (see below; slower, kept for diagnosis)
+	if (in_total) {
+		const char *hm_ = getenv("B2D_INFLATE_H2D");
+		hybrid = hm_ && !strcmp(hm_, "hybrid");
+		cudaPointerAttributes pa0, pa1;
+		if (!(hm_ && !strcmp(hm_, "copy")) &&
+		    cudaPointerGetAttributes(&pa0, in + in0) == cudaSuccess && pa0.type == cudaMemoryTypeHost && pa0.devicePointer &&
+		    cudaPointerGetAttributes(&pa1, in + in0 + in_total - 1) == cudaSuccess && pa1.type == cudaMemoryTypeHost &&
+		    (const uint8_t *)pa1.devicePointer - (const uint8_t *)pa0.devicePointer == (ptrdiff_t)(in_total - 1)) {
+			in_host = (const uint8_t *)pa0.devicePointer;
+			d_in += ((uintptr_t)in_host - (uintptr_t)d_in) & 127;       // same 128-byte phase: whole lines map to whole lines
+		}
+		cudaGetLastError();
+	}
 	uint8_t *mirror = nullptr;
 	uint32_t *progress = nullptr;
 	uint64_t slot = 0;                                           // the slots' common size (progress mode)
@@ -410,8 +434,9 @@ int inflate_host(Ctx &g, const uint8_t *in, const uint64_t *begin, const uint64_
 	for (DevBuf *b : {&g.in, &g.out, &g.meta}) if ((r = acquire(*b, g.st[0]))) return r;
 	SyncOnError guard;
 	CK(cudaMemcpyAsync(dm, hm, m_len, cudaMemcpyHostToDevice, g.st[0]));
+	if (hybrid && in_host) CK(cudaMemsetAsync(dm + m_flags, 0, 4 * 512, g.st[0]));
 	CK(cudaEventRecord(g.ev[0], g.st[0]));
-	uint32_t max_slices = 4, min_per = 1024;
+	uint32_t max_slices = 8, min_per = 512;                       // (4096 members: 8 x 512 measured 24.4 ms, 4 x 1024 24.8, 1 x 4096 26.2)
 	if (const char *sl_ = getenv("B2D_INFLATE_SLICES")) {      // diagnostic: "slices[,members per slice at least]"
 		unsigned a_ = 0, b_ = 0;
 		int got = sscanf(sl_, "%u,%u", &a_, &b_);
@@ -420,6 +445,27 @@ int inflate_host(Ctx &g, const uint8_t *in, const uint64_t *begin, const uint64_
 	}
 	uint32_t n_slices = std::min<uint32_t>(max_slices, std::max<uint32_t>(1, n / min_per));
 	uint32_t per = (n + n_slices - 1) / n_slices;
+	// Hybrid (diagnostic): the blob is copied by the copy engine as well, in groups of members on a stream of its own,
+	// and every group raises a flag when it has landed (the warps stop pulling their own input then).  Measured at
+	// 4096 x 256 KiB: the kernels end 1.5 ms earlier, but the extra copy-engine traffic slows the output copies and the
+	// call takes 27.0 ms against 24.4 with the warps pulling everything -- so it is not the default.
+	hybrid = hybrid && in_host;
+	const uint32_t group = hybrid ? std::max<uint32_t>(1, (per + 7) / 8) : 0;            // <= 8 groups per slice
+	if (hybrid) {
+		cudaStream_t sH = g.st[33];
+		CK(cudaStreamWaitEvent(sH, g.ev[0], 0));
+		for (uint32_t a = 0, sl = 0; a < n; a += per, sl++) {
+			const uint32_t b = std::min(n, a + per);
+			uint32_t fl = 8 * sl;                                // slice sl's flags: words 8 sl .. 8 sl + 7
+			for (uint32_t ga = a; ga < b; ga += group, fl++) {
+				const uint32_t gb = std::min(b, ga + group);
+				const uint64_t ia = h_begin[ga], ib = h_end[gb - 1];
+				if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, sH));
+				CK(cudaMemsetAsync(dm + m_flags + 4 * (size_t)fl, 1, 4, sH));
+			}
+		}
+		CK(cudaEventRecord(g.ev[41], sH));
+	}
 	int k = 0;
 	const char *tr_ = getenv("B2D_TRACE");                  // diagnostic: the slices' H2D / kernel / D2H timeline on stderr
 	const bool trace = tr_ != nullptr && tr_[0] == '1';
@@ -432,13 +478,14 @@ int inflate_host(Ctx &g, const uint8_t *in, const uint64_t *begin, const uint64_
 		// (a kernel may read the aligned words around its slice while a neighbour's copy lands in them; those bytes
 		// are shifted out / masked by the bit reader, so the race is benign)
 		if (trace) { for (int q = 0; q < 4; q++) cudaEventCreate(&te[k][q]); cudaEventRecord(te[k][0], st); }
-		if (ib > ia) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
+		if (ib > ia && !in_host) CK(cudaMemcpyAsync(d_in + ia, in + in0 + ia, ib - ia, cudaMemcpyHostToDevice, st));
 		if (trace) cudaEventRecord(te[k][1], st);
 		r = inflate_dev_locked(d_in, (const uint64_t *)(dm + m_begin) + a, b - a, d_out,
 		                       (const uint64_t *)(dm + m_off_out) + a, (uint64_t *)(dm + m_len) + a,
 		                       (uint64_t *)(dm + m_cons) + a, (uint32_t *)(dm + m_crc) + a,
 		                       (int32_t *)(dm + m_stat) + a, flags, st, mirror, (const uint64_t *)(dm + m_end) + a,
-		                       progress ? progress + a : nullptr);
+		                       progress ? progress + a : nullptr, in_host,
+		                       hybrid ? (const uint32_t *)(dm + m_flags) + 8 * (size_t)k : nullptr, group);
 		if (r) return r;
 		if (trace) cudaEventRecord(te[k][2], st);
 		if (ob > oa && !mirror && !progress) CK(cudaMemcpyAsync(out + out0 + oa, d_out + oa, ob - oa, cudaMemcpyDeviceToHost, st));
@@ -496,6 +543,7 @@ int inflate_host(Ctx &g, const uint8_t *in, const uint64_t *begin, const uint64_
 		CK(cudaEventRecord(g.ev[s], g.st[s]));
 		CK(cudaStreamWaitEvent(g.st[0], g.ev[s], 0));
 	}
+	if (hybrid) CK(cudaStreamWaitEvent(g.st[0], g.ev[41], 0));
 	CK(cudaMemcpyAsync(hm + m_len, dm + m_len, m_total - m_len, cudaMemcpyDeviceToHost, g.st[0]));
 	for (DevBuf *b : {&g.in, &g.out, &g.meta}) if ((r = release(*b, g.st[0]))) return r;
 	const auto t_issued = std::chrono::steady_clock::now();
@@ -626,7 +674,8 @@ int deflate_pipelined(Ctx &g, const uint8_t *in, uint64_t in_len, const DeflateP
 		CK(cudaStreamWaitEvent(sB, g.ev[k], 0));
 		r = deflate_dev_locked(g, (const uint8_t *)g.in.p + a, len, ps, (uint8_t *)g.out.p + slice_bound * k, slice_bound,
 		                       (uint64_t *)dmk, (uint64_t *)(dmk + ms_clen), want_crc ? (uint32_t *)(dmk + ms_ccrc) : nullptr, sB,
-		                       block_bits_out ? (uint32_t *)g.bits.p + (size_t)k * per * bpc : nullptr, scr[k & 1]);
+		                       block_bits_out ? (uint32_t *)g.bits.p + (size_t)k * per * bpc : nullptr, scr[k & 1],
+		                       false /* the slices overlap each other already */);
 		if (r) return r;
 		CK(cudaMemcpyAsync(hm + ms_total * k, dmk, ms_total, cudaMemcpyDeviceToHost, sB));
 		CK(cudaEventRecord(g.ev[8 + k], sB));

@@ -1144,7 +1144,8 @@ static bool g_attr_set[MAX_DEVICES] = {};
 
 cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams &p, uint8_t *d_out,
                            uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
-                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits) {
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits,
+                           const DeflateAux *aux) {
 	cudaError_t e;
 	const int slot = current_device_slot();
 	if (!g_attr_set[slot]) {
@@ -1199,17 +1200,48 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 		if (e_good && atoi(e_good) >= 4) mp.good_len = atoi(e_good);
 	}
 	if (need_search) {
-		if (n && (p.search == B2D_SEARCH_DEFAULT || p.search == 3)) {
-			const u32 n_segs = n_chunks * ((p.chunk_bytes + CHAIN_SEG - 1) / CHAIN_SEG);
-			B2D_LAUNCH(chains_kernel, n_segs, 32, 2 << HASH_BITS, st)(d_in, n, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist);
+		// The search stage of chunks [c0, c1) on stream S: links, matches, parse + histograms, codes.  Everything in it is
+		// indexed from the start of the range it is given, so a part of the input is just a smaller input.
+		auto search_part = [&](u64 a, u64 nk, u32 units_k, u32 roots_k, u32 chunks_k, cudaStream_t S, cudaEvent_t match_done) {
+			BlockRec *recs_k = recs + (size_t)(a / p.block_bytes) * hp.H;
+			if (nk && (p.search == B2D_SEARCH_DEFAULT || p.search == 3)) {
+				const u32 n_segs = chunks_k * ((p.chunk_bytes + CHAIN_SEG - 1) / CHAIN_SEG);
+				B2D_LAUNCH(chains_kernel, n_segs, 32, 2 << HASH_BITS, S)(d_in + a, nk, p.chunk_bytes, CHAIN_SEG, mp.hb, prevdist + a);
+			}
+			const u32 n_tiles = (u32)((nk + TILE - 1) / TILE);
+			if (n_tiles) B2D_LAUNCH(match_kernel, n_tiles, MATCH_THREADS, MATCH_SMEM, S)(d_in + a, nk, p.chunk_bytes, unit, mp, prevdist + a, match + a);
+			if (match_done) cudaEventRecord(match_done, S);
+			B2D_LAUNCH(parse_kernel, (units_k + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, S)(
+				match + a, nk, unit, units_k, p.lazy, tokens + a, recs_k, hp);
+			if (hp.K > 1) B2D_LAUNCH(node_hist_kernel, (roots_k + 3) / 4, 128, 0, S)(recs_k, roots_k, nk, hp);
+			if (hp.roots_only) B2D_LAUNCH(huffman_kernel, (roots_k + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, S)(recs_k, roots_k, hp.H, nk, hp);
+			else B2D_LAUNCH(huffman_kernel, (roots_k * hp.H + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, S)(recs_k, roots_k * hp.H, 1, nk, hp);
+		};
+		// chains_kernel is bound by the latency of its serial head-table updates (issue slots half idle, 13 warps per SM),
+		// parse and Huffman construction by instruction issue with little shared memory: a large input is searched in
+		// parts on two streams, part k + 1's links being built under part k's parse and Huffman kernels.  (Not under
+		// its match_kernel: that one needs 197 KB of an SM's shared memory, and chains CTAs that got there first -- 16 KB
+		// and three milliseconds each -- would keep it off the SM.)
+		// A part is one full wave of chains warps (a segment takes its ~3 ms however few of them there are, so smaller
+		// parts would only add up those latencies): 148 SMs x 13 warps x 256 KiB, rounded to 512 MiB.
+		int n_parts = 1;
+		if (aux && p.framing == 0 && p.search == B2D_SEARCH_DEFAULT && n >= (1ull << 30)) n_parts = (int)min((u64)64, n >> 29);
+		if (n_parts == 1) {
+			search_part(0, n, n_blocks, n_roots, n_chunks, st, nullptr);
+		} else {
+			if ((e = cudaEventRecord(aux->ev[0], st)) != cudaSuccess) return e;
+			if ((e = cudaStreamWaitEvent(aux->stream, aux->ev[0], 0)) != cudaSuccess) return e;
+			for (int k = 0; k < n_parts; k++) {
+				cudaStream_t S = (k & 1) ? aux->stream : st;
+				if (k > 0 && (e = cudaStreamWaitEvent(S, aux->ev[1 + ((k - 1) & 3)], 0)) != cudaSuccess) return e;     // match(k - 1) done
+				const u32 c0 = (u32)((u64)n_chunks * k / n_parts), c1 = (u32)((u64)n_chunks * (k + 1) / n_parts);
+				const u64 a = (u64)c0 * p.chunk_bytes, nk = min(n, (u64)c1 * p.chunk_bytes) - a;
+				search_part(a, nk, (u32)((nk + unit - 1) / unit), (u32)((nk + p.block_bytes - 1) / p.block_bytes), c1 - c0, S,
+				            k + 1 < n_parts ? aux->ev[1 + (k & 3)] : nullptr);
+			}
+			if ((e = cudaEventRecord(aux->ev[5], aux->stream)) != cudaSuccess) return e;
+			if ((e = cudaStreamWaitEvent(st, aux->ev[5], 0)) != cudaSuccess) return e;
 		}
-		const u32 n_tiles = (u32)((n + TILE - 1) / TILE);
-		if (n_tiles) B2D_LAUNCH(match_kernel, n_tiles, MATCH_THREADS, MATCH_SMEM, st)(d_in, n, p.chunk_bytes, unit, mp, prevdist, match);
-		B2D_LAUNCH(parse_kernel, (n_blocks + PARSE_WARPS - 1) / PARSE_WARPS, PARSE_WARPS * 32, 0, st)(
-			match, n, unit, n_blocks, p.lazy, tokens, recs, hp);
-		if (hp.K > 1) B2D_LAUNCH(node_hist_kernel, (n_roots + 3) / 4, 128, 0, st)(recs, n_roots, n, hp);
-		if (hp.roots_only) B2D_LAUNCH(huffman_kernel, (n_roots + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st)(recs, n_roots, hp.H, n, hp);
-		else B2D_LAUNCH(huffman_kernel, (n_recs + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, st)(recs, n_recs, 1, n, hp);
 	}
 	if (hp.K > 1) B2D_LAUNCH(split_decide_kernel, (n_roots + 3) / 4, 128, 0, st)(recs, n_roots, n, hp, p.mode);
 	B2D_LAUNCH(layout_kernel, (n_chunks + 127) / 128, 128, 0, st)(recs, n_blocks, n_chunks, n, p.chunk_bytes, unit,

@@ -297,6 +297,14 @@ struct Member {
 	// out + x + mdelta, a mapped host address with the same 128-byte phase, by the decoding warp itself, so no
 	// device-to-host copy follows the kernel (see mirror_progress)
 	long long mdelta;
+	// input streaming (b2d_inflate_batch with a pinned INPUT buffer): the member's compressed bytes are pulled from
+	// the mapped host address (device address + hdelta, same 128-byte phase) into device memory by the decoding warp
+	// itself, a couple of KiB ahead of the bit reader, so every member of the batch starts at once instead of
+	// waiting for a host-to-device copy of the bytes in front of it (see stage_input)
+	long long hdelta;
+	u64 in_len, staged;  // member bytes; how many of them are in device memory already
+	const u32 *landed;   // device word that turns non-zero once the host's own copy of the member's group has landed
+	u32 n_full_total;    // in.n_full once everything is staged (until then in.n_full only covers the staged bytes)
 };
 
 enum { R_EOB = 0, R_SWITCH = 1000 };
@@ -498,6 +506,45 @@ __device__ __forceinline__ void flush_tile(Member &m, const Sm &sm, u32 lane) {
 	if (m.nm) resolve(m, sm, lane);
 	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane, m.mdelta);
 	set_tile_origin(m, out_pos(m));
+}
+
+// Input streaming.  SM loads reach pinned host memory at the PCIe rate when enough of them are in flight
+// (tools/pcie_probe.cu: 51 GB/s with 4096 warps fetching 2 KiB at a time, 45-50 GB/s with decode-sized pauses between
+// the fetches and a device-to-host copy running against them), so the decoder can pull its own input: every warp
+// copies whole 128-byte lines of its member from the host address to the same place in device memory -- four 16-byte
+// loads per lane in flight, then the stores -- and the bit reader only ever sees lines that are complete (in.n_full
+// covers the staged bytes; the fast loop leaves with R_SWITCH when it runs out and the caller stages more).  The
+// lines at a member's ends are shared with its neighbours, who write the same bytes.
+constexpr u32 STAGE_AHEAD = 2048;
+__device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
+	if (upto > m.in_len) upto = m.in_len;
+	if (upto <= m.staged) return;
+	// Behind the warps' backs the host copies the whole blob with the copy engine, group of members after group, and
+	// raises a flag per group: from then on the member is simply there.  The warps only pull what they need before that
+	// (nothing for the first groups, about half of the input for the last).
+	if (m.landed && __shfl_sync(FULL_MASK, *(volatile const u32 *)m.landed, 0) != 0) {
+		m.staged = m.in_len;
+		m.in.n_full = m.n_full_total;
+		return;
+	}
+	const uintptr_t base = (uintptr_t)m.in.words + (m.in.lead8 >> 3);
+	const uintptr_t lo = (base + m.staged) & ~(uintptr_t)127, hi = (base + upto + 127) & ~(uintptr_t)127;
+	for (uintptr_t p = lo + lane * 16; p < hi; p += 2048) {
+		uint4 v[4];
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (p + k * 512 < hi) v[k] = __ldcv((const uint4 *)(p + k * 512 + m.hdelta));
+#pragma unroll
+		for (int k = 0; k < 4; k++)
+			if (p + k * 512 < hi) *(uint4 *)(p + k * 512) = v[k];
+	}
+	// the bit reader loads through the non-coherent path (ld.global.nc), which is not ordered behind these stores: they
+	// have to be performed before any lane reads the lines (none of them has been read, so none is cached, before)
+	__threadfence();
+	__syncwarp();
+	u64 st = hi - base;
+	if (st >= m.in_len) { m.staged = m.in_len; m.in.n_full = m.n_full_total; }
+	else { m.staged = st; m.in.n_full = (u32)(((m.in.lead8 >> 3) + st) >> 2); }
 }
 
 // Decodes symbols of one Huffman block until end-of-block.  Two implementations with identical results:
@@ -839,6 +886,22 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 	return ret;
 }
 
+// The fast decoder over input that may not be staged yet: when it runs out of staged words (R_SWITCH with input left
+// on the host) more is pulled and it goes on.  It returns R_SWITCH only with the whole member in device memory, which
+// is what the checked decoder expects.
+__device__ __noinline__ int decode_block_streamed(Member &m, const Sm &sm, const u32 lane) {
+	for (;;) {
+		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
+		const int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<false>(m, sm, lane) : (int)R_SWITCH;
+		if (r != R_SWITCH || m.staged >= m.in_len) return r;
+		const u64 before = m.staged;
+		stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + STAGE_AHEAD, lane);       // out of staged input: pull more
+		if (m.staged == before) stage_input(m, m.in_len, lane);   // not short of input (the slot is nearly full): the
+		                                                           // checked path takes over, with all input at hand
+		while (m.in.sh >= 32) advance(m.in);                       // the fast loop left its window untouched
+	}
+}
+
 // warp-wide global -> global copy: vector body when source and destination share 16-byte (or 4-byte) phase
 __device__ __noinline__ void copy_global(u8 *dst, const u8 *src, u64 n, u32 lane) {
 	if ((((uintptr_t)src ^ (uintptr_t)dst) & 15) == 0 && n >= 64) {
@@ -876,6 +939,7 @@ __device__ int stored_block(Member &m, const Sm &sm, int &avail, u32 lane) {
 	flush_tile(m, sm, lane);                            // the payload goes global -> global, past the tile
 	u64 pos = out_pos(m);
 	u64 byte_pos = consumed_bits(b) >> 3;
+	if (m.hdelta) stage_input(m, byte_pos + (u64)len + 64, lane);
 	u64 in_len = b.total_bits >> 3;
 	u64 have = in_len - byte_pos;
 	u64 n = (u64)len < have ? (u64)len : have;
@@ -1006,7 +1070,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const u64 *__restrict__ in_end, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
                u64 *__restrict__ out_len, u64 *__restrict__ in_consumed, int *__restrict__ status, u32 flags,
-               long long mdelta, u32 *progress) {
+               long long mdelta, u32 *progress, const u8 *in_host, const u32 *landed, u32 group_size) {
 	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	u32 mi = blockIdx.x * WARPS_PER_CTA + warp;
@@ -1024,6 +1088,14 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	m.in.total_bits = in_len * 8;
 	m.in.n_safe = (u32)((lead + in_len + 3) >> 2);
 	m.in.n_full = (u32)((lead + in_len) >> 2);
+	m.n_full_total = m.in.n_full;
+	m.in_len = in_len;
+	m.hdelta = in_host ? (long long)(in_host - in) : 0;
+	m.staged = in_len;
+	m.landed = landed ? landed + mi / group_size : nullptr;
+	// (the first fetch differs from member to member: members of a batch consume their input at about the same rate, and
+	// fetches that all fall due together would queue up behind each other on the PCIe link, stalling every warp)
+	if (m.hdelta) { m.staged = 0; m.in.n_full = 0; stage_input(m, STAGE_AHEAD / 2 + ((mi * 2654435761u) >> 27) * 128u, lane); }
 	bit_seek(m.in, 0);
 	m.out = out + o0;
 	m.cap = o1 - o0;
@@ -1040,6 +1112,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	bool last = false;
 	const bool chunk_mode = (flags & B2D_INFLATE_CHUNK_INDEXED) != 0;
 	while (!last) {                                                        // Open.read, Open.java:83-110
+		if (m.hdelta) stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + 1024, lane);   // a block header is < 600 bytes
 		norm(m.in);
 		int avail = avail_bits(m.in);
 		if (chunk_mode && avail == 0 && (m.in.sh & 7) == 0) break;         // chunk ends on a block boundary
@@ -1058,8 +1131,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 		#ifdef B2D_FORCE_CAREFUL
 		int r = R_SWITCH;
 #else
-		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<false>(m, sm, lane) : (int)R_SWITCH;
+		int r = decode_block_streamed(m, sm, lane);
 #endif
 		if (r == R_SWITCH) r = decode_block_careful<false>(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
@@ -1117,6 +1189,10 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 	m.gcap = gcap;
 	m.hist_base = bi * block_bytes;
 	m.mdelta = 0;
+	m.hdelta = 0;
+	m.landed = nullptr;
+	m.in_len = m.staged = in_len;
+	m.n_full_total = m.in.n_full;
 	set_tile_origin(m, 0);
 	m.tables = 0;
 
@@ -1260,7 +1336,8 @@ cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st) {
 
 cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out, const u64 *d_out_off,
                            u64 *d_out_len, u64 *d_in_consumed, int *d_status, u32 flags, cudaStream_t st,
-                           uint8_t *out_mirror, const u64 *d_in_end, uint32_t *progress) {
+                           uint8_t *out_mirror, const u64 *d_in_end, uint32_t *progress, const uint8_t *in_host,
+                           const uint32_t *landed, uint32_t group_size) {
 	if (n == 0) return cudaSuccess;
 	static bool attr_set[MAX_DEVICES] = {};
 	const int slot = current_device_slot();
@@ -1274,7 +1351,7 @@ cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out
 	B2D_LAUNCH(inflate_kernel, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len,
 	                                                     d_in_consumed, d_status, flags,
 	                                                     progress ? MDELTA_PROGRESS : out_mirror ? (long long)(out_mirror - d_out) : 0ll,
-	                                                     progress);
+	                                                     progress, in_host, landed, group_size ? group_size : 1u);
 	return cudaGetLastError();
 }
 

@@ -27,7 +27,11 @@ cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st);
 cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
                            int *d_status, uint32_t flags, cudaStream_t st, uint8_t *out_mirror = nullptr,
-                           const uint64_t *d_in_end = nullptr, uint32_t *progress = nullptr);
+                           const uint64_t *d_in_end = nullptr, uint32_t *progress = nullptr,
+                           const uint8_t *in_host = nullptr, const uint32_t *landed = nullptr, uint32_t group_size = 0);
+// in_host (optional): the compressed bytes are NOT in d_in yet but at this mapped host address (byte x of d_in <-> byte x
+// of in_host, (in_host - d_in) % 128 == 0); the decoding warps pull them into d_in themselves as they go, until
+// landed[i / group_size] (optional, device words) turns non-zero: the caller's own copy of member i's group has arrived
 // progress (optional, instead of out_mirror): mapped host words, one per member; member i's word receives the number of
 // whole (1 << INFLATE_PROGRESS_SHIFT)-byte pieces of its output that are final in d_out (0x7FFFFFFF when it is done)
 // d_in_end (optional): member i occupies d_in[d_in_off[i], d_in_end[i]) instead of [d_in_off[i], d_in_off[i + 1])
@@ -71,9 +75,14 @@ struct DeflateParams {
 };
 uint64_t deflate_bound_bytes(uint64_t in_len, uint32_t chunk_bytes, uint32_t block_bytes);
 size_t deflate_scratch_bytes(uint64_t in_len, const DeflateParams &p);
+struct DeflateAux {            // a second stream and six events (timing disabled) the launch may use to overlap its stages
+	cudaStream_t stream;
+	cudaEvent_t ev[6];
+};
 cudaError_t launch_deflate(const uint8_t *d_in, uint64_t in_len, const DeflateParams &p, uint8_t *d_out,
                            uint64_t out_cap, uint64_t *d_out_len_total, uint64_t *d_chunk_out_len,
-                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits = nullptr);
+                           void *d_scratch, size_t scratch_bytes, cudaStream_t st, uint32_t *d_block_bits = nullptr,
+                           const DeflateAux *aux = nullptr);
 // d_block_bits (optional): bit offset of every block inside its chunk's output, one entry per block (the restart index
 // of the block-parallel decoder); only meaningful with chunked framing.
 
