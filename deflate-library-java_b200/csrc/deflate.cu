@@ -1217,15 +1217,17 @@ cudaError_t launch_deflate(const uint8_t *d_in, uint64_t n, const DeflateParams 
 			if (hp.roots_only) B2D_LAUNCH(huffman_kernel, (roots_k + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, S)(recs_k, roots_k, hp.H, nk, hp);
 			else B2D_LAUNCH(huffman_kernel, (roots_k * hp.H + HUFF_WARPS - 1) / HUFF_WARPS, HUFF_WARPS * 32, 0, S)(recs_k, roots_k * hp.H, 1, nk, hp);
 		};
-		// chains_kernel is bound by the latency of its serial head-table updates (issue slots half idle, 13 warps per SM),
-		// parse and Huffman construction by instruction issue with little shared memory: a large input is searched in
-		// parts on two streams, part k + 1's links being built under part k's parse and Huffman kernels.  (Not under
-		// its match_kernel: that one needs 197 KB of an SM's shared memory, and chains CTAs that got there first -- 16 KB
-		// and three milliseconds each -- would keep it off the SM.)
-		// A part is one full wave of chains warps (a segment takes its ~3 ms however few of them there are, so smaller
-		// parts would only add up those latencies): 148 SMs x 13 warps x 256 KiB, rounded to 512 MiB.
+		// Parts (diagnostic, B2D_DEFLATE_PARTS=k): the search stage can run in k parts on two streams, part i + 1's links
+		// being built under part i's parse and Huffman kernels (not under its match_kernel: that one needs 197 KB of an
+		// SM's shared memory, and chains CTAs that got there first -- 16 KB and three milliseconds each -- keep it off
+		// the SM).  Measured on 1 and 2 GiB: no gain (31.0 against 28.5 ms per GiB with two wave-sized parts, far worse
+		// with smaller ones: a chains segment takes its ~3 ms however few of them there are), so one part is the default.
 		int n_parts = 1;
-		if (aux && p.framing == 0 && p.search == B2D_SEARCH_DEFAULT && n >= (1ull << 30)) n_parts = (int)min((u64)64, n >> 29);
+		{
+			static const char *e_parts = getenv("B2D_DEFLATE_PARTS");
+			if (e_parts && aux && p.framing == 0 && p.search == B2D_SEARCH_DEFAULT && atoi(e_parts) > 1 && n_chunks >= (u32)atoi(e_parts))
+				n_parts = min(64, atoi(e_parts));
+		}
 		if (n_parts == 1) {
 			search_part(0, n, n_blocks, n_roots, n_chunks, st, nullptr);
 		} else {
