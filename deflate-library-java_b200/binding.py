@@ -34,7 +34,7 @@ EXPORTS = [
     "b2d_corpus_text", "b2d_corpus_mixed", "b2d_gzip_isize", "b2d_gunzip_batch",
     "b2d_adler32", "b2d_adler32_combine", "b2d_crc32_update", "b2d_adler32_update",
     "b2d_deflate_chunks_indexed", "b2d_deflate_chunks_indexed_dev", "b2d_inflate_chunks", "b2d_inflate_chunks_dev",
-    "b2d_init_devices", "b2d_device_count", "b2d_kernel_launches",
+    "b2d_init_devices", "b2d_device_count", "b2d_kernel_launches", "b2d_inflate_stream", "b2d_inflate_stream_dev",
 ]
 
 
@@ -92,6 +92,10 @@ def lib():
     L.b2d_inflate_batch.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32]
     L.b2d_inflate_batch_dev.restype = i32
     L.b2d_inflate_batch_dev.argtypes = [vp, vp, u32, vp, vp, vp, vp, vp, vp, u32, vp]
+    L.b2d_inflate_stream.restype = i32
+    L.b2d_inflate_stream.argtypes = [vp, u64, vp, u64, vp, vp, vp, vp, u32, vp]
+    L.b2d_inflate_stream_dev.restype = i32
+    L.b2d_inflate_stream_dev.argtypes = [vp, u64, vp, u64, vp, vp]
     L.b2d_gzip_isize.restype = i32
     L.b2d_gzip_isize.argtypes = [vp, vp, u32, vp]
     L.b2d_gunzip_batch.restype = i32
@@ -245,6 +249,19 @@ def inflate_batch_raw(blob, in_off, out_off, flags=0, out=None):
                                 crc.ctypes.data, status.ctypes.data, flags)
     _check(r, "b2d_inflate_batch")
     return out, out_len[:n], in_consumed[:n], crc[:n], status[:n]
+
+
+def inflate_stream(data, out_cap, flags=INFLATE_CRC32):
+    """ONE raw-DEFLATE stream of any origin (speculative parallel decode with a sequential fallback).
+    -> (output bytes, in_consumed, checksum, status, parallel)."""
+    data = _u8(data)
+    out = np.zeros(max(int(out_cap), 1), dtype=np.uint8)
+    out_len, cons = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    crc, st, par = ctypes.c_uint32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+    r = lib().b2d_inflate_stream(data.ctypes.data if data.size else None, data.size, out.ctypes.data, int(out_cap), ctypes.byref(out_len),
+                                 ctypes.byref(cons), ctypes.byref(crc), ctypes.byref(st), flags, ctypes.byref(par))
+    _check(r, "b2d_inflate_stream")
+    return out[:out_len.value], cons.value, crc.value, st.value, par.value
 
 
 def deflate_bound(n, chunk_bytes=0):

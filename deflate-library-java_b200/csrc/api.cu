@@ -904,6 +904,16 @@ int inflate_chunks_host(Ctx &g, const uint8_t *in, const uint64_t *chunk_in_len,
 	return B2D_OK;
 }
 
+// One stream without an index, decoded speculatively in parallel (inflate.cu, "ONE foreign stream"); device pointers.
+int inflate_stream_dev_locked(Ctx &g, const uint8_t *d_in, uint64_t in_len, uint8_t *d_out, uint64_t out_cap, uint64_t *d_result,
+                              cudaStream_t st, uint32_t cap_scale = 1) {
+	int r = ensure(g.scratch2, inflate_stream_scratch_bytes(in_len, cap_scale));
+	if (r) return r;
+	if ((r = acquire(g.scratch2, st))) return r;
+	CK(launch_inflate_stream(d_in, in_len, d_out, out_cap, d_result, g.scratch2.p, st, cap_scale));
+	return release(g.scratch2, st);
+}
+
 int checksum_host(bool adler, const uint8_t *data, uint64_t len, uint32_t *inout) {
 	Ctx *gp = primary();
 	if (!gp) { set_error("b2d_init not called or failed%s%s", "", ""); return B2D_ERR_NO_DEVICE; }
@@ -1238,6 +1248,118 @@ B2D_API int b2d_inflate_chunks(const uint8_t *in, const uint64_t *chunk_in_len, 
 		if (want_sum) chunk_crc32[c] = cr;
 	}
 	return B2D_OK;
+}
+
+// ---------------------------------------------------------------- one stream from any producer, decoded in parallel
+
+// Device pointers: d_in 4-byte aligned and readable to the next 16-byte boundary past in_len; d_result receives five
+// u64 {out_len, in_consumed, status, 0, units}.  status != 0 means "not decodable in parallel, or not valid": decode it
+// with b2d_inflate_batch_dev for the reference's exact outcome.
+B2D_API int b2d_inflate_stream_dev(const uint8_t *d_in, uint64_t in_len, uint8_t *d_out, uint64_t out_cap, uint64_t *d_result, void *stream) {
+	Ctx *gp = ctx_for_pointer(d_out);
+	if (!gp) return B2D_ERR_NO_DEVICE;
+	Ctx &g = *gp;
+	std::lock_guard<std::mutex> lk(g.mu);
+	if (!g.ready) return B2D_ERR_NO_DEVICE;
+	if (!d_in || !d_result || (out_cap && !d_out) || ((uintptr_t)d_in & 3)) return B2D_ERR_BAD_ARGUMENT;
+	CK(cudaSetDevice(g.device));
+	return inflate_stream_dev_locked(g, d_in, in_len, d_out, out_cap, d_result, (cudaStream_t)stream);
+}
+
+// Host pointers.  Replaces InflaterInputStream.read -> Open.read (Open.java:83-110) for ONE raw-DEFLATE stream of any
+// origin: results (bytes, out_len, in_consumed, status) are the sequential decoder's -- when the parallel decode cannot
+// vouch for them the stream is decoded again by b2d_inflate_batch's one-warp decoder.  *parallel (optional) says which.
+B2D_API int b2d_inflate_stream(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                               uint64_t *in_consumed, uint32_t *crc32, int32_t *status, uint32_t flags, int32_t *parallel) {
+	Ctx *gp = primary();
+	if (!gp) return B2D_ERR_NO_DEVICE;
+	Ctx &g = *gp;
+	if ((in_len && !in) || (out_cap && !out) || !out_len || !in_consumed || !status) return B2D_ERR_BAD_ARGUMENT;
+	if ((flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32)) && !crc32) return B2D_ERR_BAD_ARGUMENT;
+	if (parallel) *parallel = 0;
+	bool done = false;
+	const char *off_ = getenv("B2D_STREAM_PARALLEL");
+	if (in_len >= (1u << 20) && !(off_ && off_[0] == '0')) {
+		std::lock_guard<std::mutex> lk(g.mu);
+		if (!g.ready) return B2D_ERR_NO_DEVICE;
+		CK(cudaSetDevice(g.device));
+		int r;
+		if ((r = ensure(g.in, in_len + 64))) return r;
+		if ((r = ensure(g.out, out_cap + 256))) return r;
+		if ((r = ensure(g.meta, 64))) return r;
+		if ((r = ensure_pinned_meta(g, 64 + (size_t)((out_cap >> 20) + 2) * 4))) return r;
+		cudaStream_t st = g.st[0];
+		for (DevBuf *b : {&g.in, &g.out, &g.meta}) if ((r = acquire(*b, st))) return r;
+		SyncOnError guard;
+		const char *tr_ = getenv("B2D_TRACE");
+		const bool trace = tr_ && tr_[0] == '1';
+		const auto t0 = std::chrono::steady_clock::now();
+		auto lap = [&](const char *what) {
+			if (trace) fprintf(stderr, "[b2d trace] inflate_stream: %s at %.3f ms\n", what,
+			                   std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+		};
+		CK(cudaMemcpyAsync(g.in.p, in, in_len, cudaMemcpyHostToDevice, st));
+		// The units' buffers are sized for compression ratios up to ~15 inside a unit; a unit that outgrows its buffer
+		// (long runs, long stretches of stored blocks without a dynamic block to restart at) is given 8 times as much
+		// once, memory permitting, before the stream goes to the sequential decoder.
+		uint64_t res_out = 0, res_cons = 0, res_status = 1;
+		for (uint32_t scale = 1; scale <= 8; scale *= 8) {
+			size_t free_b = 0, total_b = 0;
+			cudaMemGetInfo(&free_b, &total_b);
+			if (inflate_stream_scratch_bytes(in_len, scale) > free_b + g.scratch2.cap - (free_b >> 4)) break;
+			if ((r = inflate_stream_dev_locked(g, (const uint8_t *)g.in.p, in_len, (uint8_t *)g.out.p, out_cap, (uint64_t *)g.meta.p, st, scale))) return r;
+			lap("kernels enqueued");
+			CK(cudaMemcpyAsync(g.pinned_meta, g.meta.p, 40, cudaMemcpyDeviceToHost, st));
+			CK(cudaStreamSynchronize(st));
+			lap("result on the host");
+			res_out = ((const uint64_t *)g.pinned_meta)[0]; res_cons = ((const uint64_t *)g.pinned_meta)[1];
+			res_status = ((const uint64_t *)g.pinned_meta)[2];
+			if ((int64_t)res_status != B2D_ERR_OUTPUT_OVERFLOW || res_out > out_cap) break;
+		}
+		{
+			if (res_status == 0 && res_out <= out_cap) {
+				const uint64_t n = res_out;
+				uint32_t sum = (flags & B2D_INFLATE_ADLER32) ? 1u : 0u;
+				if (n) CK(cudaMemcpyAsync(out, g.out.p, n, cudaMemcpyDeviceToHost, st));
+				if (n && (flags & (B2D_INFLATE_CRC32 | B2D_INFLATE_ADLER32))) {
+					const bool adler = (flags & B2D_INFLATE_ADLER32) != 0;
+					const uint64_t piece = 1u << 20;
+					const uint32_t n_pieces = (uint32_t)((n + piece - 1) / piece);
+					if ((r = ensure(g.crc, (size_t)(n_pieces + 1) * 4))) return r;
+					if ((r = acquire(g.crc, st))) return r;
+					if (adler) CK(launch_adler32_pieces((const uint8_t *)g.out.p, n, piece, n_pieces, (uint32_t *)g.crc.p, st));
+					else CK(launch_crc32_pieces((const uint8_t *)g.out.p, n, piece, n_pieces, (uint32_t *)g.crc.p, st));
+					CK(cudaMemcpyAsync((uint8_t *)g.pinned_meta + 64, g.crc.p, (size_t)n_pieces * 4, cudaMemcpyDeviceToHost, st));
+					if ((r = release(g.crc, st))) return r;
+					CK(cudaStreamSynchronize(st));
+					const uint32_t *pc = (const uint32_t *)((const uint8_t *)g.pinned_meta + 64);
+					for (uint32_t i = 0; i < n_pieces; i++) {
+						const uint64_t l = std::min<uint64_t>(piece, n - (uint64_t)i * piece);
+						sum = adler ? host_adler32_combine(sum, pc[i], l) : host_crc32_combine(sum, pc[i], l);
+					}
+				}
+				*out_len = n;
+				if (crc32) *crc32 = sum;
+				done = true;
+			}
+			for (DevBuf *b : {&g.in, &g.out, &g.meta}) if ((r = release(*b, st))) return r;
+			CK(cudaStreamSynchronize(st));
+			lap("output and checksum on the host");
+			guard.armed = false;
+			if (done) {
+				*in_consumed = res_cons;
+				*status = 0;
+				if (parallel) *parallel = 1;
+			}
+		}
+	}
+	if (done) return B2D_OK;
+	// sequential: one warp, the reference's decoder restated (exact status, bytes delivered before a failure, consumed input)
+	const uint64_t io[2] = {0, in_len}, oo[2] = {0, out_cap};
+	uint32_t c = 0;
+	int r = inflate_host(g, in, io, io + 1, 1, out, oo, out_len, in_consumed, &c, status, flags);
+	if (crc32) *crc32 = c;
+	return r;
 }
 
 // ---------------------------------------------------------------- gzip members

@@ -17,6 +17,7 @@
 // Open.java is kept (first failing check wins).  Not a translation: no dictionary ring (the output buffer plus
 // the staging tile are the window), no code tree, no per-block allocation.
 #include <cstdio>
+#include <cstdlib>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -1278,6 +1279,518 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 		}
 	}
 	if (lane == 0) cstatus[c] = err;
+}
+
+// ---------------------------------------------------------------- ONE foreign stream, decoded in parallel
+// A DEFLATE stream from any producer (system gzip, zlib, the reference's own encoder) has no index: the decoder of
+// Open.java -- and the member decoder above, one warp per stream -- reads it front to back, a few tens of MB/s on one
+// warp.  Here the stream is decoded speculatively instead (the idea of pugz / rapidgzip, rebuilt for the GPU):
+//   find     the compressed bytes are cut into segments; one warp per segment looks for the first bit offset in it
+//            where a dynamic-Huffman block starts: every lane tests a different offset (block type, HLIT/HDIST in
+//            range, code-length code complete), and the survivors get the full header check of Open.java:336-431
+//            (dynamic_header: both codes complete, end-of-block present).
+//   decode   one warp per found start decodes block after block until it stands exactly at another found start (or
+//            has decoded the final block).  It cannot know the 32 KiB in front of it, so -- like phase A of the
+//            block-parallel decoder -- literals go to their places in the unit's own buffer and back-references are
+//            only listed.
+//   replay   the lists are replayed per unit, twice, on two byte planes that begin with a synthetic window: after
+//            that every byte of a unit is either known (plane H zero, plane L the byte) or is "byte j of the unknown
+//            window" (plane H = 0x80 | j >> 8, plane L = j & 0xFF).  Copies of copies sort themselves out for free.
+//   chain    one CTA walks the units in stream order -- a unit must end where the next one starts, otherwise the
+//            start was a false positive and its unit is simply never visited -- sums up the output offsets and
+//            resolves each unit's LAST 32 KiB against the window its predecessor left: the only serial step, 32 KiB
+//            per unit.
+//   finish   every unit resolves all its bytes against its predecessor's window and writes them to the output.
+// Anything unusual (no block start found in a long stretch, a unit that outgrows its buffer, a reference reaching
+// before the start of the stream, a decode error) makes the result say so, and the host entry point decodes the stream
+// again with the sequential decoder, whose status and delivered bytes are the reference's.
+constexpr u64 NO_START = ~0ull;
+constexpr u32 STREAM_END = 0xFFFFFFFFu;
+constexpr u32 STREAM_WINDOW = 32768;
+
+struct StreamUnit {
+	u64 start_bit;       // where a block starts inside the segment (NO_START: none found)
+	u64 end_bit;         // where the unit stopped (a block boundary)
+	u32 out_len;         // bytes it produced
+	u32 n_refs;          // back-references it listed
+	u32 next;            // segment whose start it stopped at; STREAM_END: it decoded the final block
+	int status;
+};
+struct StreamResult {
+	u64 out_len, in_consumed;
+	u64 status;          // 0, or nonzero: decode sequentially for the exact outcome
+	u64 crc;             // filled by the caller's checksum kernel
+	u32 n_live, pad;
+};
+
+__device__ __forceinline__ void stream_bitin(BitIn &b, const u8 *in, u64 in_len, u64 bit) {
+	b.words = (const u32 *)in;                        // `in` is 4-byte aligned
+	b.lead8 = 0;
+	b.total_bits = in_len * 8;
+	b.n_safe = (u32)((in_len + 3) >> 2);
+	b.n_full = (u32)(in_len >> 2);
+	bit_seek(b, bit >> 3);
+	b.sh += (u32)(bit & 7);
+}
+
+// Second stage of the block-start filter, one candidate per LANE (the first stage leaves a few hundred candidates per
+// segment; checking them one at a time with the whole warp -- dynamic_header builds its decode tables -- was most of the
+// kernel): the lane decodes the code-length sequence of its candidate with a canonical decoder of its own and checks
+// what Open.java:336-431 / :705-756 check -- the run lengths fit, end-of-block has a code, the literal/length code
+// is complete, the distance code is complete or one of the two special cases.  `bit` is the block's first header bit.
+__device__ bool header_plausible(const u32 *__restrict__ words, u64 n_words, u64 bit, u64 total_bits) {
+	u64 wi = bit >> 5;
+	u64 buf = 0;
+	int cnt = 0;
+	u64 pos = bit;                                   // bits consumed so far (absolute)
+	auto refill = [&]() {
+		while (cnt <= 32) { buf |= (u64)(wi < n_words ? __ldg(words + wi) : 0u) << cnt; wi++; cnt += 32; }
+	};
+	refill();
+	{ const int skip = (int)(bit & 31); buf >>= skip; cnt -= skip; }
+	auto take = [&](int nb) { refill(); const u32 v = (u32)buf & ((1u << nb) - 1); buf >>= nb; cnt -= nb; pos += nb; return v; };
+	take(3);
+	const u32 n_ll = take(5) + 257, n_d = take(5) + 1, n_cl = take(4) + 4;
+	u8 cl[19];
+#pragma unroll
+	for (int i = 0; i < 19; i++) cl[i] = 0;
+	for (u32 i = 0; i < n_cl; i++) cl[CL_ORDER[i]] = (u8)take(3);
+	// canonical code of the code-length alphabet: symbols by (length, symbol)
+	u8 count[8], sorted[19];
+#pragma unroll
+	for (int l = 0; l < 8; l++) count[l] = 0;
+	for (int i = 0; i < 19; i++) count[cl[i]]++;
+	{
+		u8 offs[8];
+		offs[1] = 0;
+		for (int l = 1; l < 7; l++) offs[l + 1] = offs[l] + count[l];
+		for (int i = 0; i < 19; i++) if (cl[i]) sorted[offs[cl[i]]++] = (u8)i;
+	}
+	const u32 total = n_ll + n_d;
+	u32 kraft_ll = 0, codes_ll = 0, kraft_d = 0, codes_d = 0, ones_d = 0, eob = 0;
+	int prev = -1;
+	for (u32 i = 0; i < total;) {
+		if (pos + 16 > total_bits) return false;
+		refill();
+		int code = 0, first = 0, index = 0, sym = -1;
+		for (int l = 1; l <= 7; l++) {                  // one bit at a time, the code's first bit first
+			code |= (int)(buf & 1);
+			buf >>= 1; cnt--; pos++;
+			const int c = count[l];
+			if (code - c < first) { sym = sorted[index + (code - first)]; break; }
+			index += c;
+			first = (first + c) << 1;
+			code <<= 1;
+		}
+		if (sym < 0) return false;
+		u32 rep = 1;
+		int len = sym;
+		if (sym == 16) { if (prev < 0) return false; len = prev; rep = 3 + take(2); }
+		else if (sym == 17) { len = 0; rep = 3 + take(3); }
+		else if (sym == 18) { len = 0; rep = 11 + take(7); }
+		if (i + rep > total) return false;
+		prev = len;
+		for (u32 r = 0; r < rep; r++, i++) {
+			if (len == 0) continue;
+			if (i < n_ll) { kraft_ll += 32768u >> len; codes_ll++; if (i == 256) eob = 1; }
+			else { kraft_d += 32768u >> len; codes_d++; ones_d += len == 1; }
+		}
+	}
+	if (!eob || codes_ll < 2 || kraft_ll != 32768u) return false;
+	if (codes_d == 0) return n_d == 1;                                  // no distance code at all (Open.java:398-401)
+	if (codes_d == 1) return ones_d == 1;                               // one code of length 1 (:421-425)
+	return kraft_d == 32768u;
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+stream_find_kernel(const u8 *__restrict__ in, u64 in_len, u32 seg_bytes, u32 n_seg, StreamUnit *__restrict__ units) {
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 k = blockIdx.x * WARPS_PER_CTA + warp;
+	if (k >= n_seg) return;
+	const Sm sm = warp_smem(smem_raw, warp);
+	u64 found = k == 0 ? 0 : NO_START;
+	const u64 total_bits = in_len * 8;
+	const u32 *__restrict__ words = (const u32 *)in;
+	const u64 n_words = (in_len + 3) >> 2;
+	const u64 b0 = (u64)k * seg_bytes * 8, b1 = min(total_bits, b0 + (u64)seg_bytes * 8);
+	// Stage 1, a bit offset per lane: block type, HLIT / HDIST in range, code-length code complete.  Its survivors (one
+	// offset in a few hundred) are queued until there are 32 of them, stage 2 (header_plausible) then checks one per
+	// lane, and what survives that -- in practice only true block starts -- is confirmed with the decoder's own header
+	// routine, lowest offset first.
+	u64 my_cand = NO_START;                            // the queued candidate of this lane
+	u32 n_cand = 0;
+	auto flush_candidates = [&]() {
+		const bool good = my_cand != NO_START && header_plausible(words, n_words, my_cand, total_bits);
+		u32 mask = __ballot_sync(FULL_MASK, good);
+		while (mask && found == NO_START) {             // (queued in ascending order: lane 0 holds the lowest offset)
+			const u64 c = __shfl_sync(FULL_MASK, my_cand, __ffs(mask) - 1);
+			mask &= mask - 1;
+			Member m;
+			stream_bitin(m.in, in, in_len, c);
+			m.tables = 0;
+			int avail = avail_bits(m.in), err = 0;
+			(void)getbits(m.in, 1, avail, err);
+			const int type = getbits(m.in, 2, avail, err);
+			if (err == 0 && type == 2 && dynamic_header(m, sm, avail, lane) == 0) found = c;
+			__syncwarp();
+		}
+		my_cand = NO_START;
+		n_cand = 0;
+	};
+	for (u64 base = b0; base < b1 && found == NO_START; base += 32) {
+		const u64 wi = base >> 5;
+		const u32 w0 = wi < n_words ? __ldg(words + wi) : 0u, w1 = wi + 1 < n_words ? __ldg(words + wi + 1) : 0u,
+		          w2 = wi + 2 < n_words ? __ldg(words + wi + 2) : 0u, w3 = wi + 3 < n_words ? __ldg(words + wi + 3) : 0u;
+		// 96 bits from bit offset base + lane
+		const u32 v0 = __funnelshift_r(w0, w1, lane), v1 = __funnelshift_r(w1, w2, lane), v2 = __funnelshift_r(w2, w3, lane);
+		const u64 bit = base + lane;
+		bool ok = bit < b1 && bit + 96 <= total_bits && ((v0 >> 1) & 3) == 2;       // BTYPE = 10 (Open.java:88-98)
+		const u32 hlit = (v0 >> 3) & 31, hdist = (v0 >> 8) & 31, hclen = ((v0 >> 13) & 15) + 4;
+		ok = ok && hlit <= 29 && hdist <= 29;
+		if (ok) {                                          // the code-length code must be complete (Open.java:344, :705-756)
+			const u64 lo = (u64)v0 | (u64)v1 << 32;
+			const u64 f = (lo >> 17) | ((u64)v2 << 47);     // bits 17 .. 80
+			u32 kraft = 0, cnt = 0;
+			for (u32 i = 0; i < hclen; i++) {
+				const u32 l = (u32)(f >> (3 * i)) & 7;
+				kraft += l ? 128u >> l : 0u;
+				cnt += l != 0;
+			}
+			ok = kraft == 128 && cnt >= 2;
+		}
+		u32 mask = __ballot_sync(FULL_MASK, ok);
+		while (mask) {                                     // queue them, lowest offset into the lowest free lane
+			const u32 room = 32 - n_cand, have = (u32)__popc(mask);
+			const u32 takes = min(room, have);
+			// the r-th set bit of mask goes to lane n_cand + r
+			const u32 r = lane - n_cand;                   // which of the new ones this lane would take
+			if (lane >= n_cand && r < takes) {
+				u32 mm = mask;
+				for (u32 q = 0; q < r; q++) mm &= mm - 1;
+				my_cand = base + (u32)(__ffs(mm) - 1);
+			}
+			for (u32 q = 0; q < takes; q++) mask &= mask - 1;
+			n_cand += takes;
+			if (n_cand == 32) { flush_candidates(); if (found != NO_START) break; }
+		}
+	}
+	if (found == NO_START && n_cand) flush_candidates();
+	if (lane == 0) {
+		StreamUnit u;
+		u.start_bit = found; u.end_bit = 0; u.out_len = 0; u.n_refs = 0; u.next = STREAM_END; u.status = 0;
+		units[k] = u;
+	}
+}
+
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
+stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit *units, u8 *planeL, u64 stride, u32 cap,
+                    u64 *__restrict__ glist, u32 gcap) {
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 k = blockIdx.x * WARPS_PER_CTA + warp;
+	if (k >= n_seg) return;
+	const u64 start = units[k].start_bit;
+	if (start == NO_START) return;
+	const Sm sm = warp_smem(smem_raw, warp);
+	Member m;
+	stream_bitin(m.in, in, in_len, start);
+	m.out = planeL + (u64)k * stride + STREAM_WINDOW;
+	m.cap = cap;
+	m.nm = 0;
+	m.glist = glist + (u64)k * gcap;
+	m.gcount = 0;
+	m.gcap = gcap;
+	m.hist_base = k ? STREAM_WINDOW : 0;               // the first unit knows that nothing precedes it (Open.java:592-593)
+	m.mdelta = 0;
+	m.hdelta = 0;
+	m.landed = nullptr;
+	m.in_len = m.staged = in_len;
+	m.n_full_total = m.in.n_full;
+	set_tile_origin(m, 0);
+	m.tables = 0;
+	int err = 0;
+	u32 next = STREAM_END, j = k + 1;
+	bool first = true;
+	for (;;) {
+		norm(m.in);
+		if (!first) {                                  // at a block boundary: does another unit start exactly here?
+			const u64 pos = consumed_bits(m.in);
+			while (j < n_seg) {
+				const u64 sj = units[j].start_bit;
+				if (sj != NO_START && sj >= pos) break;
+				j++;
+			}
+			if (j < n_seg && units[j].start_bit == pos) { next = j; break; }
+		}
+		first = false;
+		int avail = avail_bits(m.in);
+		const bool last = getbits(m.in, 1, avail, err) != 0;
+		const int type = getbits(m.in, 2, avail, err);
+		if (err) break;
+		if (type == 0) {
+			err = stored_block(m, sm, avail, lane);
+			if (err) break;
+		} else {
+			if (type == 3) { err = B2D_RESERVED_BLOCK_TYPE; break; }
+			if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
+			else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
+			norm(m.in);
+			if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
+			int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<true>(m, sm, lane) : (int)R_SWITCH;
+			if (r == R_SWITCH) r = decode_block_careful<true>(m, sm, lane);
+			if (r != R_EOB) { err = r; break; }
+		}
+		if (last) break;                                // next stays STREAM_END
+	}
+	flush_tile(m, sm, lane);
+	if (lane == 0) {
+		units[k].end_bit = consumed_bits(m.in);
+		units[k].out_len = (u32)out_pos(m);
+		units[k].n_refs = m.gcount;
+		units[k].next = next;
+		units[k].status = err;
+	}
+}
+
+// the two planes of every unit: plane H zero over the unit's bytes, and the synthetic windows in front of both
+__global__ void __launch_bounds__(256)
+stream_planes_kernel(const StreamUnit *__restrict__ units, u8 *planeL, u8 *planeH, u64 stride) {
+	const u32 k = blockIdx.x;
+	if (units[k].start_bit == NO_START || units[k].status != 0) return;
+	u8 *L = planeL + (u64)k * stride, *H = planeH + (u64)k * stride;
+	for (u32 i = threadIdx.x; i < STREAM_WINDOW / 4; i += blockDim.x) {
+		const u32 j = 4 * i;                            // window bytes j .. j + 3
+		((u32 *)L)[i] = (j & 0xFF) | ((j + 1) & 0xFF) << 8 | ((j + 2) & 0xFF) << 16 | ((j + 3) & 0xFF) << 24;
+		((u32 *)H)[i] = (0x80u | j >> 8) * 0x01010101u;
+	}
+	const u32 n16 = (units[k].out_len + 15) >> 4;
+	uint4 *h4 = (uint4 *)(H + STREAM_WINDOW);
+	for (u32 i = threadIdx.x; i < n16; i += blockDim.x) h4[i] = make_uint4(0, 0, 0, 0);
+}
+
+// replays a unit's reference list on one plane (blockIdx.y: 0 = L, 1 = H), exactly like resolve_units_kernel
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+stream_replay_kernel(const StreamUnit *__restrict__ units, u32 n_seg, u8 *planeL, u8 *planeH, u64 stride,
+                     const u64 *__restrict__ glist, u32 gcap) {
+	__shared__ ResolveSmem smem[WARPS_PER_CTA];
+	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	const u32 k = blockIdx.x * WARPS_PER_CTA + warp;
+	if (k >= n_seg) return;
+	if (units[k].start_bit == NO_START || units[k].status != 0) return;
+	ResolveSmem *sm = &smem[warp];
+	u8 *ubase = (blockIdx.y ? planeH : planeL) + (u64)k * stride + STREAM_WINDOW;
+	const u64 *list = glist + (u64)k * gcap;
+	const u32 n = units[k].n_refs;
+	for (u32 q = 0; q < n;) {
+		const u64 rec = q + lane < n ? list[q + lane] : 0;
+		const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF, dist = (u32)(rec >> 40);
+		const u32 first = __shfl_sync(FULL_MASK, pos, 0);
+		u8 *g0 = ubase + first;
+		const u32 mis = (u32)((uintptr_t)g0 & 15);
+		const bool fits = q + lane < n && (pos + len - first) + mis <= (u32)UNIT_TILE;
+		const u32 okmask = __ballot_sync(FULL_MASK, fits);
+		const u32 cnt = okmask == 0xFFFFFFFFu ? 32u : (u32)(__ffs(~okmask) - 1);
+		const u32 last_end = __shfl_sync(FULL_MASK, pos + len, cnt - 1);
+		const u32 hi = mis + (last_end - first);
+		u8 *tile_g = g0 - mis;
+		__syncwarp();
+		{
+			const u32 a = (mis + 15) & ~15u, b = hi & ~15u;
+			if (a >= b) {
+				for (u32 i = mis + lane; i < hi; i += 32) sm->tile[i] = tile_g[i];
+			} else {
+				if (mis + lane < a) sm->tile[mis + lane] = tile_g[mis + lane];
+				for (u32 v = (a >> 4) + lane; v < (b >> 4); v += 32) ((uint4 *)sm->tile)[v] = ((const uint4 *)tile_g)[v];
+				if (b + lane < hi) sm->tile[b + lane] = tile_g[b + lane];
+			}
+		}
+		sm->mq[lane] = make_uint2((mis + (pos - first)) | len << 16, dist);
+		resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane, 0);
+		store_tile(sm->tile, tile_g, mis, hi, lane, 0);
+		q += cnt;
+	}
+}
+
+// The chain, part 1: the units in stream order and their output offsets (one warp; the units are read 32 at a time and
+// followed with shuffles, since a unit's successor is nearly always one of the next few segments).
+__global__ void __launch_bounds__(32)
+stream_walk_kernel(const StreamUnit *__restrict__ units, u32 n_seg, u32 *__restrict__ live, u64 *__restrict__ off, u64 out_cap,
+                   StreamResult *res) {
+	const u32 lane = threadIdx.x;
+	u32 k = 0, t = 0, base = 0xFFFFFFFFu;
+	u64 total = 0, prev_end = 0;
+	int status = 0;
+	StreamUnit mine;
+	mine.start_bit = NO_START; mine.end_bit = 0; mine.out_len = 0; mine.n_refs = 0; mine.next = STREAM_END; mine.status = 0;
+	for (;;) {
+		if (k < base || k >= base + 32) {                  // (re)load the batch that starts at k
+			base = k;
+			if (base + lane < n_seg) mine = units[base + lane];
+			else mine.start_bit = NO_START;
+		}
+		const u32 j = k - base;
+		const u64 start = __shfl_sync(FULL_MASK, mine.start_bit, j), end = __shfl_sync(FULL_MASK, mine.end_bit, j);
+		const u32 n = __shfl_sync(FULL_MASK, mine.out_len, j), next = __shfl_sync(FULL_MASK, mine.next, j);
+		const int st = __shfl_sync(FULL_MASK, mine.status, j);
+		if (k >= n_seg || start == NO_START || start != prev_end || t >= n_seg) { status = B2D_ERR_BAD_ARGUMENT; break; }   // the chain is broken
+		if (st != 0) { status = st; break; }
+		if (total + n > out_cap) { status = B2D_ERR_OUTPUT_OVERFLOW; break; }
+		if (lane == 0) { live[t] = k; off[t] = total; }
+		total += n;
+		prev_end = end;
+		t++;
+		if (next == STREAM_END) break;
+		k = next;
+	}
+	if (lane == 0) {
+		off[t] = total;
+		res->n_live = t;
+		res->out_len = total;
+		res->in_consumed = (prev_end + 7) >> 3;            // Open.finish, Open.java:113-124
+		res->status = (u64)(long long)status;
+		res->crc = 0;
+	}
+}
+
+// The chain, part 2.  What unit t leaves behind is a MAP of the window it found to the window it leaves: entry i is a
+// byte (the unit produced it, or copied a known byte there) or "byte j of the window I found" (0x8000 | j: the unit did
+// not reach that far back, or copied it from there).  Maps compose -- (A after B)[i] = A[i] is a reference ? B[A[i]] : A[i]
+// -- and composition is associative, so the windows of ALL units come out of a parallel prefix scan over the maps
+// (Hillis-Steele, log2(units) rounds, every round all units at once) instead of a walk along the stream.
+constexpr u16 MAP_REF = 0x8000;
+__global__ void __launch_bounds__(256)
+stream_maps_kernel(const StreamUnit *__restrict__ units, const u32 *__restrict__ live, const StreamResult *__restrict__ res,
+                   const u8 *__restrict__ planeL, const u8 *__restrict__ planeH, u64 stride, u16 *__restrict__ maps) {
+	const u32 t = blockIdx.x;
+	if (res->status != 0 || t >= res->n_live) return;
+	const u32 k = live[t];
+	const u32 n = units[k].out_len;
+	const u8 *L = planeL + (u64)k * stride + STREAM_WINDOW, *H = planeH + (u64)k * stride + STREAM_WINDOW;
+	u16 *M = maps + (u64)t * STREAM_WINDOW;
+	for (u32 i = blockIdx.y * (STREAM_WINDOW / gridDim.y) + threadIdx.x; i < (blockIdx.y + 1) * (STREAM_WINDOW / gridDim.y); i += blockDim.x) {
+		u16 e;
+		if (i + n >= STREAM_WINDOW) {                      // a byte of this unit
+			const u32 idx = i + n - STREAM_WINDOW;
+			const u32 l = L[idx], h = H[idx];
+			e = (h & 0x80) ? (u16)(MAP_REF | (h & 0x7F) << 8 | l) : (u16)l;
+		} else {
+			e = (u16)(MAP_REF | (i + n));                  // the window it found, moved on by n
+		}
+		M[i] = e;
+	}
+}
+__global__ void __launch_bounds__(256)
+stream_compose_kernel(const u16 *__restrict__ src, u16 *__restrict__ dst, u32 d, const StreamResult *__restrict__ res) {
+	const u32 t = blockIdx.x;
+	if (res->status != 0 || t >= res->n_live) return;
+	const u16 *A = src + (u64)t * STREAM_WINDOW, *B = t >= d ? src + (u64)(t - d) * STREAM_WINDOW : nullptr;
+	u16 *C = dst + (u64)t * STREAM_WINDOW;
+	for (u32 i = blockIdx.y * (STREAM_WINDOW / gridDim.y) + threadIdx.x; i < (blockIdx.y + 1) * (STREAM_WINDOW / gridDim.y); i += blockDim.x) {
+		u16 e = A[i];
+		if (B && (e & MAP_REF)) e = B[e & 0x7FFF];
+		C[i] = e;
+	}
+}
+
+// every live unit: markers resolved against the window its predecessor left, bytes to their place in the output
+__global__ void __launch_bounds__(256)
+stream_finish_kernel(const StreamUnit *__restrict__ units, const u32 *__restrict__ live, const u64 *__restrict__ off,
+                     StreamResult *res, const u8 *__restrict__ planeL, const u8 *__restrict__ planeH, u64 stride,
+                     const u16 *__restrict__ maps, u8 *__restrict__ out) {
+	const u32 t = blockIdx.x;
+	if (res->status != 0 || t >= res->n_live) return;
+	const u32 k = live[t];
+	const u32 n = units[k].out_len;
+	const u64 o = off[t];
+	const u8 *L = planeL + (u64)k * stride + STREAM_WINDOW, *H = planeH + (u64)k * stride + STREAM_WINDOW;
+	const u16 *W = t ? maps + (u64)(t - 1) * STREAM_WINDOW : nullptr;     // the window in front of the unit (after the scan: bytes)
+	bool bad = false;
+	for (u32 i = (blockIdx.y * blockDim.x + threadIdx.x) * 4; i < n; i += gridDim.y * blockDim.x * 4) {
+		const u32 l4 = *(const u32 *)(L + i), h4 = *(const u32 *)(H + i);      // the unit's buffers are 16-byte aligned, padded
+		u32 v4 = l4;
+		if (h4 & 0x80808080u) {
+#pragma unroll
+			for (int b = 0; b < 4; b++) {
+				const u32 h = (h4 >> (8 * b)) & 0xFF;
+				if (h & 0x80) {
+					const u32 mk = (h & 0x7F) << 8 | ((l4 >> (8 * b)) & 0xFF);
+					// window byte mk is stream position o - 32768 + mk: it must exist (Open.java:592-593); what is still
+					// a reference after the scan points in front of the stream
+					const u32 e = W ? W[mk] : MAP_REF;
+					if (e & MAP_REF) { bad |= i + b < n; continue; }
+					v4 = (v4 & ~(0xFFu << (8 * b))) | e << (8 * b);
+				}
+			}
+		}
+		if (i + 4 <= n && ((uintptr_t)(out + o + i) & 3) == 0) *(u32 *)(out + o + i) = v4;
+		else for (u32 b = 0; b < 4 && i + b < n; b++) out[o + i + b] = (u8)(v4 >> (8 * b));
+	}
+	if (bad) atomicMax((unsigned long long *)&res->status, (unsigned long long)B2D_COPY_FROM_BEFORE_DICTIONARY_START);
+}
+
+struct StreamPlan {
+	u32 seg_bytes, n_seg, cap, gcap;
+	u64 stride;
+	size_t o_units, o_planeL, o_planeH, o_glist, o_mapsA, o_mapsB, o_live, o_off, total;
+};
+static StreamPlan stream_plan(uint64_t in_len, uint32_t cap_scale) {
+	StreamPlan p;
+	static const char *e_seg = getenv("B2D_STREAM_SEGMENT"), *e_cap = getenv("B2D_STREAM_UNIT_CAP");
+	p.seg_bytes = e_seg && atoi(e_seg) >= 4096 ? (u32)atoi(e_seg) & ~3u : 32768u;
+	p.stride = e_cap && atoll(e_cap) >= 65536 ? ((u64)atoll(e_cap) + STREAM_WINDOW + 255) & ~(u64)255 : (u64)16 * p.seg_bytes;
+	p.stride *= cap_scale ? cap_scale : 1;
+	p.cap = (u32)min((u64)0xFFFFF0, p.stride - STREAM_WINDOW - 64);
+	p.gcap = p.cap / 3 + 8;
+	p.n_seg = (u32)max((u64)1, (in_len + p.seg_bytes - 1) / p.seg_bytes);
+	size_t o = 0;
+	auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
+	p.o_units = carve((size_t)p.n_seg * sizeof(StreamUnit));
+	p.o_planeL = carve((size_t)p.n_seg * p.stride + 256);
+	p.o_planeH = carve((size_t)p.n_seg * p.stride + 256);
+	p.o_glist = carve((size_t)p.n_seg * p.gcap * 8);
+	p.o_mapsA = carve((size_t)p.n_seg * STREAM_WINDOW * 2);
+	p.o_mapsB = carve((size_t)p.n_seg * STREAM_WINDOW * 2);
+	p.o_live = carve((size_t)p.n_seg * 4);
+	p.o_off = carve((size_t)(p.n_seg + 1) * 8);
+	p.total = o;
+	return p;
+}
+size_t inflate_stream_scratch_bytes(uint64_t in_len, uint32_t cap_scale) { return stream_plan(in_len, cap_scale).total; }
+
+cudaError_t launch_inflate_stream(const u8 *d_in, u64 in_len, u8 *d_out, u64 out_cap, void *d_result, void *d_scratch, cudaStream_t st,
+                                  uint32_t cap_scale) {
+	static bool attr_set[MAX_DEVICES] = {};
+	const int slot = current_device_slot();
+	cudaError_t e;
+	if (!attr_set[slot]) {
+		if ((e = cudaFuncSetAttribute(stream_find_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+		if ((e = cudaFuncSetAttribute(stream_units_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)) != cudaSuccess) return e;
+		attr_set[slot] = true;
+	}
+	const StreamPlan p = stream_plan(in_len, cap_scale);
+	u8 *sp = (u8 *)d_scratch;
+	StreamUnit *units = (StreamUnit *)(sp + p.o_units);
+	u8 *planeL = sp + p.o_planeL, *planeH = sp + p.o_planeH;
+	u64 *glist = (u64 *)(sp + p.o_glist);
+	u16 *mapsA = (u16 *)(sp + p.o_mapsA), *mapsB = (u16 *)(sp + p.o_mapsB);
+	u32 *live = (u32 *)(sp + p.o_live);
+	u64 *off = (u64 *)(sp + p.o_off);
+	StreamResult *res = (StreamResult *)d_result;
+	const u32 wgrid = (p.n_seg + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	B2D_LAUNCH(stream_find_kernel, wgrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.seg_bytes, p.n_seg, units);
+	B2D_LAUNCH(stream_units_kernel, wgrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.n_seg, units, planeL, p.stride, p.cap, glist, p.gcap);
+	B2D_LAUNCH(stream_planes_kernel, p.n_seg, 256, 0, st)(units, planeL, planeH, p.stride);
+	B2D_LAUNCH(stream_replay_kernel, dim3(wgrid, 2), WARPS_PER_CTA * 32, 0, st)(units, p.n_seg, planeL, planeH, p.stride, glist, p.gcap);
+	B2D_LAUNCH(stream_walk_kernel, 1, 32, 0, st)(units, p.n_seg, live, off, out_cap, res);
+	B2D_LAUNCH(stream_maps_kernel, dim3(p.n_seg, 4), 256, 0, st)(units, live, res, planeL, planeH, p.stride, mapsA);
+	u16 *src = mapsA, *dst = mapsB;
+	for (u32 d = 1; d < p.n_seg; d <<= 1) {            // (the number of live units is only known on the device: enough rounds for all)
+		B2D_LAUNCH(stream_compose_kernel, dim3(p.n_seg, 4), 256, 0, st)(src, dst, d, res);
+		u16 *tmp = src; src = dst; dst = tmp;
+	}
+	B2D_LAUNCH(stream_finish_kernel, dim3(p.n_seg, 4), 256, 0, st)(units, live, off, res, planeL, planeH, p.stride, src, d_out);
+	return cudaGetLastError();
 }
 
 size_t inflate_units_scratch_bytes(uint64_t out_total, uint32_t chunk_bytes, uint32_t block_bytes) {

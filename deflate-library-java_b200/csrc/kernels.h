@@ -46,6 +46,14 @@ cudaError_t launch_inflate_units(const uint8_t *d_in, const uint64_t *d_chunk_in
                                  const uint32_t *d_block_bits, uint32_t chunk_bytes, uint32_t block_bytes,
                                  uint64_t out_total, uint8_t *d_out, int *d_chunk_status, void *d_scratch, cudaStream_t st);
 
+// speculative parallel decode of ONE raw-DEFLATE stream without an index (inflate.cu): d_in 4-byte aligned and readable
+// up to 16 bytes past in_len; d_result = 5 x u64 {out_len, in_consumed, status (0 = done, else decode sequentially for
+// the exact outcome), crc (0), n_live}
+// cap_scale: multiplies the units' buffers (default 16 x the segment size: enough for ratios up to ~15 inside a unit)
+size_t inflate_stream_scratch_bytes(uint64_t in_len, uint32_t cap_scale = 1);
+cudaError_t launch_inflate_stream(const uint8_t *d_in, uint64_t in_len, uint8_t *d_out, uint64_t out_cap, void *d_result,
+                                  void *d_scratch, cudaStream_t st, uint32_t cap_scale = 1);
+
 // crc32.cu
 // CRC-32 of n_seg independent segments: segment i = data[off[i], off[i] + len[i])  (len from d_len, u64)
 cudaError_t launch_crc32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,

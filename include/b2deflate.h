@@ -117,6 +117,21 @@ int b2d_inflate_batch_dev(const uint8_t *d_in, const uint64_t *d_in_off, uint32_
                           uint64_t *d_out_len, uint64_t *d_in_consumed, uint32_t *d_crc32, int32_t *d_status,
                           uint32_t flags, void *stream);
 
+/* ---- one stream of any origin, decoded in parallel.  What `new InflaterInputStream(in)` read to the end does for a
+ *      stream nobody indexed (a file made by system gzip, zlib, or the reference's own DeflaterOutputStream): one member on
+ *      one warp is the sequential decoder of Open.java:83-110 at a few tens of MB/s, so the stream is decoded
+ *      speculatively instead -- block starts found by a header-plausibility scan (the checks of Open.java:336-431 are
+ *      the filter), one warp per found start, back-references into the unknown 32 KiB in front of each unit carried as
+ *      markers and resolved along the chain of units (csrc/inflate.cu).  Whenever that cannot vouch for the result --
+ *      an invalid stream, long stretches without a dynamic block, a unit outgrowing its buffer -- the stream is decoded
+ *      again sequentially, so bytes, out_len, in_consumed and status are always the sequential decoder's.
+ *      *parallel (may be NULL) receives 1 if the parallel decode produced the result. ---- */
+int b2d_inflate_stream(const uint8_t *in, uint64_t in_len, uint8_t *out, uint64_t out_cap, uint64_t *out_len,
+                       uint64_t *in_consumed, uint32_t *crc32, int32_t *status, uint32_t flags, int32_t *parallel);
+/* Device pointers (d_in 4-byte aligned, readable to the next 16-byte boundary past in_len).  d_result: five uint64
+ * {out_len, in_consumed, status, 0, units}; status != 0: decode with b2d_inflate_batch_dev for the exact outcome. */
+int b2d_inflate_stream_dev(const uint8_t *d_in, uint64_t in_len, uint8_t *d_out, uint64_t out_cap, uint64_t *d_result, void *stream);
+
 /* ---- gzip members: GzipInputStream.java:38-90 over a batch ---- */
 
 /* ISIZE (mod 2^32) from each member's trailer: the output capacity a caller needs for members below 4 GiB. */
