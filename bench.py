@@ -75,6 +75,8 @@ def parse_args():
     ap.add_argument("--no-deflate", action="store_true", help="skip the deflate leg")
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-edge", action="store_true")
+    ap.add_argument("--no-single-stream", action="store_true")
+    ap.add_argument("--single-stream-mib", type=int, default=256, help="uncompressed MiB of the single-stream leg (rank 0)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -359,6 +361,11 @@ def main():
         torch.cuda.empty_cache()
     if not args.no_edge and args.edge_gib > 0:
         line["config5"] = config5_leg(env, int(args.edge_gib * 1024))
+        torch.cuda.empty_cache()
+    if not args.no_single_stream and args.single_stream_mib > 0:
+        if rank == 0:
+            line["single_stream"] = single_stream_leg(env, args.single_stream_mib)
+        env.barrier()
         torch.cuda.empty_cache()
 
     # ---------------- CPU baseline (rank 0, N = 1) ----------------
@@ -1032,6 +1039,92 @@ def config5_leg(env, total_mib):
     out["note"] = ("per case: device-resident, CUDA events, max over ranks; zeros = literal 0 + (258, distance 1) matches, the decoder's "
                    "pattern-replication path (Open.java:596-603; InflaterInputStreamTest.testFixedHuffmanOverlappingRun1)")
     return out
+
+
+# ------------------------------------------------------------------ ONE foreign stream (InflaterInputStream on a file from system gzip)
+def single_stream_leg(env, mib):
+    """One raw-DEFLATE stream made by zlib level 6 with history carried across blocks -- what `gunzip` of a system-gzip
+    file hands to InflaterInputStream (InflaterInputStream.java:147-164 -> Open.java:83-110), no index, no chunk
+    boundaries -- through b2d_inflate_stream (speculative parallel decode).  Rank 0 only: one stream is one unit."""
+    args, b2d, torch, L, dev = env.args, env.b2d, env.torch, env.L, env.dev
+    n = mib << 20
+    data = fill_corpus(L, "text", np.empty(n, dtype=np.uint8), SEED + 31000, 0, env.pool)
+    t = time.perf_counter()
+    z = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = z.compress(data.data) + z.flush()
+    t_comp = time.perf_counter() - t
+    t = time.perf_counter()
+    assert zlib.crc32(zlib.decompress(comp, -15)) == zlib.crc32(data.data)
+    t_zlib = time.perf_counter() - t
+    m = len(comp)
+    d_in = torch.zeros(m + 64, dtype=torch.uint8, device=dev)
+    d_in[:m] = torch.from_numpy(np.frombuffer(comp, dtype=np.uint8).copy()).to(dev)
+    d_out = torch.zeros(n + 256, dtype=torch.uint8, device=dev)
+    d_res = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def dev_call():
+        r = L.b2d_inflate_stream_dev(d_in.data_ptr(), m, d_out.data_ptr(), n, d_res.data_ptr(), env.sp)
+        assert r == 0, b2d.status_name(r)
+    for _ in range(2):
+        dev_call()
+    torch.cuda.synchronize()
+    res = d_res.cpu().numpy()
+    assert int(res[2]) == 0 and int(res[0]) == n and int(res[1]) == m, "single stream: the parallel decode did not vouch for the result"
+    assert torch.equal(d_out[:n], torch.from_numpy(data).to(dev)), "single stream: output differs"
+    steps = max(3, args.steps // 2)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = L.b2d_kernel_launches()
+    e0.record(env.stream)
+    for _ in range(steps):
+        dev_call()
+    e1.record(env.stream)
+    torch.cuda.synchronize()
+    env.launches += L.b2d_kernel_launches() - l0
+    dev_s = e0.elapsed_time(e1) / 1e3 / steps
+    del d_out, d_in
+    # host pointers (pinned): H2D, decode, CRC-32, D2H inside the call
+    h_in = torch.from_numpy(np.frombuffer(comp, dtype=np.uint8).copy()).pin_memory()
+    h_out = torch.empty(n + 64, dtype=torch.uint8).pin_memory()
+    ol, ic = ctypes.c_uint64(0), ctypes.c_uint64(0)
+    crc, st, par = ctypes.c_uint32(0), ctypes.c_int32(0), ctypes.c_int32(0)
+
+    def host_call():
+        r = L.b2d_inflate_stream(h_in.data_ptr(), m, h_out.data_ptr(), n, ctypes.byref(ol), ctypes.byref(ic), ctypes.byref(crc),
+                                 ctypes.byref(st), b2d.INFLATE_CRC32, ctypes.byref(par))
+        assert r == 0 and st.value == 0 and ol.value == n and ic.value == m
+    host_call()
+    assert crc.value == zlib.crc32(data.data) and par.value == 1 and np.array_equal(h_out.numpy()[:n], data)
+    l0 = L.b2d_kernel_launches()
+    t = time.perf_counter()
+    for _ in range(steps):
+        host_call()
+    host_s = (time.perf_counter() - t) / steps
+    env.launches += L.b2d_kernel_launches() - l0
+    # the one-warp sequential decoder on a 4 MiB prefix-sized stream, for scale (what every foreign stream got before)
+    small = zlib.compressobj(6, zlib.DEFLATED, -15)
+    sm_comp = small.compress(data[:4 << 20].data) + small.flush()
+    os.environ["B2D_STREAM_PARALLEL"] = "0"
+    hs = torch.from_numpy(np.frombuffer(sm_comp, dtype=np.uint8).copy()).pin_memory()
+    t = time.perf_counter()
+    r = L.b2d_inflate_stream(hs.data_ptr(), len(sm_comp), h_out.data_ptr(), 4 << 20, ctypes.byref(ol), ctypes.byref(ic), ctypes.byref(crc),
+                             ctypes.byref(st), b2d.INFLATE_CRC32, ctypes.byref(par))
+    seq_s = time.perf_counter() - t
+    os.environ.pop("B2D_STREAM_PARALLEL", None)
+    assert r == 0 and st.value == 0 and par.value == 0 and ol.value == 4 << 20
+    return {
+        "workload": f"one raw-DEFLATE stream of {mib} MiB G_TEXT made by zlib level 6 (history carried across blocks, no index): "
+                    "InflaterInputStream on a file from system gzip",
+        "value": round(n / dev_s / 1e9, 3), "unit": "GB/s", "ms_per_step": round(dev_s * 1e3, 3),
+        "e2e": {"value": round(n / host_s / 1e9, 3), "unit": "GB/s", "ms_per_step": round(host_s * 1e3, 3),
+                "h2d_bytes_per_step": m, "d2h_bytes_per_step": n + 40 + 4 * (mib + 1)},
+        "compressed_bytes": m, "units_decoded_in_parallel": int(res[4]) & 0xFFFFFFFF,
+        "sequential_one_warp_GBps": round((4 << 20) / seq_s / 1e9, 4),
+        "cpu_zlib_single_thread_GBps": round(n / t_zlib / 1e9, 4),
+        "note": "b2d_inflate_stream[_dev]: block starts found by a header-plausibility scan, one warp per found start, "
+                "back-references into the unknown window as markers, windows by a parallel prefix scan; the sequential decoder "
+                "(one warp, the number next to it) takes over for anything unusual",
+    }
 
 
 def run_reference(args, cores, n_members):

@@ -271,11 +271,12 @@ private:
 		uint64_t cap = sizeHint ? sizeHint : std::max<uint64_t>(1 << 16, (uint64_t)in_len * 6);
 		for (;;) {
 			pout.reserve(cap + 64);
-			uint64_t in_off[2] = {0, in_len}, out_off[2] = {0, cap}, out_len = 0, cons = 0;
+			uint64_t out_len = 0, cons = 0;
 			int32_t st = 0;
-			int rc = b2d_inflate_batch(pin.p, in_off, 1, pout.p, out_off, &out_len, &cons, &crc, &st,
-			                           adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32);
-			if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_batch: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
+			// a stream nobody indexed: speculative parallel decode, sequential decoder behind it for anything unusual
+			int rc = b2d_inflate_stream(pin.p, in_len, pout.p, cap, &out_len, &cons, &crc, &st,
+			                            adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32, nullptr);
+			if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_stream: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
 			if (st == B2D_ERR_OUTPUT_OVERFLOW) {                         // the size is unknown up front: retry larger
 				if (cap > ((uint64_t)1 << 40)) throw IOException("decompressed size exceeds 1 TiB");
 				cap = cap * 2 + (1 << 20);

@@ -40,6 +40,9 @@ public final class B2Deflate {
 	}
 
 	private static final MethodHandle INIT = h("b2d_init", FunctionDescriptor.of(JAVA_INT, JAVA_INT));
+	private static final MethodHandle INIT_DEVICES = h("b2d_init_devices", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_INT));
+	private static final MethodHandle INFLATE_STREAM = h("b2d_inflate_stream", FunctionDescriptor.of(JAVA_INT,
+		ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS));
 	private static final MethodHandle STRERROR = h("b2d_strerror", FunctionDescriptor.of(ADDRESS, JAVA_INT));
 	private static final MethodHandle LAST_ERROR = h("b2d_last_error", FunctionDescriptor.of(ADDRESS));
 	private static final MethodHandle ALLOC_PINNED = h("b2d_alloc_pinned", FunctionDescriptor.of(ADDRESS, JAVA_LONG));
@@ -53,15 +56,30 @@ public final class B2Deflate {
 
 	private static volatile boolean ready;
 
-	/** Binds the process to one GPU; IOException-worthy if there is none (there is no CPU fallback). */
+	/** Binds the process to one GPU -- or, with -Db2deflate.devices=all, to every GPU of the box (the host entry points
+	 *  then shard their units over them) -- IOException-worthy if there is none (there is no CPU fallback). */
 	public static void requireDevice() {
 		if (ready) return;
 		synchronized (B2Deflate.class) {
 			if (ready) return;
-			int rc = call(() -> (int)INIT.invokeExact(Integer.getInteger("b2deflate.device", 0)));
+			final int rc;
+			if ("all".equals(System.getProperty("b2deflate.devices"))) {
+				rc = call(() -> (int)INIT_DEVICES.invokeExact(MemorySegment.NULL, 0));
+			} else {
+				// (invokeExact is signature-polymorphic: the argument has to be a primitive int, not the Integer that
+				// Integer.getInteger returns)
+				final int device = Integer.getInteger("b2deflate.device", 0).intValue();
+				rc = call(() -> (int)INIT.invokeExact(device));
+			}
 			if (rc != 0) throw new IllegalStateException(strerror(rc) + " [" + lastError() + "]");
 			ready = true;
 		}
+	}
+
+	/** One raw-DEFLATE stream of any origin (b2d_inflate_stream): speculative parallel decode, sequential decoder behind it. */
+	public static int inflateStream(MemorySegment in, long inLen, MemorySegment out, long outCap, MemorySegment outLen,
+			MemorySegment inConsumed, MemorySegment crc32, MemorySegment status, int flags) {
+		return call(() -> (int)INFLATE_STREAM.invokeExact(in, inLen, out, outCap, outLen, inConsumed, crc32, status, flags, MemorySegment.NULL));
 	}
 
 	public static String strerror(int status) {
