@@ -42,9 +42,9 @@ import zlib
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# libb2deflate's host pipelines run up to 32 streams side by side; CUDA's default of 8 hardware queues would serialise
+# libb2deflate's host pipelines run a dozen streams side by side; CUDA's default of 8 hardware queues would serialise
 # streams that share one.  Read at context creation, so it has to be in the environment before torch touches CUDA.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "16")
 
 import numpy as np  # noqa: E402
 

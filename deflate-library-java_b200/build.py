@@ -68,7 +68,7 @@ def build_host(force=False):
         exe = os.path.join(bindir, name)
         if force or _stale(exe, [src] + deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wall", "-o", exe, src, "-L" + HERE, "-lb2deflate",
-                                   "-Wl,-rpath,$ORIGIN/.."])
+                                   "-Wl,-rpath,$ORIGIN/..", "-pthread"])
 
 
 if __name__ == "__main__":

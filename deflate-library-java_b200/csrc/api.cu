@@ -195,11 +195,12 @@ int init_ctx(Ctx &g, int device) {
 }
 
 int init_devices_locked(const int *devices, int n) {
-	// The host pipelines keep up to 32 streams busy at once (slices of a batch each decode on their own stream).  CUDA
-	// maps streams onto 8 hardware queues by default and streams that share a queue serialise; the setting is read when
-	// the process creates its first CUDA context, so it only helps if nobody initialised CUDA before us (a harness that
-	// did -- bench.py imports torch first -- sets the variable itself).
-	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+	// The host pipelines keep a dozen streams busy at once (eight slices of a batch each decode on their own stream, next
+	// to the copy streams).  CUDA maps streams onto 8 hardware queues by default and streams that share a queue
+	// serialise; the setting is read when the process creates its first CUDA context, so it only helps if nobody
+	// initialised CUDA before us (a harness that did -- bench.py imports torch first -- sets the variable itself).
+	// (16, not 32: context creation takes 1.2 s with 8 or 16 queues and 2.2 s with 32.)
+	setenv("CUDA_DEVICE_MAX_CONNECTIONS", "16", 0);
 	bool same = n == g_ndev;
 	for (int i = 0; same && i < n; i++) same = g_ctx[i].ready && g_ctx[i].device == devices[i];
 	if (same) return B2D_OK;

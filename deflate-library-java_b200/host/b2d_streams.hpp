@@ -157,8 +157,25 @@ public:
 };
 
 // ---------------------------------------------------------------- device binding
+// B2D_DEVICE=<ordinal> (default 0) binds one GPU; B2D_DEVICES=all or B2D_DEVICES=0,2,3 binds several, and the host entry
+// points then shard chunks / members over them (b2d_init_devices).
+inline int bindDevices() {
+	if (const char *ds = getenv("B2D_DEVICES")) {
+		if (!strcmp(ds, "all")) return b2d_init_devices(nullptr, 0);
+		std::vector<int> v;
+		for (const char *p = ds; *p;) {
+			char *e;
+			long d = strtol(p, &e, 10);
+			if (e == p) break;
+			v.push_back((int)d);
+			p = *e == ',' ? e + 1 : e;
+		}
+		if (!v.empty()) return b2d_init_devices(v.data(), (int)v.size());
+	}
+	return b2d_init(getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0);
+}
 inline void requireDevice() {
-	static int rc = b2d_init(getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0);
+	static int rc = bindDevices();
 	if (rc != B2D_OK) throw IOException(std::string(b2d_strerror(rc)) + " [" + b2d_last_error() + "]");
 }
 
