@@ -745,8 +745,9 @@ def config4_leg(env, total_mib, n_slices=4):
     from importlib import import_module
     sharding = import_module("b2deflate.sharding")
     n_chunks = total_mib
-    if n_chunks < world * n_slices:
-        n_slices = max(1, n_chunks // world)
+    # slices of at least 512 MiB per rank (one full wave of the encoder's chains warps: smaller launches only add up
+    # their latencies), at most four
+    n_slices = max(1, min(n_slices, n_chunks // world // 512))
     bpc = CHUNK_BYTES // BLOCK_BYTES
     ranges = sharding.slice_ranges(n_chunks, rank, world, n_slices)
     my_chunks = sum(hi - lo for lo, hi in ranges)
