@@ -9,8 +9,9 @@ The directory name carries a hyphen (it mirrors the reference repository's name)
 (`b2d_loader.load()` at the repository root does exactly this.)
 
 Contents: csrc/ (CUDA kernels + C-ABI host runtime -> libb2deflate.so), binding.py (ctypes over the C ABI),
-streams.py (host-side mirror of InflaterInputStream / DeflaterOutputStream / Gzip*Stream), java/ (Panama FFM
-sources of the same classes; uncompiled here -- no JDK in the image).
+sharding.py (unit ranges and the gather to rank 0 for torch.distributed runs), host/ (C++ mirror of InflaterInputStream /
+DeflaterOutputStream / Gzip*Stream / Zlib*Stream and of the gzip / gunzip CLIs -> bin/), java/ (Panama FFM sources of the
+same classes; uncompiled here -- no JDK in the image).
 """
 from . import binding  # noqa: F401
 from .binding import *  # noqa: F401,F403

@@ -10,12 +10,14 @@
 //   DeflaterOutputStream.java:119-137 framing                       -> independent chunks joined by empty stored blocks
 //
 // Pipeline (all on one stream, no host round trips):
-//   chains : one warp per block re-inserts the preceding 32 KiB and links every position to the previous
-//            position with the same 15-bit hash (u16 distance per input byte)
+//   chains : one warp per 256 KiB segment of a chunk re-inserts the preceding 32 KiB and links every position to the
+//            previous position with the same 13-bit hash of its next 4 bytes (u16 distance per input byte)
 //   match  : one CTA per 32 KiB tile; the 64 KiB window and its links are staged in shared memory with 128-bit
-//            loads; one thread per position walks the chain (depth-limited) -> (len, dist) per position
-//   parse  : one warp per block walks the positions (greedy or lazy), writes tokens and lit/len + distance
-//            histograms
+//            loads; every thread takes runs of 16 consecutive positions and walks each position's chain
+//            (depth-limited), candidates compared 12 bytes at a time from registers -> (len, dist) per position
+//   parse  : one warp per parse unit (16 KiB piece or block): what every position would emit is worked out for 32
+//            positions at once, the warp follows the greedy / lazy chain through them, the visited positions
+//            write their tokens and count their symbols (lit/len + distance histograms)
 //   huffman: one warp per block: exact package-merge (limit 15 / 7), code-length RLE, header bits, block costs
 //   layout : one thread per chunk picks stored / fixed / dynamic per block and assigns bit offsets;
 //            scan_kernel turns chunk sizes into byte offsets

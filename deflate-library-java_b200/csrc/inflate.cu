@@ -429,8 +429,27 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 	}
 }
 
+// Record mode (block-parallel decode of our own streams, units of a foreign stream: m.glist set): the queued references
+// are not materialised -- their sources may lie in a part of the output another warp is still producing -- but
+// appended to the unit's list in global memory, one record per lane (a coalesced 256-byte store), as
+// (position inside the unit | length << 24 | distance << 40).  The symbol loop is the same in both modes.
+__device__ __noinline__ void drain_records(u64 *glist, u32 gcount, u32 gcap, const uint2 *mq, u32 nm, long long tile_off, u32 lane) {
+	__syncwarp();                                   // queue stores of the symbol loop are visible
+	if (lane < nm && gcount + lane < gcap) {
+		const uint2 q = mq[lane];
+		glist[gcount + lane] = (u64)((long long)(q.x & 0xFFFFu) + tile_off) | (u64)(q.x >> 16) << 24 | (u64)q.y << 40;
+	}
+	__syncwarp();
+}
 __device__ __forceinline__ void resolve(Member &m, const Sm &sm, u32 lane) {
-	resolve_pending(sm->tile, sm.mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
+	if (m.glist) {
+		// tile address -> position inside the unit: - (window address of tile[0]) + (unit offset of tile[0])
+		drain_records(m.glist, m.gcount, m.gcap, sm.mq, m.nm,
+		              (long long)(m.tile_g - m.out) - (long long)(u32)__cvta_generic_to_shared(sm->tile), lane);
+		m.gcount += m.nm;                           // (beyond gcap nothing was stored; the kernels report the overflow)
+	} else {
+		resolve_pending(sm->tile, sm.mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
+	}
 	m.nm = 0;
 }
 
@@ -560,7 +579,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 //    last <= 12 bytes of a member and when the member's output slot is nearly full.
 enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 
-template <bool DEFER>
 __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
 	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;     // sh < 32, widx + 3 <= n_full
@@ -577,14 +595,10 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 	                                                 // full when the next slot's address wraps to 0 mod 256)
 	const u32 fast_last = b.n_full - 3;
 	const u32 *const words = b.words;
-	u64 *gp = DEFER ? m.glist + m.gcount : nullptr;  // DEFER: next free record, end of the list, unit offset of tile[0]
-	u64 *const gend = DEFER ? m.glist + m.gcap : nullptr;
-	u32 ubase = DEFER ? (u32)(m.tile_g - m.out) - tile_s : 0;
 #define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = widx; b.sh = sh; m.tpos = tp - tile_s; \
-                          m.nm = (qp - mq_s) >> 3; if (DEFER) m.gcount = (u32)(gp - m.glist); } while (0)
+                          m.nm = (qp - mq_s) >> 3; } while (0)
 #define LOAD_TILE() do { tp = tile_s + m.tpos; tend = tile_s + m.tlimit; qp = mq_s + m.nm * 8; \
-                         pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; \
-                         if (DEFER) ubase = (u32)(m.tile_g - m.out) - tile_s; } while (0)
+                         pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; } while (0)
 	// LUT entry addresses: (bits << 2) masked and OR-ed into the aligned table address
 #define LL_AT(bits) lds_u32(llb | (((bits) << 2) & ((4u << LL_TB) - 4)))
 #define DL_AT(bits) lds_u32(quarter(llb) | (((bits) << 2) & ((4u << D_TB) - 4)))
@@ -632,14 +646,9 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			const int dmax = pos_off + (int)tp;
 			tp += qx >> 16;
 			if ((int)dist > dmax || (int)tp > tguard) { len = qx >> 16; ev = EV_SLOWMATCH; break; }
-			if (DEFER) {                                     // record only: (unit-relative position, length, distance)
-				if (gp >= gend) { len = qx >> 16; ev = EV_SLOWMATCH; break; }
-				*gp++ = (u64)(ubase + (qx & 0xFFFF)) | (u64)(qx >> 16) << 24 | (u64)dist << 40;
-			} else {
-				sts_v2(qp, qx, dist);                        // same value from every lane: one broadcast write
-				qp += 8;
-				if ((qp & 0xFF) == 0) { ev = EV_QFULL; break; }
-			}
+			sts_v2(qp, qx, dist);                            // same value from every lane: one broadcast write
+			qp += 8;
+			if ((qp & 0xFF) == 0) { ev = EV_QFULL; break; }
 			NEXT_SYMBOL();
 		}
 		// ---- events
@@ -684,17 +693,12 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 				const u32 fit = tend - tp;
 				const u32 take = len < fit ? len : fit;
 				if (take) {
-					if (DEFER) {
-						if (gp >= gend) { SAVE_STATE(); return B2D_ERR_OUTPUT_OVERFLOW; }
-						*gp++ = (u64)(ubase + tp) | (u64)take << 24 | (u64)dist << 40;
-					} else {
-						sts_v2(qp, tp | take << 16, dist);
-						qp += 8;
-					}
+					sts_v2(qp, tp | take << 16, dist);
+					qp += 8;
 					tp += take;
 					len -= take;
 				}
-				if (len == 0 && (DEFER || (qp & 0xFF) != 0)) break;
+				if (len == 0 && (qp & 0xFF) != 0) break;
 				SAVE_STATE();
 				if (len == 0) { resolve(m, sm, lane); qp = mq_s; break; }
 				flush_tile(m, sm, lane);
@@ -729,7 +733,6 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 #undef DL_AT
 }
 
-template <bool DEFER>
 __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
 	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;
@@ -831,13 +834,6 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 		sh += d & 31;
 		// common case: the source exists (Open.java:592-593) and the whole reference fits the tile
 		if ((int)dist <= pos_base + (int)tpos && (int)(tpos + len) <= (CAREFUL ? (int)tlimit : tguard)) {
-			if (DEFER) {                                     // record only: (unit-relative position, length, distance)
-				if (m.gcount >= m.gcap) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
-				const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
-				m.glist[m.gcount++] = upos | (u64)len << 24 | (u64)dist << 40;
-				tpos += len;
-				continue;
-			}
 			sm.mq[nm] = make_uint2(tile_s + tpos + (len << 16), dist);   // same value from every lane: one broadcast write
 			tpos += len;
 			if (++nm == 32) {
@@ -855,14 +851,8 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 			const u32 fit = tlimit - tpos;
 			const u32 take = len < fit ? len : fit;
 			if (take) {
-				if (DEFER) {
-					if (m.gcount >= m.gcap) { ret = B2D_ERR_OUTPUT_OVERFLOW; break; }
-					const u64 upos = (u64)((long long)(m.tile_g - m.out) + (long long)tpos);
-					m.glist[m.gcount++] = upos | (u64)take << 24 | (u64)dist << 40;
-				} else {
-					if (lane == 0) sm.mq[nm] = make_uint2((tile_s + tpos) | take << 16, dist);
-					nm++;
-				}
+				if (lane == 0) sm.mq[nm] = make_uint2((tile_s + tpos) | take << 16, dist);
+				nm++;
 				tpos += take;
 				len -= take;
 			}
@@ -889,11 +879,13 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 
 // The fast decoder over input that may not be staged yet: when it runs out of staged words (R_SWITCH with input left
 // on the host) more is pulled and it goes on.  It returns R_SWITCH only with the whole member in device memory, which
-// is what the checked decoder expects.
+// is what the checked decoder expects.  Every kernel calls the symbol loop through this thin function, streaming or
+// not: ptxas allocates registers across calls, and called straight from a kernel body with its dozens of live values
+// the loop's clone keeps its table address and window limit in local memory (7 LDL per trip instead of 1).
 __device__ __noinline__ int decode_block_streamed(Member &m, const Sm &sm, const u32 lane) {
 	for (;;) {
 		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		const int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<false>(m, sm, lane) : (int)R_SWITCH;
+		const int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast(m, sm, lane) : (int)R_SWITCH;
 		if (r != R_SWITCH || m.staged >= m.in_len) return r;
 		const u64 before = m.staged;
 		stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + STAGE_AHEAD, lane);       // out of staged input: pull more
@@ -1134,7 +1126,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 #else
 		int r = decode_block_streamed(m, sm, lane);
 #endif
-		if (r == R_SWITCH) r = decode_block_careful<false>(m, sm, lane);
+		if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);                                               // also resolves what is pending
@@ -1213,14 +1205,13 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 		if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
 		norm(m.in);
-		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-		int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<true>(m, sm, lane) : (int)R_SWITCH;
-		if (r == R_SWITCH) r = decode_block_careful<true>(m, sm, lane);
+		int r = decode_block_streamed(m, sm, lane);         // (through the same thin wrapper as the member decoder: see there)
+		if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);
-	if (err == 0 && out_pos(m) != expect) err = B2D_ERR_OUTPUT_OVERFLOW;
-	if (lane == 0) { gcount[u] = m.gcount; ustatus[u] = err; }
+	if (err == 0 && (out_pos(m) != expect || m.gcount > m.gcap)) err = B2D_ERR_OUTPUT_OVERFLOW;
+	if (lane == 0) { gcount[u] = min(m.gcount, m.gcap); ustatus[u] = err; }
 }
 
 struct ResolveSmem {
@@ -1536,9 +1527,8 @@ stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit
 			if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 			else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
 			norm(m.in);
-			if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
-			int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast<true>(m, sm, lane) : (int)R_SWITCH;
-			if (r == R_SWITCH) r = decode_block_careful<true>(m, sm, lane);
+			int r = decode_block_streamed(m, sm, lane);     // (through the same thin wrapper as the member decoder: see there)
+			if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 			if (r != R_EOB) { err = r; break; }
 		}
 		if (last) break;                                // next stays STREAM_END
@@ -1547,9 +1537,9 @@ stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit
 	if (lane == 0) {
 		units[k].end_bit = consumed_bits(m.in);
 		units[k].out_len = (u32)out_pos(m);
-		units[k].n_refs = m.gcount;
+		units[k].n_refs = min(m.gcount, m.gcap);
 		units[k].next = next;
-		units[k].status = err;
+		units[k].status = err == 0 && m.gcount > m.gcap ? B2D_ERR_OUTPUT_OVERFLOW : err;
 	}
 }
 

@@ -27,8 +27,11 @@ def _sass(kernel):
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(OBJ), reason="needs the built object and cuobjdump")
-def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic():
-    sass = _sass("14inflate_kernel")
+@pytest.mark.parametrize("kernel", ["14inflate_kernel", "20inflate_units_kernel", "19stream_units_kernel"])
+def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
+    """Every kernel carries its own clone of the symbol loop (member decoder, block-parallel decoder of our own streams,
+    units of a foreign stream), allocated in that kernel's context: all three are checked."""
+    sass = _sass(kernel)
     # the literal path: `sh += e >> 27` is the only LEA.HI with a 5-bit shift; the loop body follows it
     hits = [i for i, ins in enumerate(sass) if re.match(r"LEA\.HI R\d+, R\d+, R\d+, RZ, 0x5$", ins)]
     assert hits, "symbol loop not found"
