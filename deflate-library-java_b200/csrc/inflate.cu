@@ -879,13 +879,17 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 
 // The fast decoder over input that may not be staged yet: when it runs out of staged words (R_SWITCH with input left
 // on the host) more is pulled and it goes on.  It returns R_SWITCH only with the whole member in device memory, which
-// is what the checked decoder expects.  Every kernel calls the symbol loop through this thin function, streaming or
-// not: ptxas allocates registers across calls, and called straight from a kernel body with its dozens of live values
-// the loop's clone keeps its table address and window limit in local memory (7 LDL per trip instead of 1).
+// is what the checked decoder expects.  The unit decoders call the symbol loop through this thin function too: ptxas
+// allocates registers across calls, and called straight from THEIR kernel bodies with dozens of live values the loop's
+// clone keeps its table address and window limit in local memory (7 LDL per trip instead of 1).  (The plain member
+// decoder is the exception: there the direct call gives the clean loop, the wrapper one LDL on the refill path that
+// costs 4 % -- tests/test_sass_hot_loop.py checks every clone.)
+template <bool STREAM>
 __device__ __noinline__ int decode_block_streamed(Member &m, const Sm &sm, const u32 lane) {
 	for (;;) {
 		if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
 		const int r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast(m, sm, lane) : (int)R_SWITCH;
+		if (!STREAM) return r;
 		if (r != R_SWITCH || m.staged >= m.in_len) return r;
 		const u64 before = m.staged;
 		stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + STAGE_AHEAD, lane);       // out of staged input: pull more
@@ -919,6 +923,7 @@ __device__ __noinline__ void copy_global(u8 *dst, const u8 *src, u64 n, u32 lane
 }
 
 // Open.UncompressedBlock (Open.java:227-306)
+template <bool STREAM>
 __device__ int stored_block(Member &m, const Sm &sm, int &avail, u32 lane) {
 	BitIn &b = m.in;
 	int err = 0;
@@ -932,7 +937,7 @@ __device__ int stored_block(Member &m, const Sm &sm, int &avail, u32 lane) {
 	flush_tile(m, sm, lane);                            // the payload goes global -> global, past the tile
 	u64 pos = out_pos(m);
 	u64 byte_pos = consumed_bits(b) >> 3;
-	if (m.hdelta) stage_input(m, byte_pos + (u64)len + 64, lane);
+	if (STREAM && m.hdelta) stage_input(m, byte_pos + (u64)len + 64, lane);
 	u64 in_len = b.total_bits >> 3;
 	u64 have = in_len - byte_pos;
 	u64 n = (u64)len < have ? (u64)len : have;
@@ -1059,6 +1064,9 @@ __device__ void fixed_tables(Member &m, const Sm &sm, u32 lane) {
 	m.tables = 1;
 }
 
+// STREAM: the host entry point's variant for a pinned input buffer (the warps pull their input, see stage_input); the
+// device-resident path runs the instantiation without any of it.
+template <bool STREAM>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
 inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const u64 *__restrict__ in_end, u32 n_members,
                u8 *out, const u64 *__restrict__ out_off,
@@ -1083,12 +1091,12 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	m.in.n_full = (u32)((lead + in_len) >> 2);
 	m.n_full_total = m.in.n_full;
 	m.in_len = in_len;
-	m.hdelta = in_host ? (long long)(in_host - in) : 0;
+	m.hdelta = STREAM && in_host ? (long long)(in_host - in) : 0;
 	m.staged = in_len;
-	m.landed = landed ? landed + mi / group_size : nullptr;
+	m.landed = STREAM && landed ? landed + mi / group_size : nullptr;
 	// (the first fetch differs from member to member: members of a batch consume their input at about the same rate, and
 	// fetches that all fall due together would queue up behind each other on the PCIe link, stalling every warp)
-	if (m.hdelta) { m.staged = 0; m.in.n_full = 0; stage_input(m, STAGE_AHEAD / 2 + ((mi * 2654435761u) >> 27) * 128u, lane); }
+	if (STREAM && m.hdelta) { m.staged = 0; m.in.n_full = 0; stage_input(m, STAGE_AHEAD / 2 + ((mi * 2654435761u) >> 27) * 128u, lane); }
 	bit_seek(m.in, 0);
 	m.out = out + o0;
 	m.cap = o1 - o0;
@@ -1105,7 +1113,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	bool last = false;
 	const bool chunk_mode = (flags & B2D_INFLATE_CHUNK_INDEXED) != 0;
 	while (!last) {                                                        // Open.read, Open.java:83-110
-		if (m.hdelta) stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + 1024, lane);   // a block header is < 600 bytes
+		if (STREAM && m.hdelta) stage_input(m, ((consumed_bits(m.in) + 7) >> 3) + 1024, lane);   // a block header is < 600 bytes
 		norm(m.in);
 		int avail = avail_bits(m.in);
 		if (chunk_mode && avail == 0 && (m.in.sh & 7) == 0) break;         // chunk ends on a block boundary
@@ -1113,7 +1121,7 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 		int type = getbits(m.in, 2, avail, err);
 		if (err) break;
 		if (type == 0) {
-			err = stored_block(m, sm, avail, lane);
+			err = stored_block<STREAM>(m, sm, avail, lane);
 			if (err) break;
 			continue;
 		}
@@ -1124,7 +1132,12 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 		#ifdef B2D_FORCE_CAREFUL
 		int r = R_SWITCH;
 #else
-		int r = decode_block_streamed(m, sm, lane);
+		int r;
+		if (STREAM) r = decode_block_streamed<true>(m, sm, lane);
+		else {             // (called straight from here, this kernel's clone of the loop is the one without any local-memory access)
+			if (m.tpos + LIT_GUARD > m.tlimit) flush_tile(m, sm, lane);
+			r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast(m, sm, lane) : (int)R_SWITCH;
+		}
 #endif
 		if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
@@ -1197,7 +1210,7 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 		int type = getbits(m.in, 2, avail, err);
 		if (err) break;
 		if (type == 0) {
-			err = stored_block(m, sm, avail, lane);
+			err = stored_block<false>(m, sm, avail, lane);
 			if (err) break;
 			continue;
 		}
@@ -1205,7 +1218,7 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 		if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
 		norm(m.in);
-		int r = decode_block_streamed(m, sm, lane);         // (through the same thin wrapper as the member decoder: see there)
+		int r = decode_block_streamed<false>(m, sm, lane);  // (through the same thin wrapper as the member decoder: see there)
 		if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 		if (r != R_EOB) { err = r; break; }
 	}
@@ -1520,14 +1533,14 @@ stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit
 		const int type = getbits(m.in, 2, avail, err);
 		if (err) break;
 		if (type == 0) {
-			err = stored_block(m, sm, avail, lane);
+			err = stored_block<false>(m, sm, avail, lane);
 			if (err) break;
 		} else {
 			if (type == 3) { err = B2D_RESERVED_BLOCK_TYPE; break; }
 			if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 			else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
 			norm(m.in);
-			int r = decode_block_streamed(m, sm, lane);     // (through the same thin wrapper as the member decoder: see there)
+			int r = decode_block_streamed<false>(m, sm, lane);   // (through the same thin wrapper as the member decoder: see there)
 			if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
 			if (r != R_EOB) { err = r; break; }
 		}
@@ -1845,16 +1858,19 @@ cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out
 	static bool attr_set[MAX_DEVICES] = {};
 	const int slot = current_device_slot();
 	if (!attr_set[slot]) {
-		cudaError_t e = cudaFuncSetAttribute(inflate_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-		                                     cudaSharedmemCarveoutMaxShared);
+		cudaError_t e = cudaFuncSetAttribute(inflate_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(inflate_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 		if (e != cudaSuccess) return e;
 		attr_set[slot] = true;
 	}
 	u32 grid = (n + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	B2D_LAUNCH(inflate_kernel, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len,
-	                                                     d_in_consumed, d_status, flags,
-	                                                     progress ? MDELTA_PROGRESS : out_mirror ? (long long)(out_mirror - d_out) : 0ll,
-	                                                     progress, in_host, landed, group_size ? group_size : 1u);
+	const long long mdelta = progress ? MDELTA_PROGRESS : out_mirror ? (long long)(out_mirror - d_out) : 0ll;
+	if (in_host)
+		B2D_LAUNCH(inflate_kernel<true>, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len, d_in_consumed,
+		                                                                  d_status, flags, mdelta, progress, in_host, landed, group_size ? group_size : 1u);
+	else
+		B2D_LAUNCH(inflate_kernel<false>, grid, WARPS_PER_CTA * 32, 0, st)(d_in, d_in_off, d_in_end, n, d_out, d_out_off, d_out_len, d_in_consumed,
+		                                                                   d_status, flags, mdelta, progress, nullptr, nullptr, 1u);
 	return cudaGetLastError();
 }
 

@@ -27,10 +27,10 @@ def _sass(kernel):
 
 
 @pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(OBJ), reason="needs the built object and cuobjdump")
-@pytest.mark.parametrize("kernel", ["14inflate_kernel", "20inflate_units_kernel", "19stream_units_kernel"])
+@pytest.mark.parametrize("kernel", ["14inflate_kernelILb0E", "14inflate_kernelILb1E", "20inflate_units_kernel", "19stream_units_kernel"])
 def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
     """Every kernel carries its own clone of the symbol loop (member decoder, block-parallel decoder of our own streams,
-    units of a foreign stream), allocated in that kernel's context: all three are checked."""
+    units of a foreign stream; the member decoder once more with input streaming), allocated in that kernel's context: all are checked."""
     sass = _sass(kernel)
     # the literal path: `sh += e >> 27` is the only LEA.HI with a 5-bit shift; the loop body follows it
     hits = [i for i, ins in enumerate(sass) if re.match(r"LEA\.HI R\d+, R\d+, R\d+, RZ, 0x5$", ins)]
@@ -45,4 +45,4 @@ def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
     assert sum(ins.startswith("LDS R") for ins in body) >= 2 and any(ins.startswith("STS.U8") for ins in body)
     # ... and nothing goes through local memory, except in the window refill's leave-the-loop path
     local = [ins for ins in body if "LDL" in ins or "STL" in ins]
-    assert len(local) <= 1, local
+    assert len(local) <= (0 if kernel == "14inflate_kernelILb0E" else 1), local      # the headline kernel: none at all

@@ -6,10 +6,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import b2d_loader
 b2d = b2d_loader.load()
-if os.environ.get("B2D_SO"):
-    import b2deflate.binding as bd
-    bd.SO_PATH = os.environ["B2D_SO"]
-b2d.init(0); L = b2d.lib()
+if os.environ.get("B2D_SO"):                      # another build of the library (any age: only the calls below are bound)
+    L = ctypes.CDLL(os.environ["B2D_SO"])
+    assert L.b2d_init(0) == 0
+    vp = ctypes.c_void_p
+    L.b2d_inflate_batch_dev.argtypes = [vp, vp, ctypes.c_uint32, vp, vp, vp, vp, vp, vp, ctypes.c_uint32, vp]
+else:
+    b2d.init(0); L = b2d.lib()
 N, SZ = 4096, 256 << 10
 raw = np.concatenate([b2d.corpus('text', 0xDEF1A7E + k, 64 << 20) for k in range(N * SZ >> 26)])
 def comp(i):
