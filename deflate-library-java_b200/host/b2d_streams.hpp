@@ -18,6 +18,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <future>
 #include <memory>
 #include <optional>
 #include <stdexcept>
@@ -224,9 +225,9 @@ public:
 	void setOutputSizeHint(uint64_t n) { sizeHint = n; }
 	void setTrailerBytes(size_t n) { trailerBytes = n; }     // bytes after the DEFLATE data that belong to the caller
 	void setChecksumAdler32(bool on) { adler = on; }         // checksum() is Adler-32 (zlib container) instead of CRC-32
-	uint32_t crc32() { decodeAll(); return crc; }            // checksum of everything decoded (computed on the GPU)
+	uint32_t crc32() { decodeEverything(); return crc; }     // checksum of everything decoded (computed on the GPU)
 	uint32_t checksum() { return crc32(); }
-	uint64_t consumedBytes() { decodeAll(); return consumed; }
+	uint64_t consumedBytes() { decodeEverything(); return consumed; }
 
 	int read() override {                                                                // :121-134
 		uint8_t b;
@@ -237,7 +238,10 @@ public:
 		if (closed) throw IllegalStateException("Stream already closed");                 // :160-161
 		if (sticky) throw IOException(*sticky);                                           // StickyException.java:17-26
 		if (len == 0) return 0;
-		try { decodeAll(); }
+		try {
+			decodeAll();
+			while (pos >= out.size() && moreBatches()) adoptNextBatch(false);
+		}
 		catch (const IOException &e) { sticky = e.what(); throw; }                        // I/O errors are sticky (:152-157)
 		if (pos < out.size()) {
 			size_t k = std::min(len, out.size() - pos);
@@ -267,18 +271,118 @@ private:
 	int status = 0;
 	uint32_t crc = 0;
 
+	// A stream with a block index is decoded in batches of batchChunks() chunks: while the caller consumes (writes out)
+	// batch k, a second thread already decodes batch k + 1 on the GPU -- the read side of the overlapped file pipeline
+	// (the write side is bin/gzip's).  The compressed input is still read in one go.
+	static uint32_t batchChunks() {                      // B2D_GUNZIP_BATCH=<chunks per batch> (default 256)
+		static const uint32_t n = getenv("B2D_GUNZIP_BATCH") ? std::max<uint32_t>(1, (uint32_t)strtoul(getenv("B2D_GUNZIP_BATCH"), nullptr, 10)) : 256u;
+		return n;
+	}
+	struct Batch { std::vector<uint8_t> bytes; std::vector<uint32_t> crcs; bool ok = false; std::string error; };
+	std::unique_ptr<PinnedBuffer> batchIn;               // the whole compressed input, kept while batches are pending
+	std::vector<uint64_t> batchInOff;                    // chunk offsets in it
+	uint32_t nextChunk = 0;                              // first chunk that is neither delivered nor being decoded
+	uint32_t pendingFirst = 0, pendingCount = 0;
+	std::future<Batch> pending;
+	size_t usableIn = 0;
+
+	bool moreBatches() const { return pending.valid(); }
+	Batch decodeBatch(uint32_t c0, uint32_t nb) {
+		Batch r;
+		const uint32_t n = (uint32_t)index.sizes.size();
+		const uint64_t bpc = index.chunk_bytes / index.block_bytes;
+		const uint64_t o0 = (uint64_t)c0 * index.chunk_bytes, o1 = std::min<uint64_t>(sizeHint, (uint64_t)(c0 + nb) * index.chunk_bytes);
+		PinnedBuffer pout;
+		pout.reserve(o1 - o0 + 64);
+		r.crcs.resize(nb);
+		std::vector<int32_t> st(nb);
+		int rc = b2d_inflate_chunks(batchIn->p + batchInOff[c0], index.sizes.data() + c0, nb, index.block_bits.data() + (size_t)c0 * bpc,
+		                            index.chunk_bytes, index.block_bytes, pout.p, o1 - o0, r.crcs.data(), st.data(),
+		                            adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32);
+		if (rc != B2D_OK) { r.error = std::string("b2d_inflate_chunks: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]"; return r; }
+		r.ok = true;
+		for (uint32_t i = 0; i < nb; i++) if (st[i] != 0) r.ok = false;     // the chunk-indexed path reports the exact outcome
+		if (r.ok) r.bytes.assign(pout.p, pout.p + (o1 - o0));
+		(void)n;
+		return r;
+	}
+	void launchBatch() {
+		const uint32_t n = (uint32_t)index.sizes.size();
+		if (nextChunk >= n) return;
+		pendingFirst = nextChunk;
+		pendingCount = std::min<uint32_t>(batchChunks(), n - nextChunk);
+		nextChunk += pendingCount;
+		pending = std::async(std::launch::async, [this, c0 = pendingFirst, nb = pendingCount] { return decodeBatch(c0, nb); });
+	}
+	// takes over the batch that is being decoded; append = keep what is still unread of the current one in front of it
+	void adoptNextBatch(bool append) {
+		Batch b = pending.get();
+		if (!b.error.empty()) throw IOException(b.error);
+		const uint32_t c0 = pendingFirst, nb = pendingCount;
+		if (!b.ok) {                                    // something unusual in this batch: the rest goes the careful way, chunk by chunk
+			std::vector<uint8_t> keep;
+			if (append) keep.assign(out.begin() + (long)pos, out.end());
+			PinnedBuffer pout;
+			decodeIndexedFrom(*batchIn, pout, usableIn, c0, keep);
+			pos = 0;
+			batchIn.reset();
+			return;
+		}
+		for (uint32_t i = 0; i < nb; i++) {
+			const uint64_t len = std::min<uint64_t>(index.chunk_bytes, sizeHint - (uint64_t)(c0 + i) * index.chunk_bytes);
+			crc = adler ? b2d_adler32_combine(crc, b.crcs[i], len) : b2d_crc32_combine(crc, b.crcs[i], len);
+		}
+		if (append) { out.erase(out.begin(), out.begin() + (long)pos); out.insert(out.end(), b.bytes.begin(), b.bytes.end()); }
+		else out = std::move(b.bytes);
+		pos = 0;
+		consumed = batchInOff[c0 + nb];
+		launchBatch();
+		if (!pending.valid()) {                          // that was the last batch
+			status = 0;
+			batchIn.reset();
+			if (endExactly) {                            // Open.finish, Open.java:113-124
+				input->reset();
+				input->skipNBytes(consumed);
+			}
+		}
+	}
+	void decodeEverything() {
+		decodeAll();
+		while (moreBatches()) adoptNextBatch(true);
+	}
+	// the batched path applies when the index has block offsets and the exact size is known (what bin/gzip writes)
+	bool startBatches(std::unique_ptr<PinnedBuffer> &pin, size_t in_len) {
+		const uint32_t n = (uint32_t)index.sizes.size();
+		if (n <= batchChunks() || index.block_bytes == 0 || sizeHint == 0 || index.chunk_bytes % index.block_bytes != 0) return false;
+		const uint64_t bpc = index.chunk_bytes / index.block_bytes;
+		if (index.block_bits.size() != (size_t)n * bpc) return false;
+		if ((uint64_t)n * index.chunk_bytes < sizeHint || (uint64_t)(n - 1) * index.chunk_bytes >= sizeHint) return false;
+		batchInOff.assign(n + 1, 0);
+		for (uint32_t i = 0; i < n; i++) batchInOff[i + 1] = batchInOff[i] + index.sizes[i];
+		if (batchInOff[n] > in_len) return false;
+		batchIn = std::move(pin);
+		usableIn = in_len;
+		crc = adler ? 1 : 0;
+		nextChunk = 0;
+		launchBatch();
+		adoptNextBatch(false);
+		return true;
+	}
+
 	void decodeAll() {
 		if (decoded) return;
 		decoded = true;
 		requireDevice();
 		std::vector<uint8_t> raw = input->readAllBytes();
 		const size_t usable = raw.size() >= trailerBytes ? raw.size() - trailerBytes : raw.size();
-		PinnedBuffer pin, pout;
-		pin.reserve(raw.size() + 64);
-		if (!raw.empty()) memcpy(pin.p, raw.data(), raw.size());
-		if (!index.empty()) decodeIndexed(pin, pout, usable);
-		else decodeSerial(pin, pout, usable);
-		if (endExactly && status == 0) {                                 // Open.finish, Open.java:113-124
+		std::unique_ptr<PinnedBuffer> pin(new PinnedBuffer());
+		PinnedBuffer pout;
+		pin->reserve(raw.size() + 64);
+		if (!raw.empty()) memcpy(pin->p, raw.data(), raw.size());
+		if (!index.empty() && startBatches(pin, usable)) { /* batches deliver as they come */ }
+		else if (!index.empty()) decodeIndexed(*pin, pout, usable);
+		else decodeSerial(*pin, pout, usable);
+		if (endExactly && status == 0 && !moreBatches()) {               // Open.finish, Open.java:113-124
 			input->reset();
 			input->skipNBytes(consumed);
 		}
@@ -335,13 +439,21 @@ private:
 	}
 
 	void decodeIndexed(PinnedBuffer &pin, PinnedBuffer &pout, size_t in_len) {
-		const uint32_t n = (uint32_t)index.sizes.size();
 		if (decodeBlocks(pin, pout, in_len)) return;
-		std::vector<uint64_t> in_off(n + 1, 0), out_off(n + 1, 0), out_len(n), cons(n);
+		crc = adler ? 1 : 0;
+		decodeIndexedFrom(pin, pout, in_len, 0, std::vector<uint8_t>());
+	}
+	// chunks c0 .. end, one warp per chunk (exact status and delivered bytes); `front` = bytes to deliver before them;
+	// crc holds the checksum of everything in front of chunk c0
+	void decodeIndexedFrom(PinnedBuffer &pin, PinnedBuffer &pout, size_t in_len, uint32_t c0, const std::vector<uint8_t> &front) {
+		const uint32_t n_all = (uint32_t)index.sizes.size(), n = n_all - c0;
+		uint64_t base_in = 0;
+		for (uint32_t i = 0; i < c0; i++) base_in += index.sizes[i];
+		std::vector<uint64_t> in_off(n + 1, base_in), out_off(n + 1, 0), out_len(n), cons(n);
 		std::vector<uint32_t> crcs(n);
 		std::vector<int32_t> st(n);
 		for (uint32_t i = 0; i < n; i++) {
-			in_off[i + 1] = in_off[i] + index.sizes[i];
+			in_off[i + 1] = in_off[i] + index.sizes[c0 + i];
 			out_off[i + 1] = out_off[i] + index.chunk_bytes;
 		}
 		if (in_off[n] > in_len) throw DataFormatException::unexpectedEnd();
@@ -349,14 +461,13 @@ private:
 		int rc = b2d_inflate_batch(pin.p, in_off.data(), n, pout.p, out_off.data(), out_len.data(), cons.data(), crcs.data(),
 		                           st.data(), (adler ? B2D_INFLATE_ADLER32 : B2D_INFLATE_CRC32) | B2D_INFLATE_CHUNK_INDEXED);
 		if (rc != B2D_OK) throw IOException(std::string("b2d_inflate_batch: ") + b2d_strerror(rc) + " [" + b2d_last_error() + "]");
-		out.clear();
-		out.reserve(out_off[n]);
-		crc = adler ? 1 : 0;
+		out = front;
+		out.reserve(front.size() + out_off[n]);
 		for (uint32_t i = 0; i < n; i++) {                               // deliver up to the first failing chunk, as a serial decode would
 			out.insert(out.end(), pout.p + out_off[i], pout.p + out_off[i] + out_len[i]);
 			crc = adler ? b2d_adler32_combine(crc, crcs[i], out_len[i]) : b2d_crc32_combine(crc, crcs[i], out_len[i]);
 			consumed = in_off[i] + cons[i];
-			if (st[i] != 0 || cons[i] != index.sizes[i] || (i + 1 < n && out_len[i] != index.chunk_bytes)) {
+			if (st[i] != 0 || cons[i] != index.sizes[c0 + i] || (i + 1 < n && out_len[i] != index.chunk_bytes)) {
 				status = st[i] != 0 ? st[i] : B2D_UNEXPECTED_END_OF_STREAM;
 				return;
 			}

@@ -22,8 +22,10 @@ def run(*args, env=None):
     return subprocess.run(list(args), capture_output=True, text=True, env=e)
 
 
-@pytest.mark.parametrize("kind,n", [("text", 0), ("text", 1), ("text", 70000), ("mixed", (5 << 20) + 12345), ("random", 3 << 20)])
-@pytest.mark.parametrize("index", ["1", "0", "split"])
+# (every CLI run is a process that creates a CUDA context, 2-3 s on the GPU boxes: the matrix is kept small)
+@pytest.mark.parametrize("kind,n,index", [("text", 0, "1"), ("text", 0, "0"), ("text", 1, "1"), ("text", 70000, "0"), ("text", 70000, "split"),
+                                          ("mixed", (5 << 20) + 12345, "1"), ("mixed", (5 << 20) + 12345, "0"),
+                                          ("mixed", (5 << 20) + 12345, "split"), ("random", 3 << 20, "1")])
 def test_cli_roundtrip_and_interop(b2d, oracle, tmp_path, kind, n, index):
     data = b2d.corpus(kind, 0xDEF1A7E, n).tobytes()
     src, gz, back = tmp_path / "in.bin", tmp_path / "out.gz", tmp_path / "back.bin"
@@ -161,7 +163,7 @@ def test_reference_stream_tests_on_host_mirror(b2d, tmp_path):
     assert "passed" in r.stdout and "of" in r.stdout
 
 
-@pytest.mark.parametrize("batch_mib", ["1", "2", "256"])
+@pytest.mark.parametrize("batch_mib", ["1", "2"])
 def test_gzip_streams_the_file_in_batches(b2d, oracle, tmp_path, batch_mib):
     """bin/gzip reads, compresses and writes in batches (reader and writer threads next to the GPU call) and rewrites the
     header in place with the chunk index once the sizes are known: whatever the batch size, the file is the same member
@@ -200,3 +202,33 @@ def test_gunzip_decodes_a_system_gzip_file_in_parallel(b2d, tmp_path):
     assert r.returncode == 0, r.stderr
     assert back.read_bytes() == data
     assert "inflate_stream: result on the host" in r.stderr                  # the parallel path ran
+
+
+@pytest.mark.parametrize("batch_chunks", ["1", "2"])
+def test_gunzip_decodes_indexed_files_in_batches(b2d, tmp_path, batch_chunks):
+    """bin/gunzip on a file with the block index decodes batch k + 1 on the GPU while batch k is being written: the output,
+    the CRC / ISIZE verdict and the error convention are those of the one-shot decode, whatever the batch size -- also
+    when a chunk in a later batch is damaged (the bytes in front of the damage are delivered, then the exception)."""
+    n = (5 << 20) + 4321
+    data = b2d.corpus("mixed", 0xDEF1A7E + 9, n).tobytes()
+    src, gz, back = tmp_path / "in.bin", tmp_path / "out.gz", tmp_path / "back.bin"
+    src.write_bytes(data)
+    assert run(GZIP, str(src), str(gz)).returncode == 0
+    env = {"B2D_GUNZIP_BATCH": batch_chunks}
+    r = run(GUNZIP, str(gz), str(back), env=env)
+    assert r.returncode == 0, r.stderr
+    assert back.read_bytes() == data
+    member = bytearray(gz.read_bytes())
+    member[-6] ^= 1                                               # CRC-32 in the trailer
+    bad = tmp_path / "badcrc.gz"
+    bad.write_bytes(bytes(member))
+    r = run(GUNZIP, str(bad), str(back), env=env)
+    assert r.returncode == 1 and "Decompression CRC-32 mismatch" in r.stderr
+    member = bytearray(gz.read_bytes())
+    member[len(member) * 3 // 4] ^= 0x10                          # inside a chunk of a later batch
+    bad2 = tmp_path / "badbody.gz"
+    bad2.write_bytes(bytes(member))
+    ref = run(GUNZIP, str(bad2), str(tmp_path / "ref.out"), env={"B2D_GUNZIP_BATCH": "100000"})
+    r = run(GUNZIP, str(bad2), str(back), env=env)
+    assert r.returncode == 1 and ref.returncode == 1
+    assert r.stderr.splitlines()[-1] == ref.stderr.splitlines()[-1]                  # the same exception line
