@@ -1407,11 +1407,21 @@ __device__ bool header_plausible(const u32 *__restrict__ words, u64 n_words, u64
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
-stream_find_kernel(const u8 *__restrict__ in, u64 in_len, u32 seg_bytes, u32 n_seg, StreamUnit *__restrict__ units) {
+stream_find_kernel(const u8 *__restrict__ in, u64 in_len, u32 seg_bytes, u32 n_seg, u32 n_units, StreamUnit *__restrict__ units,
+                   u32 *__restrict__ pool) {
 	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 k = blockIdx.x * WARPS_PER_CTA + warp;
-	if (k >= n_seg) return;
+	if (k >= n_units) return;
+	if (k == 0 && lane == 0) *pool = 0;
+	if (k >= n_seg) {                                  // a spare unit (see stream_units_kernel): nobody starts here
+		if (lane == 0) {
+			StreamUnit u;
+			u.start_bit = NO_START; u.end_bit = 0; u.out_len = 0; u.n_refs = 0; u.next = STREAM_END; u.status = 0;
+			units[k] = u;
+		}
+		return;
+	}
 	const Sm sm = warp_smem(smem_raw, warp);
 	u64 found = k == 0 ? 0 : NO_START;
 	const u64 total_bits = in_len * 8;
@@ -1488,11 +1498,11 @@ stream_find_kernel(const u8 *__restrict__ in, u64 in_len, u32 seg_bytes, u32 n_s
 }
 
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM)
-stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit *units, u8 *planeL, u64 stride, u32 cap,
-                    u64 *__restrict__ glist, u32 gcap) {
+stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, u32 n_units, StreamUnit *units, u8 *planeL, u64 stride, u32 cap,
+                    u64 *__restrict__ glist, u32 gcap, u32 *__restrict__ pool) {
 	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-	const u32 k = blockIdx.x * WARPS_PER_CTA + warp;
+	u32 k = blockIdx.x * WARPS_PER_CTA + warp;
 	if (k >= n_seg) return;
 	const u64 start = units[k].start_bit;
 	if (start == NO_START) return;
@@ -1526,6 +1536,31 @@ stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, StreamUnit
 				j++;
 			}
 			if (j < n_seg && units[j].start_bit == pos) { next = j; break; }
+			// Nobody starts here, and the unit's buffer is half full (long stretches of stored or fixed blocks have no
+			// dynamic block to restart at): the warp goes on in a SPARE unit -- a fresh buffer, list and unknown
+			// window -- and the chain leads from this unit to that one like to any other.
+			if (out_pos(m) > cap / 2) {
+				flush_tile(m, sm, lane);
+				u32 s = 0;
+				if (lane == 0) s = n_seg + atomicAdd(pool, 1u);
+				s = __shfl_sync(FULL_MASK, s, 0);
+				if (s >= n_units) { err = B2D_ERR_OUTPUT_OVERFLOW; break; }
+				if (lane == 0) {
+					units[k].end_bit = pos;
+					units[k].out_len = (u32)out_pos(m);
+					units[k].n_refs = min(m.gcount, m.gcap);
+					units[k].next = s;
+					units[k].status = m.gcount > m.gcap ? B2D_ERR_OUTPUT_OVERFLOW : 0;
+					units[s].start_bit = pos;
+				}
+				__syncwarp();
+				k = s;
+				m.out = planeL + (u64)k * stride + STREAM_WINDOW;
+				m.glist = glist + (u64)k * gcap;
+				m.gcount = 0;
+				m.hist_base = STREAM_WINDOW;
+				set_tile_origin(m, 0);
+			}
 		}
 		first = false;
 		int avail = avail_bits(m.in);
@@ -1733,9 +1768,9 @@ stream_finish_kernel(const StreamUnit *__restrict__ units, const u32 *__restrict
 }
 
 struct StreamPlan {
-	u32 seg_bytes, n_seg, cap, gcap;
+	u32 seg_bytes, n_seg, n_units, cap, gcap;
 	u64 stride;
-	size_t o_units, o_planeL, o_planeH, o_glist, o_mapsA, o_mapsB, o_live, o_off, total;
+	size_t o_units, o_planeL, o_planeH, o_glist, o_mapsA, o_mapsB, o_live, o_off, o_pool, total;
 };
 static StreamPlan stream_plan(uint64_t in_len, uint32_t cap_scale) {
 	StreamPlan p;
@@ -1746,16 +1781,18 @@ static StreamPlan stream_plan(uint64_t in_len, uint32_t cap_scale) {
 	p.cap = (u32)min((u64)0xFFFFF0, p.stride - STREAM_WINDOW - 64);
 	p.gcap = p.cap / 3 + 8;
 	p.n_seg = (u32)max((u64)1, (in_len + p.seg_bytes - 1) / p.seg_bytes);
+	p.n_units = p.n_seg + max(16u, p.n_seg / 4);          // + spare units for stretches without a block start
 	size_t o = 0;
 	auto carve = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~(size_t)255; return r; };
-	p.o_units = carve((size_t)p.n_seg * sizeof(StreamUnit));
-	p.o_planeL = carve((size_t)p.n_seg * p.stride + 256);
-	p.o_planeH = carve((size_t)p.n_seg * p.stride + 256);
-	p.o_glist = carve((size_t)p.n_seg * p.gcap * 8);
-	p.o_mapsA = carve((size_t)p.n_seg * STREAM_WINDOW * 2);
-	p.o_mapsB = carve((size_t)p.n_seg * STREAM_WINDOW * 2);
-	p.o_live = carve((size_t)p.n_seg * 4);
-	p.o_off = carve((size_t)(p.n_seg + 1) * 8);
+	p.o_units = carve((size_t)p.n_units * sizeof(StreamUnit));
+	p.o_planeL = carve((size_t)p.n_units * p.stride + 256);
+	p.o_planeH = carve((size_t)p.n_units * p.stride + 256);
+	p.o_glist = carve((size_t)p.n_units * p.gcap * 8);
+	p.o_mapsA = carve((size_t)p.n_units * STREAM_WINDOW * 2);
+	p.o_mapsB = carve((size_t)p.n_units * STREAM_WINDOW * 2);
+	p.o_live = carve((size_t)p.n_units * 4);
+	p.o_off = carve((size_t)(p.n_units + 1) * 8);
+	p.o_pool = carve(256);
 	p.total = o;
 	return p;
 }
@@ -1780,19 +1817,20 @@ cudaError_t launch_inflate_stream(const u8 *d_in, u64 in_len, u8 *d_out, u64 out
 	u32 *live = (u32 *)(sp + p.o_live);
 	u64 *off = (u64 *)(sp + p.o_off);
 	StreamResult *res = (StreamResult *)d_result;
-	const u32 wgrid = (p.n_seg + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
-	B2D_LAUNCH(stream_find_kernel, wgrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.seg_bytes, p.n_seg, units);
-	B2D_LAUNCH(stream_units_kernel, wgrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.n_seg, units, planeL, p.stride, p.cap, glist, p.gcap);
-	B2D_LAUNCH(stream_planes_kernel, p.n_seg, 256, 0, st)(units, planeL, planeH, p.stride);
-	B2D_LAUNCH(stream_replay_kernel, dim3(wgrid, 2), WARPS_PER_CTA * 32, 0, st)(units, p.n_seg, planeL, planeH, p.stride, glist, p.gcap);
-	B2D_LAUNCH(stream_walk_kernel, 1, 32, 0, st)(units, p.n_seg, live, off, out_cap, res);
-	B2D_LAUNCH(stream_maps_kernel, dim3(p.n_seg, 4), 256, 0, st)(units, live, res, planeL, planeH, p.stride, mapsA);
+	u32 *pool = (u32 *)(sp + p.o_pool);
+	const u32 wgrid = (p.n_seg + WARPS_PER_CTA - 1) / WARPS_PER_CTA, ugrid = (p.n_units + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+	B2D_LAUNCH(stream_find_kernel, ugrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.seg_bytes, p.n_seg, p.n_units, units, pool);
+	B2D_LAUNCH(stream_units_kernel, wgrid, WARPS_PER_CTA * 32, 0, st)(d_in, in_len, p.n_seg, p.n_units, units, planeL, p.stride, p.cap, glist, p.gcap, pool);
+	B2D_LAUNCH(stream_planes_kernel, p.n_units, 256, 0, st)(units, planeL, planeH, p.stride);
+	B2D_LAUNCH(stream_replay_kernel, dim3(ugrid, 2), WARPS_PER_CTA * 32, 0, st)(units, p.n_units, planeL, planeH, p.stride, glist, p.gcap);
+	B2D_LAUNCH(stream_walk_kernel, 1, 32, 0, st)(units, p.n_units, live, off, out_cap, res);
+	B2D_LAUNCH(stream_maps_kernel, dim3(p.n_units, 4), 256, 0, st)(units, live, res, planeL, planeH, p.stride, mapsA);
 	u16 *src = mapsA, *dst = mapsB;
-	for (u32 d = 1; d < p.n_seg; d <<= 1) {            // (the number of live units is only known on the device: enough rounds for all)
-		B2D_LAUNCH(stream_compose_kernel, dim3(p.n_seg, 4), 256, 0, st)(src, dst, d, res);
+	for (u32 d = 1; d < p.n_units; d <<= 1) {          // (the number of live units is only known on the device: enough rounds for all)
+		B2D_LAUNCH(stream_compose_kernel, dim3(p.n_units, 4), 256, 0, st)(src, dst, d, res);
 		u16 *tmp = src; src = dst; dst = tmp;
 	}
-	B2D_LAUNCH(stream_finish_kernel, dim3(p.n_seg, 4), 256, 0, st)(units, live, off, res, planeL, planeH, p.stride, src, d_out);
+	B2D_LAUNCH(stream_finish_kernel, dim3(p.n_units, 4), 256, 0, st)(units, live, off, res, planeL, planeH, p.stride, src, d_out);
 	return cudaGetLastError();
 }
 

@@ -92,3 +92,15 @@ def test_segment_and_buffer_knobs(b2d):
         assert st == 0 and out.tobytes() == data and consumed == len(comp)
     os.environ.pop("B2D_STREAM_SEGMENT", None)
     os.environ.pop("B2D_STREAM_UNIT_CAP", None)
+
+
+def test_long_stretch_without_a_dynamic_block(b2d, oracle):
+    """Three MiB of random bytes in the middle of a text: zlib stores them (48 stored blocks, nothing for the block finder
+    to restart at).  The unit that runs into the stretch moves on through spare units instead of outgrowing its buffer,
+    so the stream is still decoded by the parallel path."""
+    rng = random.Random(12)
+    data = _text(b2d, 31, 2 << 20) + rng.randbytes(3 << 20) + _text(b2d, 32, 2 << 20)
+    comp = zlib_raw(data, 6)
+    out, consumed, crc, st, par = b2d.inflate_stream(comp, len(data) + 16)
+    assert st == 0 and par == 1 and consumed == len(comp)
+    assert out.tobytes() == data and crc == zlib.crc32(data)
