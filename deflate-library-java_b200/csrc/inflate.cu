@@ -129,6 +129,16 @@ struct BitIn {
 	u32 sh;               // bits of `cur` already consumed; >= 32 means advance() is due
 };
 
+// words = the 128-byte line of the member's first byte: word numbers are then line-relative (decode_block_fast keeps one
+// line of input per lane), and the lead bytes in front of the member are simply skipped bits
+__device__ __forceinline__ void bitin_init(BitIn &b, const u8 *src, u64 in_len) {
+	const u32 lead = (u32)((uintptr_t)src & 127);
+	b.words = (const u32 *)(src - lead);
+	b.lead8 = lead * 8;
+	b.total_bits = in_len * 8;
+	b.n_safe = (u32)((lead + in_len + 3) >> 2);
+	b.n_full = (u32)((lead + in_len) >> 2);
+}
 __device__ __forceinline__ u32 load_word(const BitIn &b, u32 i) {
 	return i < b.n_safe ? __ldg(b.words + i) : 0u;
 }
@@ -579,92 +589,194 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 //    last <= 12 bytes of a member and when the member's output slot is nearly full.
 enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 
+// The hot loop is written in PTX: every lane of the warp decodes the same symbol, so every branch of the loop is
+// uniform -- which the compiler cannot know (the LUT entries come from shared memory), and it fences each of them with
+// convergence barriers (BSSY / BSYNC / BREAK, BRA.DIV around the shuffle), duplicates induction variables across the
+// nested exits and so spends 15 instructions on a literal, 40 on a length/distance pair and 24 on a window refill.
+// With `bra.uni` the same loop is 11 / 31 / 9.  The block has two entries (look the next symbol up, or dispatch an
+// entry the caller resolved) and leaves with an event code at exactly the states the handlers below expect.
+#define A_CUR "%0"
+#define A_NXT "%1"
+#define A_PRE "%2"
+#define A_SH "%3"
+#define A_W "%4"
+#define A_TP "%5"
+#define A_QP "%6"
+#define A_E "%7"
+#define A_LO "%8"
+#define A_D "%9"
+#define A_LO2 "%10"
+#define A_EV "%11"
+#define A_BUF "%12"
+#define A_WSTOP1 "%13"
+#define A_TGUARD "%14"
+#define A_POSOFF "%15"
+#define A_LLB "%16"
+#define A_ENTRY "%17"
+#define A_REFILL_WORD                                                                   \
+	"add.u32 " A_W ", " A_W ", 1;\n\t"                                                  \
+	"sub.u32 " A_SH ", " A_SH ", 32;\n\t"                                               \
+	"mov.b32 " A_CUR ", " A_NXT ";\n\t"                                                 \
+	"mov.b32 " A_NXT ", " A_PRE ";\n\t"                                                 \
+	"shfl.sync.idx.b32 " A_PRE ", " A_BUF ", " A_W ", 31, 0xffffffff;\n\t"
+#define HOT_LOOP()                                                                      \
+	asm volatile("{\n\t"                                                                \
+		".reg .b32 t, u, a, bb, x, dist, qx, len;\n\t"                                  \
+		".reg .pred p, q;\n\t"                                                          \
+		"setp.ne.u32 p, " A_ENTRY ", 0;\n\t"                                            \
+		"@p bra.uni L_DISPATCH;\n"                                                      \
+		"L_LOOKUP:\n\t"                                                                 \
+		"shf.r.wrap.b32 " A_LO ", " A_CUR ", " A_NXT ", " A_SH ";\n\t"                  \
+		"shl.b32 t, " A_LO ", 2;\n\t"                                                   \
+		"lop3.b32 t, t, 0xFFC, " A_LLB ", 0xEA;\n\t"                                    \
+		"ld.shared.u32 " A_E ", [t];\n"                                                 \
+		"L_DISPATCH:\n\t"                                                               \
+		"and.b32 t, " A_E ", 0x10000;\n\t"                                              \
+		"setp.eq.u32 p, t, 0;\n\t"                                                      \
+		"@p bra.uni L_NOTLIT;\n\t"                                                      \
+		/* literal: every lane stores the same byte (one broadcast write) */            \
+		"st.shared.u8 [" A_TP "], " A_E ";\n\t"                                         \
+		"add.u32 " A_TP ", " A_TP ", 1;\n\t"                                            \
+		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
+		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
+		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
+		"@p bra.uni L_LOOKUP;\n\t"                                                      \
+		/* a literal crosses at most one word */                                        \
+		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
+		"@p bra.uni L_X_BOUNDARY;\n\t"                                                  \
+		A_REFILL_WORD                                                                   \
+		"setp.gt.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
+		"@!p bra.uni L_LOOKUP;\n\t"                                                     \
+		"bra.uni L_X_BOUNDARY;\n"                                                       \
+		"L_NOTLIT:\n\t"                                                                 \
+		"and.b32 t, " A_E ", 0x20000;\n\t"                                              \
+		"setp.eq.u32 p, t, 0;\n\t"                                                      \
+		"@p bra.uni L_X_RARE;\n\t"                                                      \
+		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
+		"add.u32 " A_SH ", " A_SH ", t;\n\t"           /* <= 51: the distance may start in nxt */ \
+		"and.b32 t, " A_SH ", 32;\n\t"                                                  \
+		"setp.ne.u32 p, t, 0;\n\t"                                                      \
+		"selp.b32 a, " A_NXT ", " A_CUR ", p;\n\t"                                      \
+		"selp.b32 bb, " A_PRE ", " A_NXT ", p;\n\t"                                     \
+		"shf.r.wrap.b32 " A_LO2 ", a, bb, " A_SH ";\n\t"                                \
+		"shr.u32 u, " A_LLB ", 2;\n\t"                                                  \
+		"shl.b32 t, " A_LO2 ", 2;\n\t"                                                  \
+		"lop3.b32 t, t, 0x3FC, u, 0xEA;\n\t"                                            \
+		"ld.shared.u32 " A_D ", [t];\n\t"                                               \
+		"and.b32 t, " A_D ", 0x80;\n\t"                                                 \
+		"setp.ne.u32 p, t, 0;\n\t"                                                      \
+		"@p bra.uni L_X_DSPECIAL;\n\t"                                                  \
+		/* dist = base + extra bits (entry_value) */                                    \
+		"shf.l.wrap.b32 x, 0, 0xFFFFFFFF, " A_D ";\n\t"                                 \
+		"lop3.b32 x, " A_LO2 ", x, 0, 0x30;\n\t"                                        \
+		"shr.u32 t, " A_D ", 8;\n\t"                                                    \
+		"shf.r.wrap.b32 x, x, 0, t;\n\t"                                                \
+		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
+		"add.u32 dist, t, x;\n\t"                                                       \
+		"and.b32 t, " A_D ", 31;\n\t"                                                   \
+		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
+		/* queued form: tile address | length << 16 (the kind bits shift out); the source must exist    \
+		   (Open.java:592-593) and the whole reference fit the tile with the literal guard kept; tp is  \
+		   advanced first (the slow path takes it back) */                              \
+		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
+		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
+		"add.s32 t, " A_POSOFF ", " A_TP ";\n\t"                                        \
+		"shr.u32 len, qx, 16;\n\t"                                                      \
+		"add.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
+		"setp.gt.s32 p, dist, t;\n\t"                                                   \
+		"setp.gt.s32 q, " A_TP ", " A_TGUARD ";\n\t"                                    \
+		"or.pred p, p, q;\n\t"                                                          \
+		"@p bra.uni L_X_SLOWMATCH;\n\t"                                                 \
+		"st.shared.v2.u32 [" A_QP "], {qx, dist};\n\t"                                  \
+		"add.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
+		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
+		"setp.eq.u32 p, t, 0;\n\t"                                                      \
+		"@p bra.uni L_X_QFULL;\n\t"                                                     \
+		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
+		"@p bra.uni L_LOOKUP;\n"                                                        \
+		"L_REFILL2:\n\t"                               /* a pair can cross two words */ \
+		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
+		"@p bra.uni L_X_BOUNDARY;\n\t"                                                  \
+		A_REFILL_WORD                                                                   \
+		"setp.ge.u32 p, " A_SH ", 32;\n\t"                                              \
+		"@p bra.uni L_REFILL2;\n\t"                                                     \
+		"setp.gt.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
+		"@!p bra.uni L_LOOKUP;\n"                                                       \
+		"L_X_BOUNDARY:\n\t"                                                             \
+		"mov.u32 " A_EV ", 2;\n\t"                                                      \
+		"bra.uni L_END;\n"                                                              \
+		"L_X_RARE:\n\t"                                                                 \
+		"mov.u32 " A_EV ", 3;\n\t"                                                      \
+		"bra.uni L_END;\n"                                                              \
+		"L_X_DSPECIAL:\n\t"                                                             \
+		"mov.u32 " A_EV ", 4;\n\t"                                                      \
+		"bra.uni L_END;\n"                                                              \
+		"L_X_SLOWMATCH:\n\t"                                                            \
+		"mov.u32 " A_EV ", 5;\n\t"                                                      \
+		"bra.uni L_END;\n"                                                              \
+		"L_X_QFULL:\n\t"                                                                \
+		"mov.u32 " A_EV ", 6;\n"                                                        \
+		"L_END:\n\t"                                                                    \
+		"}"                                                                             \
+		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(lo), "+r"(d), "+r"(lo2), "=r"(ev) \
+		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(entry)     \
+		: "memory")
+static_assert(EV_FLUSH == 2 && EV_RARE == 3 && EV_DSPECIAL == 4 && EV_SLOWMATCH == 5 && EV_QFULL == 6, "event codes of HOT_LOOP");
+
 __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
-	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, widx = b.widx, sh = b.sh;     // sh < 32, widx + 3 <= n_full
+	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, sh = b.sh;     // sh < 32, widx + 3 <= n_full
 	// The output position is kept as the shared-window ADDRESS of the next tile byte (tp = tile_s + tpos), so a
 	// literal store needs no address arithmetic; limits and the queued references are in the same terms.
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile);
 	const u32 mq_s = (u32)__cvta_generic_to_shared(sm.mq);
-	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);       // 4 KiB-aligned; the distance LUT sits at llb >> 2
+	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);       // 4 KiB-aligned; the distance LUT sits at llb >> 2:
+	                                                             // entry address = (bits << 2) masked, OR-ed into the table's
 	u32 tp = tile_s + m.tpos;
 	u32 tend = tile_s + m.tlimit;                    // end of the usable tile
-	int tguard = (int)tend - (int)LIT_GUARD;         // tp <= tguard at every word boundary (see NEXT_SYMBOL)
+	int tguard = (int)tend - (int)LIT_GUARD;         // tp <= tguard at every word boundary (see below)
 	int pos_off = m.pos_base - (int)tile_s;          // output position of the byte at tp = pos_off + tp
 	u32 qp = mq_s + m.nm * 8;                        // next free slot of the reference queue (256 B, 256-aligned:
 	                                                 // full when the next slot's address wraps to 0 mod 256)
-	const u32 fast_last = b.n_full - 3;
-	const u32 *const words = b.words;
-#define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = widx; b.sh = sh; m.tpos = tp - tile_s; \
+	// Input: the 32 lanes hold one 128-byte line of the member each way (buf = the line of the word in `pre`, bufn =
+	// the line behind it, loaded a whole line ahead with one coalesced request), and a refill takes its word from the
+	// lane that has it: no load instruction, no address arithmetic and no memory latency on the refill path.  b.words is
+	// 128-byte aligned (bitin_init), so word numbers are line-relative as they are; w = the number of the word in `pre`.
+	// The three buffered words must stay real input, so only full words (all of them staged) are ever fetched: wstop,
+	// the next number that needs a decision, is the nearer of the next line's first word and the first word that is
+	// not full; there the loop is left with the window untouched (the checked path advances by itself).
+	u32 w = b.widx + 2;
+	u32 wstop, buf, bufn;
+#define LOAD_LINE(first) ((first) + lane >= (b.lead8 >> 5) && (first) + lane < b.n_full ? __ldg(b.words + ((first) + lane)) : 0u)
+	buf = LOAD_LINE(w & ~31u);
+	bufn = LOAD_LINE((w & ~31u) + 32);
+	wstop = min((w | 31u) + 1, b.n_full);
+#define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = w - 2; b.sh = sh; m.tpos = tp - tile_s; \
                           m.nm = (qp - mq_s) >> 3; } while (0)
 #define LOAD_TILE() do { tp = tile_s + m.tpos; tend = tile_s + m.tlimit; qp = mq_s + m.nm * 8; \
                          pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; } while (0)
-	// LUT entry addresses: (bits << 2) masked and OR-ed into the aligned table address
-#define LL_AT(bits) lds_u32(llb | (((bits) << 2) & ((4u << LL_TB) - 4)))
-#define DL_AT(bits) lds_u32(quarter(llb) | (((bits) << 2) & ((4u << D_TB) - 4)))
-	// Window refill at a symbol boundary.  The three buffered words must stay real input, so the word about to be
-	// loaded (widx + 3) has to be a full one; otherwise the hot loop is left with the window untouched (the checked
-	// path advances by itself).  A length/distance pair can cross two words: then the loop runs twice.  Literals are
-	// stored without a capacity check: fewer than LIT_GUARD symbols can start before the next word boundary is crossed
-	// (<= 79 bits at >= 1 bit each), so room for that many is secured here, once per word.
-#define NEXT_SYMBOL()                                                     \
-	if (sh >= 32) {                                                       \
-		_Pragma("unroll 1")                                               \
-		do {                                                              \
-			if (widx >= fast_last) break;                                 \
-			sh -= 32; cur = nxt; nxt = pre; widx++;                       \
-			pre = __ldg(words + widx + 2);                                \
-		} while (sh >= 32);                                               \
-		if (sh >= 32) { ev = EV_SWITCH; break; }                          \
-		if ((int)tp > tguard) { ev = EV_FLUSH; break; }                   \
-	}                                                                     \
-	lo = __funnelshift_r(cur, nxt, sh);                                   \
-	e = LL_AT(lo);
-	u32 lo = __funnelshift_r(cur, nxt, sh);
-	u32 e = LL_AT(lo);
+	u32 e = 0, lo = 0, entry = 0;
 	for (;;) {
-		int ev;
-		u32 len = 0, d = 0, lo2 = 0;
-		for (;;) {                                       // ---- the hot loop: no call inside
-			if (e & K_LIT) {
-				sts_u8(tp, e);                               // every lane stores the same byte: one broadcast write, no predicate
-				tp++;
-				sh += e >> 27;
-				NEXT_SYMBOL();
-				continue;
-			}
-			if (!(e & K_LEN)) { ev = EV_RARE; break; }
-			sh += e >> 27;                                   // <= 51: the distance may start in nxt
-			lo2 = (sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh);
-			d = DL_AT(lo2);
-			if (d & KD_SPECIAL) { len = e & 0xFFFF; ev = EV_DSPECIAL; break; }
-			const u32 dist = entry_value(d, lo2);
-			sh += d & 31;
-			// the source must exist (Open.java:592-593) and the whole reference fit the tile with the literal guard
-			// kept; tp is advanced first so that the update is in place (the slow path takes it back)
-			const u32 qx = tp + (e << 16);                   // tile address | length << 16 (the kind bits shift out)
-			const int dmax = pos_off + (int)tp;
-			tp += qx >> 16;
-			if ((int)dist > dmax || (int)tp > tguard) { len = qx >> 16; ev = EV_SLOWMATCH; break; }
-			sts_v2(qp, qx, dist);                            // same value from every lane: one broadcast write
-			qp += 8;
-			if ((qp & 0xFF) == 0) { ev = EV_QFULL; break; }
-			NEXT_SYMBOL();
-		}
+		// ---- the hot loop: literals, and length/distance pairs whose reference exists and fits the tile.  Literals are
+		// stored without a capacity check: fewer than LIT_GUARD symbols can start before the next word boundary is
+		// crossed (<= 79 bits at >= 1 bit each), so room for that many is secured once per word (tp <= tguard).
+		u32 ev, d = 0, lo2 = 0;
+		HOT_LOOP();
+		entry = 0;
+		u32 len = e & 0xFFFF;                            // (of a length entry)
 		// ---- events
 		if (ev == EV_RARE) {
-			if (e & K_LENX) { e = lenx_resolve(e, lo); continue; }
+			if (e & K_LENX) { e = lenx_resolve(e, lo); entry = 1; continue; }
 			u32 v = e & 0xFFFF;
 			if (v == V_LONG) {
 				e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
-				if (!(e & K_OTHER)) continue;
+				if (!(e & K_OTHER)) { entry = 1; continue; }
 				v = e & 0xFFFF;
 			}
 			if (v == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
 			SAVE_STATE();
 			return B2D_RESERVED_LENGTH_SYMBOL;
 		}
-		if (ev == EV_SWITCH) { SAVE_STATE(); return R_SWITCH; }
 		if (ev == EV_DSPECIAL) {
 			u32 v = d >> 16;
 			if (v == 0) {
@@ -711,11 +823,17 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			resolve(m, sm, lane);
 			qp = mq_s;
 		}
-		// ---- back to a symbol boundary of the hot loop: window, literal guard, lookup
+		// ---- back to a symbol boundary of the hot loop: window (with the change of line), literal guard
 		while (sh >= 32) {
-			if (widx >= fast_last) { SAVE_STATE(); return R_SWITCH; }
-			sh -= 32; cur = nxt; nxt = pre; widx++;
-			pre = __ldg(words + widx + 2);
+			if (w + 1 == wstop) {
+				if (wstop >= b.n_full) { SAVE_STATE(); return R_SWITCH; }
+				buf = bufn;
+				bufn = LOAD_LINE(wstop + 32);
+				wstop = min(wstop + 32, b.n_full);
+			}
+			w++;
+			sh -= 32; cur = nxt; nxt = pre;
+			pre = __shfl_sync(FULL_MASK, buf, w);
 		}
 		if ((int)tp > tguard) {
 			SAVE_STATE();
@@ -723,14 +841,10 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			LOAD_TILE();
 			if ((int)tp > tguard) { SAVE_STATE(); return R_SWITCH; }         // the member's slot is nearly full: checked path
 		}
-		lo = __funnelshift_r(cur, nxt, sh);
-		e = LL_AT(lo);
 	}
 #undef SAVE_STATE
 #undef LOAD_TILE
-#undef NEXT_SYMBOL
-#undef LL_AT
-#undef DL_AT
+#undef LOAD_LINE
 }
 
 __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const u32 lane) {
@@ -1082,13 +1196,8 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	u64 i0 = in_off[mi], i1 = in_end ? in_end[mi] : in_off[mi + 1];     // in_end: members need not be back to back
 	u64 o0 = out_off[mi], o1 = out_off[mi + 1];
 	const u8 *src = in + i0;
-	u32 lead = (u32)((uintptr_t)src & 3);
 	u64 in_len = i1 > i0 ? i1 - i0 : 0;
-	m.in.words = (const u32 *)(src - lead);
-	m.in.lead8 = lead * 8;
-	m.in.total_bits = in_len * 8;
-	m.in.n_safe = (u32)((lead + in_len + 3) >> 2);
-	m.in.n_full = (u32)((lead + in_len) >> 2);
+	bitin_init(m.in, src, in_len);
 	m.n_full_total = m.in.n_full;
 	m.in_len = in_len;
 	m.hdelta = STREAM && in_host ? (long long)(in_host - in) : 0;
@@ -1177,13 +1286,8 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 	Member m;
 	const u64 i0 = chunk_in_off[c], i1 = chunk_in_off[c + 1];
 	const u8 *src = in + i0;
-	const u32 lead = (u32)((uintptr_t)src & 3);
 	const u64 in_len = i1 - i0;
-	m.in.words = (const u32 *)(src - lead);
-	m.in.lead8 = lead * 8;
-	m.in.total_bits = in_len * 8;
-	m.in.n_safe = (u32)((lead + in_len + 3) >> 2);
-	m.in.n_full = (u32)((lead + in_len) >> 2);
+	bitin_init(m.in, src, in_len);
 	const u32 bit0 = block_bits[u];
 	bit_seek(m.in, bit0 >> 3);
 	m.in.sh += bit0 & 7;
@@ -1328,11 +1432,7 @@ struct StreamResult {
 };
 
 __device__ __forceinline__ void stream_bitin(BitIn &b, const u8 *in, u64 in_len, u64 bit) {
-	b.words = (const u32 *)in;                        // `in` is 4-byte aligned
-	b.lead8 = 0;
-	b.total_bits = in_len * 8;
-	b.n_safe = (u32)((in_len + 3) >> 2);
-	b.n_full = (u32)(in_len >> 2);
+	bitin_init(b, in, in_len);
 	bit_seek(b, bit >> 3);
 	b.sh += (u32)(bit & 7);
 }
