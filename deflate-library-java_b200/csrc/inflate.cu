@@ -316,7 +316,17 @@ struct Member {
 	u64 in_len, staged;  // member bytes; how many of them are in device memory already
 	const u32 *landed;   // device word that turns non-zero once the host's own copy of the member's group has landed
 	u32 n_full_total;    // in.n_full once everything is staged (until then in.n_full only covers the staged bytes)
+#ifdef B2D_PROF
+	long long prof[6];
+#endif
 };
+#ifdef B2D_PROF
+#define PROF_T0() const long long prof_t0 = clock64()
+#define PROF_ADD(m, i) ((m).prof[i] += clock64() - prof_t0)
+#else
+#define PROF_T0()
+#define PROF_ADD(m, i)
+#endif
 
 enum { R_EOB = 0, R_SWITCH = 1000 };
 
@@ -452,6 +462,7 @@ __device__ __noinline__ void drain_records(u64 *glist, u32 gcount, u32 gcap, con
 	__syncwarp();
 }
 __device__ __forceinline__ void resolve(Member &m, const Sm &sm, u32 lane) {
+	PROF_T0();
 	if (m.glist) {
 		// tile address -> position inside the unit: - (window address of tile[0]) + (unit offset of tile[0])
 		drain_records(m.glist, m.gcount, m.gcap, sm.mq, m.nm,
@@ -461,6 +472,7 @@ __device__ __forceinline__ void resolve(Member &m, const Sm &sm, u32 lane) {
 		resolve_pending(sm->tile, sm.mq, m.tile_g, (int)m.tstart, m.nm, lane, (u32)__cvta_generic_to_shared(sm->tile));
 	}
 	m.nm = 0;
+	PROF_ADD(m, 3);
 }
 
 // Host mirror.  Stores from an SM reach pinned host memory at PCIe speed only as whole 128-byte lines (measured with
@@ -534,6 +546,7 @@ __device__ __noinline__ void store_tile(const u8 *tile, u8 *g, u32 lo, u32 hi, u
 // Resolves what is queued, writes the staged bytes out and re-bases the tile at the current output position.
 __device__ __forceinline__ void flush_tile(Member &m, const Sm &sm, u32 lane) {
 	if (m.nm) resolve(m, sm, lane);
+	PROF_T0();
 	store_tile(sm->tile, m.tile_g, m.tstart, m.tpos, lane, m.mdelta);
 	set_tile_origin(m, out_pos(m));
 }
@@ -587,14 +600,24 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 //    it, which keeps the register allocation of the hot loop free of the calls' save/restore traffic.
 //  * decode_block_careful: checks after every field, in the reference's order (Open.java:565-593); used for the
 //    last <= 12 bytes of a member and when the member's output slot is nearly full.
-enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
-
-// The hot loop is written in PTX: every lane of the warp decodes the same symbol, so every branch of the loop is
-// uniform -- which the compiler cannot know (the LUT entries come from shared memory), and it fences each of them with
-// convergence barriers (BSSY / BSYNC / BREAK, BRA.DIV around the shuffle), duplicates induction variables across the
-// nested exits and so spends 15 instructions on a literal, 40 on a length/distance pair and 24 on a window refill.
-// With `bra.uni` the same loop is 11 / 31 / 9.  The block has two entries (look the next symbol up, or dispatch an
-// entry the caller resolved) and leaves with an event code at exactly the states the handlers below expect.
+// The hot loop is written in PTX.  Every lane of the warp decodes the same symbol, so every branch of the loop is
+// uniform -- which the compiler cannot know (the LUT entries come from shared memory): it fences each of them with
+// convergence barriers (BSSY / BSYNC / BREAK), duplicates induction variables across the nested exits and spent 15
+// instructions on a literal, 40 on a length/distance pair and 24 on a window refill; as written here they are 10, 27
+// and 12.  What was measured on the way (tools/loop_bench.py: the loop on synthetic tables, one warp; inflate_probe.py:
+// config 2 with one warp per SM and with all 28):
+//  * a warp on its own pays for PREDICATES, not instructions: a test and the branch (or predicated instruction) that
+//    uses it are 15 cycles apart, so a literal with two branches takes 93 cycles against the 45 of its dependency chain
+//    (LDS 29 + four ALU steps) and a pair with six of them 261;
+//  * looking the next entry up before the branches (speculatively, behind a literal) brings a lone warp's literal to
+//    60 cycles, merged exits and hoisted tests bring a pair to ~215 -- and with 28 warps per SM all of that LOSES: there
+//    the time follows the instruction count (13.4 ms per GiB with this loop, 13.8 - 15.9 with the faster-alone ones),
+//    so the loop is the one with the fewest instructions;
+//  * ptxas "structures" a reducible loop even when every branch is .uni (a BSSY at the top of every trip, all ways back
+//    merged into one BSYNC + BRA): a second, never-taken way into the loop makes it irreducible and is left alone.
+// The block leaves with ev = EV_BOUNDARY (at a symbol boundary; the window may need a word), EV_SYMBOL (E is not a
+// literal or length entry: its bits are skipped, nothing else), EV_PAIR (a pair that needs care: E's and the distance
+// entry's bits are skipped and tp is advanced by the length) or EV_QFULL (the pair took the last slot of the queue).
 #define A_CUR "%0"
 #define A_NXT "%1"
 #define A_PRE "%2"
@@ -603,7 +626,7 @@ enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 #define A_TP "%5"
 #define A_QP "%6"
 #define A_E "%7"
-#define A_LO "%8"
+#define A_LEN "%8"
 #define A_D "%9"
 #define A_LO2 "%10"
 #define A_EV "%11"
@@ -612,7 +635,6 @@ enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 #define A_TGUARD "%14"
 #define A_POSOFF "%15"
 #define A_LLB "%16"
-#define A_ENTRY "%17"
 #define A_REFILL_WORD                                                                   \
 	"add.u32 " A_W ", " A_W ", 1;\n\t"                                                  \
 	"sub.u32 " A_SH ", " A_SH ", 32;\n\t"                                               \
@@ -621,51 +643,69 @@ enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 	"shfl.sync.idx.b32 " A_PRE ", " A_BUF ", " A_W ", 31, 0xffffffff;\n\t"
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
-		".reg .b32 t, u, a, bb, x, dist, qx, len;\n\t"                                  \
-		".reg .pred p, q;\n\t"                                                          \
-		"setp.ne.u32 p, " A_ENTRY ", 0;\n\t"                                            \
-		"@p bra.uni L_DISPATCH;\n"                                                      \
+		".reg .b32 t, u, x, dist, qx, len, dmax;\n\t"                                   \
+		".reg .pred p, pl, plt, p32, pk, pd, pq, ptg;\n\t"                              \
+		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
+		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
+		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
+		"setp.eq.u32 p, " A_LLB ", 0;\n\t"                                              \
+		"@p bra.uni L_MID;\n"                                                           \
 		"L_LOOKUP:\n\t"                                                                 \
-		"shf.r.wrap.b32 " A_LO ", " A_CUR ", " A_NXT ", " A_SH ";\n\t"                  \
-		"shl.b32 t, " A_LO ", 2;\n\t"                                                   \
+		"shf.r.wrap.b32 t, " A_CUR ", " A_NXT ", " A_SH ";\n\t"                         \
 		"lop3.b32 t, t, 0xFFC, " A_LLB ", 0xEA;\n\t"                                    \
-		"ld.shared.u32 " A_E ", [t];\n"                                                 \
-		"L_DISPATCH:\n\t"                                                               \
+		"ld.shared.u32 " A_E ", [t];\n\t"                                               \
+		/* E = the entry of the symbol at SH (< 32) */                                  \
+		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
+		"add.u32 " A_SH ", " A_SH ", t;\n"             /* behind the entry's bits (<= 51) */ \
+		"L_MID:\n\t"                                                                    \
 		"and.b32 t, " A_E ", 0x10000;\n\t"                                              \
-		"setp.eq.u32 p, t, 0;\n\t"                                                      \
-		"@p bra.uni L_NOTLIT;\n\t"                                                      \
-		/* literal: every lane stores the same byte (one broadcast write) */            \
+		"setp.ne.u32 pl, t, 0;\n\t"                                                     \
+		"@!pl bra.uni L_NOTLIT;\n\t"                                                    \
+		/* ---- literal: every lane stores the same byte (one broadcast write) */       \
 		"st.shared.u8 [" A_TP "], " A_E ";\n\t"                                         \
 		"add.u32 " A_TP ", " A_TP ", 1;\n\t"                                            \
-		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
-		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
 		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
 		"@p bra.uni L_LOOKUP;\n\t"                                                      \
-		/* a literal crosses at most one word */                                        \
+		/* it ended in the next word (at most one) */                                   \
 		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
-		"@p bra.uni L_X_BOUNDARY;\n\t"                                                  \
+		"@p bra.uni L_X_BOUNDARY1;\n\t"                                                 \
 		A_REFILL_WORD                                                                   \
 		"setp.gt.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
 		"@!p bra.uni L_LOOKUP;\n\t"                                                     \
-		"bra.uni L_X_BOUNDARY;\n"                                                       \
+		"bra.uni L_X_BOUNDARY1;\n"                                                      \
 		"L_NOTLIT:\n\t"                                                                 \
-		"and.b32 t, " A_E ", 0x20000;\n\t"                                              \
-		"setp.eq.u32 p, t, 0;\n\t"                                                      \
-		"@p bra.uni L_X_RARE;\n\t"                                                      \
-		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
-		"add.u32 " A_SH ", " A_SH ", t;\n\t"           /* <= 51: the distance may start in nxt */ \
+		/* ---- length/distance pair.  A test and the branch (or predicated instruction) that uses it are   \
+		   15 cycles apart for a lone warp: every test is issued as early as its inputs allow, its user     \
+		   late, with independent work in between. */                                   \
 		"and.b32 t, " A_SH ", 32;\n\t"                                                  \
-		"setp.ne.u32 p, t, 0;\n\t"                                                      \
-		"selp.b32 a, " A_NXT ", " A_CUR ", p;\n\t"                                      \
-		"selp.b32 bb, " A_PRE ", " A_NXT ", p;\n\t"                                     \
-		"shf.r.wrap.b32 " A_LO2 ", a, bb, " A_SH ";\n\t"                                \
+		"setp.ne.u32 p32, t, 0;\n\t"                                                    \
+		"and.b32 t, " A_E ", 0x20000;\n\t"                                              \
+		"setp.eq.u32 pk, t, 0;\n\t"                    /* not a length entry */         \
+		/* queued form: tile address | length << 16 (the kind bits shift out) */        \
+		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
+		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
+		"add.s32 dmax, " A_POSOFF ", " A_TP ";\n\t"                                     \
 		"shr.u32 u, " A_LLB ", 2;\n\t"                                                  \
-		"shl.b32 t, " A_LO2 ", 2;\n\t"                                                  \
-		"lop3.b32 t, t, 0x3FC, u, 0xEA;\n\t"                                            \
+		"shr.u32 len, qx, 16;\n\t"                                                      \
+		/* the distance code, wherever it starts */                                     \
+		"@p32 shf.r.wrap.b32 " A_LO2 ", " A_NXT ", " A_PRE ", " A_SH ";\n\t"            \
+		"@!p32 shf.r.wrap.b32 " A_LO2 ", " A_CUR ", " A_NXT ", " A_SH ";\n\t"           \
+		"lop3.b32 t, " A_LO2 ", 0x3FC, u, 0xEA;\n\t"                                    \
 		"ld.shared.u32 " A_D ", [t];\n\t"                                               \
-		"and.b32 t, " A_D ", 0x80;\n\t"                                                 \
-		"setp.ne.u32 p, t, 0;\n\t"                                                      \
-		"@p bra.uni L_X_DSPECIAL;\n\t"                                                  \
+		/* while it is on its way: does the reference fit the tile with the literal guard kept (tp is      \
+		   advanced: the handlers take it back), is this the last free slot of the queue */ \
+		"add.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
+		"add.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
+		"setp.gt.s32 ptg, " A_TP ", " A_TGUARD ";\n\t"                                  \
+		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
+		"setp.eq.u32 pq, t, 0;\n\t"                                                     \
+		"shr.u32 " A_LO2 ", " A_LO2 ", 2;\n\t"         /* the stream's own bits, for the distance's extra bits */ \
+		"@pk bra.uni L_X_SYMBOL;\n\t"                                                   \
+		"and.b32 t, " A_D ", 0x80;\n\t"                /* special: long code, reserved symbol, no distance code */ \
+		"setp.ne.u32 pd, t, 0;\n\t"                                                     \
+		"and.b32 t, " A_D ", 31;\n\t"                                                   \
+		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
+		"setp.lt.u32 plt, " A_SH ", 32;\n\t"                                            \
 		/* dist = base + extra bits (entry_value) */                                    \
 		"shf.l.wrap.b32 x, 0, 0xFFFFFFFF, " A_D ";\n\t"                                 \
 		"lop3.b32 x, " A_LO2 ", x, 0, 0x30;\n\t"                                        \
@@ -673,27 +713,12 @@ enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 		"shf.r.wrap.b32 x, x, 0, t;\n\t"                                                \
 		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
 		"add.u32 dist, t, x;\n\t"                                                       \
-		"and.b32 t, " A_D ", 31;\n\t"                                                   \
-		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
-		/* queued form: tile address | length << 16 (the kind bits shift out); the source must exist    \
-		   (Open.java:592-593) and the whole reference fit the tile with the literal guard kept; tp is  \
-		   advanced first (the slow path takes it back) */                              \
-		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
-		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
-		"add.s32 t, " A_POSOFF ", " A_TP ";\n\t"                                        \
-		"shr.u32 len, qx, 16;\n\t"                                                      \
-		"add.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
-		"setp.gt.s32 p, dist, t;\n\t"                                                   \
-		"setp.gt.s32 q, " A_TP ", " A_TGUARD ";\n\t"                                    \
-		"or.pred p, p, q;\n\t"                                                          \
-		"@p bra.uni L_X_SLOWMATCH;\n\t"                                                 \
-		"st.shared.v2.u32 [" A_QP "], {qx, dist};\n\t"                                  \
-		"add.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
-		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
-		"setp.eq.u32 p, t, 0;\n\t"                                                      \
-		"@p bra.uni L_X_QFULL;\n\t"                                                     \
-		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
-		"@p bra.uni L_LOOKUP;\n"                                                        \
+		"setp.gt.or.s32 ptg, dist, dmax, ptg;\n\t"     /* the source must exist (Open.java:592-593) */ \
+		"@pd bra.uni L_X_DSPECIAL;\n\t"                                                 \
+		"@ptg bra.uni L_X_PAIR;\n\t"                                                    \
+		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t" /* same value from every lane: one broadcast write */ \
+		"@pq bra.uni L_X_QFULL;\n\t"                                                    \
+		"@plt bra.uni L_LOOKUP;\n"                                                      \
 		"L_REFILL2:\n\t"                               /* a pair can cross two words */ \
 		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
 		"@p bra.uni L_X_BOUNDARY;\n\t"                                                  \
@@ -705,27 +730,42 @@ enum { EV_SWITCH = 1, EV_FLUSH, EV_RARE, EV_DSPECIAL, EV_SLOWMATCH, EV_QFULL };
 		"L_X_BOUNDARY:\n\t"                                                             \
 		"mov.u32 " A_EV ", 2;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_RARE:\n\t"                                                                 \
+		"L_X_BOUNDARY1:\n\t"                                                            \
+		"mov.u32 " A_EV ", 2;\n\t"                                                      \
+		"bra.uni L_END;\n"                                                              \
+		"L_X_SYMBOL:\n\t"                              /* (from the literal path nothing is to be taken back) */ \
+		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
+		"sub.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
 		"mov.u32 " A_EV ", 3;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
 		"L_X_DSPECIAL:\n\t"                                                             \
+		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
+		"mov.u32 " A_LEN ", len;\n\t"                                                   \
 		"mov.u32 " A_EV ", 4;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_SLOWMATCH:\n\t"                                                            \
-		"mov.u32 " A_EV ", 5;\n\t"                                                      \
+		"L_X_PAIR:\n\t"                                                                 \
+		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
+		"mov.u32 " A_LEN ", len;\n\t"                                                   \
+		"mov.u32 " A_EV ", 4;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
 		"L_X_QFULL:\n\t"                                                                \
-		"mov.u32 " A_EV ", 6;\n"                                                        \
+		"mov.u32 " A_EV ", 5;\n"                                                        \
 		"L_END:\n\t"                                                                    \
 		"}"                                                                             \
-		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(lo), "+r"(d), "+r"(lo2), "=r"(ev) \
-		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(entry)     \
+		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
+		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb)                \
 		: "memory")
-static_assert(EV_FLUSH == 2 && EV_RARE == 3 && EV_DSPECIAL == 4 && EV_SLOWMATCH == 5 && EV_QFULL == 6, "event codes of HOT_LOOP");
+enum { EV_BOUNDARY = 2, EV_SYMBOL = 3, EV_PAIR = 4, EV_QFULL = 5 };
 
 __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
-	u32 cur = b.cur, nxt = b.nxt, pre = b.pre, sh = b.sh;     // sh < 32, widx + 3 <= n_full
+	// The window holds words of the stream SHIFTED LEFT BY TWO BITS (word k = stream word k << 2 | word k - 1 >> 30):
+	// 32 bits taken from it at a stream position are the stream's bits there times four with two stale bits below,
+	// i.e. a LUT entry's byte offset after one mask -- the lookup's address is funnel shift + LOP3.  The two bits in
+	// front of the member's first word are never looked at.
+	u32 sh = b.sh;                                   // sh < 32, widx + 3 <= n_full
+	u32 cur = __funnelshift_l(b.widx ? load_word(b, b.widx - 1) : 0u, b.cur, 2);
+	u32 nxt = __funnelshift_l(b.cur, b.nxt, 2), pre = __funnelshift_l(b.nxt, b.pre, 2);
 	// The output position is kept as the shared-window ADDRESS of the next tile byte (tp = tile_s + tpos), so a
 	// literal store needs no address arithmetic; limits and the queued references are in the same terms.
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile);
@@ -747,52 +787,73 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 	// not full; there the loop is left with the window untouched (the checked path advances by itself).
 	u32 w = b.widx + 2;
 	u32 wstop, buf, bufn;
-#define LOAD_LINE(first) ((first) + lane >= (b.lead8 >> 5) && (first) + lane < b.n_full ? __ldg(b.words + ((first) + lane)) : 0u)
-	buf = LOAD_LINE(w & ~31u);
-	bufn = LOAD_LINE((w & ~31u) + 32);
+	// (the next line is kept as it was loaded, this lane's word and the one in front of it, and only shifted when its turn
+	// comes: shifting it at once would wait for the loads -- 6 % of the kernel when that was tried)
+#define LOAD_RAW(i) ((i) >= (b.lead8 >> 5) && (i) < b.n_full ? __ldg(b.words + (i)) : 0u)
+#define LOAD_NEXT(first) do { bufn_lo = (first) + lane ? LOAD_RAW((first) + lane - 1) : 0u; bufn = LOAD_RAW((first) + lane); } while (0)
+	u32 bufn_lo;
+	LOAD_NEXT(w & ~31u);
+	buf = __funnelshift_l(bufn_lo, bufn, 2);
+	LOAD_NEXT((w & ~31u) + 32);
 	wstop = min((w | 31u) + 1, b.n_full);
-#define SAVE_STATE() do { b.cur = cur; b.nxt = nxt; b.pre = pre; b.widx = w - 2; b.sh = sh; m.tpos = tp - tile_s; \
-                          m.nm = (qp - mq_s) >> 3; } while (0)
+	// before resolve() / flush_tile(): the tile's state; before a return: the bit reader's as well (its own, unshifted words)
+#define SAVE_TILE() do { m.tpos = tp - tile_s; m.nm = (qp - mq_s) >> 3; } while (0)
+#define SAVE_STATE() do { b.widx = w - 2; b.sh = sh; b.cur = load_word(b, b.widx); b.nxt = load_word(b, b.widx + 1); \
+                          b.pre = load_word(b, b.widx + 2); SAVE_TILE(); } while (0)
 #define LOAD_TILE() do { tp = tile_s + m.tpos; tend = tile_s + m.tlimit; qp = mq_s + m.nm * 8; \
                          pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; } while (0)
-	u32 e = 0, lo = 0, entry = 0;
+	u32 e = 0;
 	for (;;) {
 		// ---- the hot loop: literals, and length/distance pairs whose reference exists and fits the tile.  Literals are
 		// stored without a capacity check: fewer than LIT_GUARD symbols can start before the next word boundary is
 		// crossed (<= 79 bits at >= 1 bit each), so room for that many is secured once per word (tp <= tguard).
-		u32 ev, d = 0, lo2 = 0;
+		u32 ev, d = 0, lo2 = 0, len = 0;
+#ifdef B2D_PROF
+		{ const long long t0 = clock64();
 		HOT_LOOP();
-		entry = 0;
-		u32 len = e & 0xFFFF;                            // (of a length entry)
-		// ---- events
-		if (ev == EV_RARE) {
-			if (e & K_LENX) { e = lenx_resolve(e, lo); entry = 1; continue; }
-			u32 v = e & 0xFFFF;
-			if (v == V_LONG) {
-				e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
-				if (!(e & K_OTHER)) { entry = 1; continue; }
-				v = e & 0xFFFF;
-			}
-			if (v == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
-			SAVE_STATE();
-			return B2D_RESERVED_LENGTH_SYMBOL;
-		}
-		if (ev == EV_DSPECIAL) {
-			u32 v = d >> 16;
-			if (v == 0) {
-				d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted);
-				v = (d & KD_SPECIAL) ? d >> 16 : 0;
-			}
-			if (v) {
+		m.prof[5] += clock64() - t0; m.prof[1] += 1; if (ev == EV_SYMBOL) m.prof[4] += 1; }
+#else
+		HOT_LOOP();
+#endif
+		if (ev == EV_SYMBOL) {                               // ---- a rare entry: decoded here
+			sh -= e >> 27;                                   // nothing of it is consumed yet
+			const u32 lo = __funnelshift_r(cur, nxt, sh) >> 2;
+			if (e & K_LENX) e = lenx_resolve(e, lo);
+			else if ((e & 0xFFFF) == V_LONG) e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
+			if (e & K_OTHER) {
+				if ((e & 0xFFFF) == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
 				SAVE_STATE();
-				return v == V_NODIST ? B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE : B2D_RESERVED_DISTANCE_SYMBOL;
+				return B2D_RESERVED_LENGTH_SYMBOL;
 			}
-			sh += d & 31;
-			tp += len;
-			ev = EV_SLOWMATCH;
+			sh += e >> 27;                                   // (<= 51)
+			if (e & K_LIT) {                                 // a literal with a long code
+				sts_u8(tp, e);
+				tp++;
+				ev = EV_BOUNDARY;
+			} else {                                         // a length: the distance lookup of the loop, then as below
+				len = e & 0xFFFF;
+				lo2 = ((sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh)) >> 2;
+				d = lds_u32(quarter(llb) | ((lo2 << 2) & ((4u << D_TB) - 4)));
+				sh += d & 31;
+				tp += len;
+				ev = EV_PAIR;
+			}
 		}
-		if (ev == EV_SLOWMATCH) {
-			tp -= len;                                       // the hot loop had advanced it already
+		if (ev == EV_PAIR) {                                 // ---- a pair that needs care
+			tp -= len;                                       // the loop had advanced it already
+			if (d & KD_SPECIAL) {
+				sh -= d & 31;                                // (what the loop added for the special entry)
+				u32 v = d >> 16;
+				if (v == 0) {
+					d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted);
+					v = (d & KD_SPECIAL) ? d >> 16 : 0;
+				}
+				if (v) {
+					SAVE_STATE();
+					return v == V_NODIST ? B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE : B2D_RESERVED_DISTANCE_SYMBOL;
+				}
+				sh += d & 31;
+			}
 			const u32 dist = entry_value(d, lo2);
 			if ((int)dist > pos_off + (int)tp) {             // Open.java:592-593 (the distance bits stay unconsumed)
 				sh -= d & 31;
@@ -811,15 +872,15 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 					len -= take;
 				}
 				if (len == 0 && (qp & 0xFF) != 0) break;
-				SAVE_STATE();
+				SAVE_TILE();
 				if (len == 0) { resolve(m, sm, lane); qp = mq_s; break; }
 				flush_tile(m, sm, lane);
 				LOAD_TILE();
 				if (tp >= tend) { SAVE_STATE(); return B2D_ERR_OUTPUT_OVERFLOW; }
 			}
 		}
-		if (ev == EV_QFULL) {
-			SAVE_STATE();
+		if (ev == EV_QFULL) {                                // ---- the reference queue is full
+			SAVE_TILE();
 			resolve(m, sm, lane);
 			qp = mq_s;
 		}
@@ -827,8 +888,8 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 		while (sh >= 32) {
 			if (w + 1 == wstop) {
 				if (wstop >= b.n_full) { SAVE_STATE(); return R_SWITCH; }
-				buf = bufn;
-				bufn = LOAD_LINE(wstop + 32);
+				buf = __funnelshift_l(bufn_lo, bufn, 2);
+				LOAD_NEXT(wstop + 32);
 				wstop = min(wstop + 32, b.n_full);
 			}
 			w++;
@@ -836,16 +897,64 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			pre = __shfl_sync(FULL_MASK, buf, w);
 		}
 		if ((int)tp > tguard) {
-			SAVE_STATE();
+			SAVE_TILE();
 			flush_tile(m, sm, lane);
 			LOAD_TILE();
 			if ((int)tp > tguard) { SAVE_STATE(); return R_SWITCH; }         // the member's slot is nearly full: checked path
 		}
 	}
 #undef SAVE_STATE
+#undef SAVE_TILE
+#undef LOAD_RAW
 #undef LOAD_TILE
-#undef LOAD_LINE
+#undef LOAD_NEXT
 }
+
+#ifdef B2D_LOOPBENCH
+// Development aid (tools/variants.py ... loopbench=-DB2D_LOOPBENCH): the symbol loop on synthetic tables, one warp.
+// mode 0: literals of 5 bits; 1: length/distance pairs of 7 + 5 bits; 2: both, chosen by the stream's bits
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) loop_bench_kernel(u32 *out, int mode, int rounds) {
+	__shared__ __align__(1024) u8 smem_raw[SM_BYTES];
+	const u32 lane = threadIdx.x & 31;
+	if (threadIdx.x >= 32) return;
+	const Sm sm = warp_smem(smem_raw, 0);
+	for (u32 i = lane; i < (1u << LL_TB); i += 32) {
+		const bool lit = mode == 0 || (mode == 2 && (__popc(i & 0x1F) & 1));
+		sm.ll[i] = lit ? (5u << 27 | K_LIT | 0x41u) : (7u << 27 | K_LEN | 5u);
+	}
+	for (u32 i = lane; i < (1u << D_TB); i += 32) sm.dl[i] = 4u << 16 | 5u << 8 | 5u;
+	__syncwarp();
+	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile), mq_s = (u32)__cvta_generic_to_shared(sm.mq);
+	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);
+	u32 buf = (lane + 1) * 0x9E3779B9u, cur = 0x12345678u, nxt = 0x9ABCDEF1u, pre = 0x0F1E2D3Cu, sh = 0, w = 2, wstop = 0x7FFFFFF0u;
+	u32 tp = tile_s + 100, qp = mq_s, e = 0;
+	const int tguard = (int)tile_s + 900, pos_off = 1 << 20;
+	long long bytes = 0, events = 0;
+	const long long t0 = clock64();
+	for (int r = 0; r < rounds; r++) {
+		u32 ev, d = 0, lo2 = 0, len = 0;
+		HOT_LOOP();
+		events++;
+		if (ev == EV_QFULL) qp = mq_s;
+		else if (ev != EV_BOUNDARY && ev != EV_PAIR) break;  // (a pair leaving with EV_PAIR ran into the guard: counted as done)
+		while (sh >= 32) { w++; sh -= 32; cur = nxt; nxt = pre; pre = __shfl_sync(FULL_MASK, buf, w); }
+		if ((int)tp > tguard) { bytes += tp - (tile_s + 100); tp = tile_s + 100; }
+	}
+	const long long t1 = clock64();
+	bytes += tp - (tile_s + 100);
+	const long long bits = (long long)(w - 2) * 32 + sh;
+	if (lane == 0) { out[0] = (u32)(t1 - t0); out[1] = (u32)bytes; out[2] = (u32)bits; out[3] = (u32)events; }
+}
+cudaError_t run_loop_bench(int mode, int rounds, uint32_t *out4) {
+	u32 *d = nullptr;
+	cudaError_t e = cudaMalloc(&d, 16);
+	if (e != cudaSuccess) return e;
+	for (int k = 0; k < 2; k++) loop_bench_kernel<<<1, WARPS_PER_CTA * 32>>>(d, mode, rounds);
+	e = cudaMemcpy(out4, d, 16, cudaMemcpyDeviceToHost);
+	cudaFree(d);
+	return e;
+}
+#endif
 
 __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
@@ -1213,6 +1322,10 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	m.glist = nullptr;
 	m.gcount = m.gcap = m.hist_base = 0;
 	m.mdelta = mdelta;
+#ifdef B2D_PROF
+	for (int i = 1; i < 6; i++) m.prof[i] = 0;
+	m.prof[0] = clock64();
+#endif
 	if (lane == 0) { sm->m_out = m.out; sm->m_done = 0; sm->m_prog = progress ? progress + mi : nullptr; }
 	__syncwarp();
 	set_tile_origin(m, 0);
@@ -1235,9 +1348,12 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 			continue;
 		}
 		if (type == 3) { err = B2D_RESERVED_BLOCK_TYPE; break; }          // :96
+		{ PROF_T0();
 		if (type == 1) { if (m.tables != 1) fixed_tables(m, sm, lane); }
 		else { err = dynamic_header(m, sm, avail, lane); if (err) break; }
+		}
 		norm(m.in);
+		PROF_T0();
 		#ifdef B2D_FORCE_CAREFUL
 		int r = R_SWITCH;
 #else
@@ -1248,10 +1364,14 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 			r = (m.in.widx + 3 <= m.in.n_full && m.tpos + LIT_GUARD <= m.tlimit) ? decode_block_fast(m, sm, lane) : (int)R_SWITCH;
 		}
 #endif
-		if (r == R_SWITCH) r = decode_block_careful(m, sm, lane);
+		PROF_ADD(m, 2);
+		if (r == R_SWITCH) { r = decode_block_careful(m, sm, lane); }
 		if (r != R_EOB) { err = r; break; }
 	}
 	flush_tile(m, sm, lane);                                               // also resolves what is pending
+#ifdef B2D_PROF
+	if (mi == 7 && lane == 0) printf("PROF n=%u total %lld entries %lld fast %lld resolve %lld rare %lld inloop %lld\n", n_members, clock64() - m.prof[0], m.prof[1], m.prof[2], m.prof[3], m.prof[4], m.prof[5]);
+#endif
 	if (m.mdelta) mirror_progress(sm.w, m.out + out_pos(m), m.mdelta, true, lane);
 	if (lane == 0) {
 		out_len[mi] = out_pos(m);
@@ -2013,3 +2133,9 @@ cudaError_t launch_inflate(const u8 *d_in, const u64 *d_in_off, u32 n, u8 *d_out
 }
 
 }  // namespace b2d
+
+#ifdef B2D_LOOPBENCH
+extern "C" __attribute__((visibility("default"))) int b2d_loop_bench(int mode, int rounds, uint32_t *out4) {
+	return (int)b2d::run_loop_bench(mode, rounds, out4);
+}
+#endif
