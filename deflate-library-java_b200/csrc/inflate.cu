@@ -94,7 +94,9 @@ static_assert(sizeof(SideSmem) * 4 <= 0x800, "SideSmem area");
 constexpr u32 SM_WINDOW_BASE = INFLATE_SMEM_WINDOW_BASE;
 constexpr int SM_MQ_OFF = 0x400 - 0x400, SM_D_OFF = 0x800 - 0x400, SM_SIDE_OFF = 0x1800 - 0x400, SM_LL_OFF = 0x2000 - 0x400,
               SM_W_OFF = 0x6000 - 0x400;
-constexpr int SM_BYTES = SM_W_OFF + WARPS_PER_CTA * (int)sizeof(WarpSmem);
+constexpr int SM_MEMBER_BYTES = 208;      // a warp's Member (decoder state), see inflate_kernel
+constexpr int SM_M_OFF = SM_W_OFF + WARPS_PER_CTA * (int)sizeof(WarpSmem);
+constexpr int SM_BYTES = SM_M_OFF + WARPS_PER_CTA * SM_MEMBER_BYTES;
 static_assert(7 * (SM_BYTES + 1024) <= 233472, "seven CTAs per SM");
 struct Sm {                               // one warp's view, in registers
 	WarpSmem *w;
@@ -328,6 +330,9 @@ struct Member {
 #define PROF_ADD(m, i)
 #endif
 
+#ifndef B2D_PROF
+static_assert(sizeof(Member) <= SM_MEMBER_BYTES, "Member's place in shared memory");
+#endif
 enum { R_EOB = 0, R_SWITCH = 1000 };
 
 __device__ __forceinline__ u64 out_pos(const Member &m) { return (u64)((long long)(m.tile_g - m.out) + (long long)m.tpos); }
@@ -388,19 +393,26 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 	const int off = (int)((q.x & 0xFFFFu) - qbase), len = (int)(q.x >> 16), dist = (int)q.y;
 	const int s = off - dist;                        // tile index of the source start (may be negative)
 	const bool far = have && (s + len <= ts);        // source lies wholly in global memory (already flushed)
-	// (1) far, short: each lane gathers its own reference with aligned 32-bit loads (only words that hold a needed
-	// byte are touched), shifts the up to 16 bytes into place and stores them byte by byte; all loads are issued
-	// before the first store
+	// (1) short references whose source is final already -- it lies wholly in global memory (far), or wholly in the tile
+	// in front of the first destination of this batch (near, but independent of every queued reference): each lane
+	// gathers its own with aligned 32-bit loads (only words that hold a needed byte are touched), shifts the up to 16
+	// bytes into place and stores them byte by byte; all loads are issued before the first store
+	const int first_dst = __shfl_sync(FULL_MASK, off, 0);
+#ifdef B2D_NO_NEARIND
+	const bool near_ind = false && first_dst;
+#else
+	const bool near_ind = have && !far && len <= 16 && s >= ts && s + len <= first_dst;
+#endif
 	{
-		const bool mine = far && len <= 16;
+		const bool mine_g = far && len <= 16, mine = mine_g || near_ind;
 		if (__any_sync(FULL_MASK, mine)) {
-			const uintptr_t a = (uintptr_t)(tile_g + s);
-			const u32 *wp = (const u32 *)(a & ~(uintptr_t)3);
-			const u32 lead = (u32)(a & 3);
+			const u32 *wp = (const u32 *)(tile_g + (s & ~3));                 // (tile_g is 16-byte aligned, like the tile)
+			const u32 ws = (u32)__cvta_generic_to_shared(tile) + (u32)(s & ~3);
+			const u32 lead = (u32)s & 3;
 			const int nw = mine ? (int)((lead + (u32)len + 3) >> 2) : 0;     // 1..5 words
 			u32 w[5];
 #pragma unroll
-			for (int k = 0; k < 5; k++) w[k] = k < nw ? ldg_u32(wp + k) : 0u;
+			for (int k = 0; k < 5; k++) w[k] = k < nw ? (mine_g ? ldg_u32(wp + k) : lds_u32(ws + 4 * k)) : 0u;
 			u32 v[4];
 #pragma unroll
 			for (int k = 0; k < 4; k++) v[k] = __funnelshift_r(w[k], w[k + 1], lead * 8);
@@ -425,8 +437,9 @@ __device__ __noinline__ void resolve_pending(u8 *tile, const uint2 *mq, u8 *tile
 		}
 	}
 	__syncwarp();
-	// (3) near: source overlaps the tile; strictly in stream order, from shared memory
-	for (u32 mask = __ballot_sync(FULL_MASK, have && !far); mask; mask &= mask - 1) {
+	// (3) the rest: the source overlaps the tile and may be another queued reference's destination; strictly in stream
+	// order, from shared memory
+	for (u32 mask = __ballot_sync(FULL_MASK, have && !far && !near_ind); mask; mask &= mask - 1) {
 		const int j = __ffs(mask) - 1;
 		const int o = __shfl_sync(FULL_MASK, off, j), l = __shfl_sync(FULL_MASK, len, j), d = __shfl_sync(FULL_MASK, dist, j);
 		const int si = o - d;
@@ -1301,7 +1314,11 @@ inflate_kernel(const u8 *__restrict__ in, const u64 *__restrict__ in_off, const 
 	if (mi >= n_members) return;
 	const Sm sm = warp_smem(smem_raw, warp);
 
-	Member m;
+	// The decoder's state lives in shared memory, one copy per warp (every lane reads and writes the same values): as
+	// a local variable it is a copy per LANE in local memory, 6 KB per warp that 28 warps push through what the
+	// shared-memory carve-out leaves of L1 -- every hand-over between the symbol loop and its handlers then waited
+	// for L2.
+	Member &m = *((Member *)(smem_raw + SM_M_OFF) + warp);
 	u64 i0 = in_off[mi], i1 = in_end ? in_end[mi] : in_off[mi + 1];     // in_end: members need not be back to back
 	u64 o0 = out_off[mi], o1 = out_off[mi + 1];
 	const u8 *src = in + i0;
@@ -1403,7 +1420,7 @@ inflate_units_kernel(const u8 *__restrict__ in, const u64 *__restrict__ chunk_in
 	if (pos0 >= out_total) { if (lane == 0) { gcount[u] = 0; ustatus[u] = 0; } return; }
 	const u64 expect = min((u64)block_bytes, out_total - pos0);
 
-	Member m;
+	Member &m = *((Member *)(smem_raw + SM_M_OFF) + warp);       // (in shared memory: see inflate_kernel)
 	const u64 i0 = chunk_in_off[c], i1 = chunk_in_off[c + 1];
 	const u8 *src = in + i0;
 	const u64 in_len = i1 - i0;
@@ -1727,7 +1744,7 @@ stream_units_kernel(const u8 *__restrict__ in, u64 in_len, u32 n_seg, u32 n_unit
 	const u64 start = units[k].start_bit;
 	if (start == NO_START) return;
 	const Sm sm = warp_smem(smem_raw, warp);
-	Member m;
+	Member &m = *((Member *)(smem_raw + SM_M_OFF) + warp);       // (in shared memory: see inflate_kernel)
 	stream_bitin(m.in, in, in_len, start);
 	m.out = planeL + (u64)k * stride + STREAM_WINDOW;
 	m.cap = cap;

@@ -152,6 +152,34 @@ def test_truncations_and_corruptions_match_oracle(b2d, oracle):
     _check_against_oracle(b2d, oracle, members, 8192)
 
 
+def test_members_at_every_phase_of_a_128_byte_line(b2d, oracle):
+    """The symbol loop keeps a 128-byte line of the member's input across the lanes of the warp, numbered from the line
+    of the member's first byte (decode_block_fast, bitin_init): members starting at every byte phase of a line, long
+    enough for several lines and short enough to end inside the first, and cut short at every length around a line's
+    end, must decode like the oracle says."""
+    rng = random.Random(128)
+    text = _text(rng, 9000)
+    body = zlib_raw(text[:6000], 6)                       # ~2.5 KB: some twenty lines
+    short = zlib_raw(text[:40], 6)                        # ends inside its first line
+    stored = zlib_raw(rng.randbytes(700), 0)
+    members, offset = [], 0
+    for phase in range(128):
+        pad = (phase - offset) % 128
+        if pad:
+            members.append(rng.randbytes(pad))            # (garbage: whatever it decodes to, the oracle says the same)
+            offset += pad
+        m = (body, short, stored)[phase % 3] if phase % 5 else body[:len(body) - 1 - phase]
+        members.append(m)
+        offset += len(m)
+    _check_against_oracle(b2d, oracle, members, 8192, flags=b2d.INFLATE_CRC32)
+    # the end of input against the line: every length of the last 300 bytes, at two phases
+    for lead in (0, 77):
+        members = [rng.randbytes(lead)] if lead else []
+        for cut in range(300):
+            members.append(body[:len(body) - cut])
+        _check_against_oracle(b2d, oracle, members, 8192)
+
+
 def test_uncovered_reasons(b2d, oracle):
     bw = BitWriter()
     bw.put(1, 1); bw.put(1, 2); bw.put_code(*fixed_lit_code(257)); bw.put_code(0, 5)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """The deflate pipeline alone on cuda:0: 1 GiB (or --mib) of G_MIXED / G_TEXT resident in HBM, N timed calls of
 b2d_deflate_chunks_dev.  For A/B runs of kernel changes and as the command ncu captures.
-usage: tools/deflate_probe.py [--mib 1024] [--kind mixed|text] [--steps 5] [--split 0]"""
+usage: tools/deflate_probe.py [--mib 1024] [--kind mixed|text] [--steps 5] [--split 0] [--depth 0]"""
 import argparse
 import concurrent.futures as cf
 import ctypes
@@ -18,6 +18,8 @@ ap.add_argument("--mib", type=int, default=1024)
 ap.add_argument("--kind", default="mixed")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--split", type=int, default=0)
+ap.add_argument("--crc", type=int, default=0, help="1: CRC-32 per chunk as well (config 3)")
+ap.add_argument("--depth", type=int, default=0, help="chain depth (0 = the default)")
 a = ap.parse_args()
 b2d = b2d_loader.load()
 b2d.init(0)
@@ -33,11 +35,12 @@ bound = b2d.deflate_bound(n, 1 << 20)
 d_out = torch.empty(bound, dtype=torch.uint8, device="cuda")
 d_tot = torch.zeros(1, dtype=torch.int64, device="cuda")
 d_cl = torch.zeros(n >> 20, dtype=torch.int64, device="cuda")
-opts = b2d.make_opts(chunk_bytes=1 << 20, block_bytes=1 << 16, split_min_bytes=a.split)
+d_crc = torch.zeros(n >> 20, dtype=torch.int32, device="cuda")
+opts = b2d.make_opts(chunk_bytes=1 << 20, block_bytes=1 << 16, split_min_bytes=a.split, chain_depth=a.depth)
 
 
 def run():
-    r = L.b2d_deflate_chunks_dev(d_in.data_ptr(), n, ctypes.byref(opts), d_out.data_ptr(), bound, d_tot.data_ptr(), d_cl.data_ptr(), None, None)
+    r = L.b2d_deflate_chunks_dev(d_in.data_ptr(), n, ctypes.byref(opts), d_out.data_ptr(), bound, d_tot.data_ptr(), d_cl.data_ptr(), ctypes.c_void_p(d_crc.data_ptr()) if a.crc else None, None)
     assert r == 0, r
 
 
@@ -51,4 +54,4 @@ for _ in range(a.steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
-print(f"deflate {a.kind} {a.mib} MiB: {ms:.3f} ms/call = {n / ms / 1e6:.2f} GB/s, out {int(d_tot.item())} bytes (ratio {n / int(d_tot.item()):.4f})")
+print(f"deflate {a.kind} {a.mib} MiB depth {a.depth}: {ms:.3f} ms/call = {n / ms / 1e6:.2f} GB/s, out {int(d_tot.item())} bytes (ratio {n / int(d_tot.item()):.4f})")
