@@ -44,11 +44,14 @@ constexpr u32 K_LIT = 1u << 16;
 constexpr u32 K_LEN = 1u << 17;
 constexpr u32 K_LENX = 1u << 18;
 constexpr u32 K_OTHER = 1u << 19;
-// distance LUT entry: [4:0] total bits (code + extra)   [7] special   [12:8] code length   [31:16] distance base
-// (the two shift counts sit where a wrap-mode funnel shift can take them straight from the entry)
-constexpr u32 KD_SPECIAL = 1u << 7;       // value 0 = long code, 30/31 = reserved symbol (Open.java:546-551),
+// distance LUT entry: [4:0] total bits (code + extra)   [7] special   [12:8] code length + 2   [31:16] distance base
+// (the two shift counts sit where a wrap-mode funnel shift can take them straight from the entry; the + 2 because the
+// symbol loop's bits come shifted left by two, see decode_block_fast).  The value of a special entry sits where the
+// base does and is at least 0xFF00: the "distance" of such an entry is beyond every valid one, so the symbol loop's
+// test of the distance against the output position (clamped to POS_CLAMP) catches the special entries as well.
+constexpr u32 KD_SPECIAL = 1u << 7;       // value V_DLONG = long code, V_DLONG | 30/31 = reserved symbol (Open.java:546-551),
                                           //       0xFFFF = the block has no distance code (Open.java:398-401)
-constexpr u32 V_EOB = 0, V_LONG = 1, V_NODIST = 0xFFFF;
+constexpr u32 V_EOB = 0, V_LONG = 1, V_NODIST = 0xFFFF, V_DLONG = 0xFF00;
 
 __constant__ u8 CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
@@ -197,16 +200,19 @@ __device__ __forceinline__ u32 lenx_resolve(u32 e, u32 lo) {
 	const u32 eb = (e >> 20) & 7, cl = (e >> 23) & 15;
 	return (e & 0xF8000000u) | K_LEN | ((e & 0xFFFF) + ((lo >> cl) & ((1u << eb) - 1)));
 }
+constexpr int POS_CLAMP = 1 << 15;        // (every valid distance is <= 32768)
 __device__ __forceinline__ u32 d_entry(int sym, int l) {
-	if (sym > 29) return KD_SPECIAL | (u32)sym << 16 | (u32)l << 8 | (u32)l;
+	if (sym > 29) return KD_SPECIAL | (V_DLONG | (u32)sym) << 16 | (u32)(l + 2) << 8 | (u32)l;
 	int base, eb;
 	dist_sym_info(sym, base, eb);
-	return (u32)base << 16 | (u32)l << 8 | (u32)(l + eb);
+	return (u32)base << 16 | (u32)(l + 2) << 8 | (u32)(l + eb);
 }
-// base + extra bits of a distance entry: extra = (lo & ((1 << tot) - 1)) >> clen, with both shift counts read by
-// wrap-mode funnel shifts from the entry itself
-__device__ __forceinline__ u32 entry_value(u32 e, u32 lo) {
-	u32 x = lo & ~__funnelshift_l(0u, 0xFFFFFFFFu, e);
+__device__ __forceinline__ u32 d_code_len(u32 e) { return ((e >> 8) & 31) - 2; }
+// base + extra bits of a distance entry; lo4 = the stream's bits at the code, shifted left by two (the low two bits are
+// anything): extra = (lo4 & ((4 << tot) - 1)) >> (clen + 2), with both shift counts read by wrap-mode funnel shifts
+// from the entry itself
+__device__ __forceinline__ u32 entry_value(u32 e, u32 lo4) {
+	u32 x = lo4 & ~__funnelshift_l(0u, 0xFFFFFFFCu, e);
 	return (e >> 16) + __funnelshift_r(x, 0u, e >> 8);
 }
 
@@ -262,7 +268,7 @@ __device__ int build_code(const u8 *lens, int n, u32 *lut, u16 *sorted, Canon *c
 					for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = ll_entry(i, l, j >> l, TB);
 				}
 			} else {
-				lut[rev & ((1u << TB) - 1)] = IS_DIST ? KD_SPECIAL : ((u32)TB << 27 | K_OTHER | V_LONG);
+				lut[rev & ((1u << TB) - 1)] = IS_DIST ? (KD_SPECIAL | V_DLONG << 16 | 2u << 8) : ((u32)TB << 27 | K_OTHER | V_LONG);
 			}
 		}
 	}
@@ -284,7 +290,7 @@ __device__ __noinline__ u32 slow_decode(u32 lo, const Canon *cn, const u16 *sort
 			return (e & K_LENX) ? lenx_resolve(e, lo) : e;
 		}
 	}
-	return IS_DIST ? (KD_SPECIAL | 31u << 16 | 15u << 8 | 15u) : (15u << 27 | K_OTHER | 287u);   // unreachable for complete codes
+	return IS_DIST ? d_entry(31, 15) : (15u << 27 | K_OTHER | 287u);   // unreachable for complete codes
 }
 
 // Per-member decoder state.  Output goes through a TILE-byte staging tile in shared memory: tile[i] holds the
@@ -345,7 +351,7 @@ __device__ __forceinline__ void set_tile_origin(Member &m, u64 pos) {
 	u64 room = m.cap - pos;
 	m.tlimit = room >= (u64)(TILE - mis) ? (u32)TILE : mis + (u32)room;
 	long long rel0 = (long long)pos - (long long)mis + (long long)m.hist_base;
-	m.pos_base = rel0 > (1 << 20) ? (1 << 20) : (int)rel0;
+	m.pos_base = rel0 > POS_CLAMP ? POS_CLAMP : (int)rel0;
 }
 
 // shared-memory accesses by 32-bit shared-window address, and plain (L1-cached, coherent) global loads: through a
@@ -648,6 +654,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 #define A_TGUARD "%14"
 #define A_POSOFF "%15"
 #define A_LLB "%16"
+#define A_DLB "%17"
 #define A_REFILL_WORD                                                                   \
 	"add.u32 " A_W ", " A_W ", 1;\n\t"                                                  \
 	"sub.u32 " A_SH ", " A_SH ", 32;\n\t"                                               \
@@ -656,8 +663,8 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 	"shfl.sync.idx.b32 " A_PRE ", " A_BUF ", " A_W ", 31, 0xffffffff;\n\t"
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
-		".reg .b32 t, u, x, dist, qx, len, dmax;\n\t"                                   \
-		".reg .pred p, pl, plt, p32, pk, pd, pq, ptg;\n\t"                              \
+		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                   \
+		".reg .pred p, pl, plt, p32, pk, pq, ptg;\n\t"                              \
 		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
 		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
 		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
@@ -698,12 +705,11 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
 		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
 		"add.s32 dmax, " A_POSOFF ", " A_TP ";\n\t"                                     \
-		"shr.u32 u, " A_LLB ", 2;\n\t"                                                  \
 		"shr.u32 len, qx, 16;\n\t"                                                      \
 		/* the distance code, wherever it starts */                                     \
 		"@p32 shf.r.wrap.b32 " A_LO2 ", " A_NXT ", " A_PRE ", " A_SH ";\n\t"            \
 		"@!p32 shf.r.wrap.b32 " A_LO2 ", " A_CUR ", " A_NXT ", " A_SH ";\n\t"           \
-		"lop3.b32 t, " A_LO2 ", 0x3FC, u, 0xEA;\n\t"                                    \
+		"lop3.b32 t, " A_LO2 ", 0x3FC, " A_DLB ", 0xEA;\n\t"                                    \
 		"ld.shared.u32 " A_D ", [t];\n\t"                                               \
 		/* while it is on its way: does the reference fit the tile with the literal guard kept (tp is      \
 		   advanced: the handlers take it back), is this the last free slot of the queue */ \
@@ -712,22 +718,20 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"setp.gt.s32 ptg, " A_TP ", " A_TGUARD ";\n\t"                                  \
 		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
 		"setp.eq.u32 pq, t, 0;\n\t"                                                     \
-		"shr.u32 " A_LO2 ", " A_LO2 ", 2;\n\t"         /* the stream's own bits, for the distance's extra bits */ \
 		"@pk bra.uni L_X_SYMBOL;\n\t"                                                   \
-		"and.b32 t, " A_D ", 0x80;\n\t"                /* special: long code, reserved symbol, no distance code */ \
-		"setp.ne.u32 pd, t, 0;\n\t"                                                     \
 		"and.b32 t, " A_D ", 31;\n\t"                                                   \
 		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
 		"setp.lt.u32 plt, " A_SH ", 32;\n\t"                                            \
 		/* dist = base + extra bits (entry_value) */                                    \
-		"shf.l.wrap.b32 x, 0, 0xFFFFFFFF, " A_D ";\n\t"                                 \
+		"shf.l.wrap.b32 x, 0, 0xFFFFFFFC, " A_D ";\n\t"                                 \
 		"lop3.b32 x, " A_LO2 ", x, 0, 0x30;\n\t"                                        \
 		"shr.u32 t, " A_D ", 8;\n\t"                                                    \
 		"shf.r.wrap.b32 x, x, 0, t;\n\t"                                                \
 		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
 		"add.u32 dist, t, x;\n\t"                                                       \
-		"setp.gt.or.s32 ptg, dist, dmax, ptg;\n\t"     /* the source must exist (Open.java:592-593) */ \
-		"@pd bra.uni L_X_DSPECIAL;\n\t"                                                 \
+		/* the source must exist (Open.java:592-593); a special entry (long code, reserved symbol, no      \
+		   distance code) has a "distance" beyond every valid one */                    \
+		"setp.gt.or.s32 ptg, dist, dmax, ptg;\n\t"                                      \
 		"@ptg bra.uni L_X_PAIR;\n\t"                                                    \
 		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t" /* same value from every lane: one broadcast write */ \
 		"@pq bra.uni L_X_QFULL;\n\t"                                                    \
@@ -738,8 +742,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		A_REFILL_WORD                                                                   \
 		"setp.ge.u32 p, " A_SH ", 32;\n\t"                                              \
 		"@p bra.uni L_REFILL2;\n\t"                                                     \
-		"setp.gt.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
-		"@!p bra.uni L_LOOKUP;\n"                                                       \
+		"bra.uni L_LOOKUP;\n"                           /* (the pair has kept the literal guard itself) */ \
 		"L_X_BOUNDARY:\n\t"                                                             \
 		"mov.u32 " A_EV ", 2;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
@@ -751,11 +754,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"sub.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
 		"mov.u32 " A_EV ", 3;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_DSPECIAL:\n\t"                                                             \
-		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
-		"mov.u32 " A_LEN ", len;\n\t"                                                   \
-		"mov.u32 " A_EV ", 4;\n\t"                                                      \
-		"bra.uni L_END;\n"                                                              \
 		"L_X_PAIR:\n\t"                                                                 \
 		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
 		"mov.u32 " A_LEN ", len;\n\t"                                                   \
@@ -766,7 +764,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"L_END:\n\t"                                                                    \
 		"}"                                                                             \
 		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
-		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb)                \
+		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(llb >> 2) \
 		: "memory")
 enum { EV_BOUNDARY = 2, EV_SYMBOL = 3, EV_PAIR = 4, EV_QFULL = 5 };
 
@@ -845,8 +843,8 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 				ev = EV_BOUNDARY;
 			} else {                                         // a length: the distance lookup of the loop, then as below
 				len = e & 0xFFFF;
-				lo2 = ((sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh)) >> 2;
-				d = lds_u32(quarter(llb) | ((lo2 << 2) & ((4u << D_TB) - 4)));
+				lo2 = (sh & 32) ? __funnelshift_r(nxt, pre, sh) : __funnelshift_r(cur, nxt, sh);
+				d = lds_u32(quarter(llb) | (lo2 & ((4u << D_TB) - 4)));
 				sh += d & 31;
 				tp += len;
 				ev = EV_PAIR;
@@ -857,8 +855,8 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 			if (d & KD_SPECIAL) {
 				sh -= d & 31;                                // (what the loop added for the special entry)
 				u32 v = d >> 16;
-				if (v == 0) {
-					d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted);
+				if (v == V_DLONG) {
+					d = slow_decode<D_TB, true>(lo2 >> 2, &sm.side->d_canon, sm.side->d_sorted);
 					v = (d & KD_SPECIAL) ? d >> 16 : 0;
 				}
 				if (v) {
@@ -935,7 +933,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) loop_bench_ke
 		const bool lit = mode == 0 || (mode == 2 && (__popc(i & 0x1F) & 1));
 		sm.ll[i] = lit ? (5u << 27 | K_LIT | 0x41u) : (7u << 27 | K_LEN | 5u);
 	}
-	for (u32 i = lane; i < (1u << D_TB); i += 32) sm.dl[i] = 4u << 16 | 5u << 8 | 5u;
+	for (u32 i = lane; i < (1u << D_TB); i += 32) sm.dl[i] = 4u << 16 | 7u << 8 | 5u;
 	__syncwarp();
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile), mq_s = (u32)__cvta_generic_to_shared(sm.mq);
 	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);
@@ -1057,16 +1055,16 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 		if (d & KD_SPECIAL) {
 			const u32 v = d >> 16;
 			if (v == V_NODIST) { ret = B2D_LENGTH_ENCOUNTERED_WITH_EMPTY_DISTANCE_CODE; break; }
-			if (v == 0) { d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted); goto dispatch_d; }
-			if (CAREFUL && (int)((d >> 8) & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if (v == V_DLONG) { d = slow_decode<D_TB, true>(lo2, &sm.side->d_canon, sm.side->d_sorted); goto dispatch_d; }
+			if (CAREFUL && (int)d_code_len(d) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			ret = B2D_RESERVED_DISTANCE_SYMBOL;
 			break;
 		}
 		if (CAREFUL) {
-			if ((int)((d >> 8) & 31) > avail || (int)(d & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
+			if ((int)d_code_len(d) > avail || (int)(d & 31) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			avail -= d & 31;
 		}
-		const u32 dist = entry_value(d, lo2);
+		const u32 dist = entry_value(d, lo2 << 2);
 		sh += d & 31;
 		// common case: the source exists (Open.java:592-593) and the whole reference fits the tile
 		if ((int)dist <= pos_base + (int)tpos && (int)(tpos + len) <= (CAREFUL ? (int)tlimit : tguard)) {
@@ -1270,7 +1268,7 @@ __device__ int dynamic_header(Member &m, const Sm &sm, int &avail, u32 lane) {
 	u8 *dl = sm->lens + num_ll;
 	if (num_d == 1 && dl[0] == 0) {
 		// no distance code: any length symbol is an error (:526-527,578-579), reported by the distance lookup
-		for (int i = lane; i < (1 << D_TB); i += 32) sm.dl[i] = KD_SPECIAL | V_NODIST << 16;
+		for (int i = lane; i < (1 << D_TB); i += 32) sm.dl[i] = KD_SPECIAL | V_NODIST << 16 | 2u << 8;
 		__syncwarp();
 	} else {
 		int v = (int)lane < num_d ? dl[lane] : 0;
