@@ -52,6 +52,11 @@ constexpr u32 K_OTHER = 1u << 19;
 constexpr u32 KD_SPECIAL = 1u << 7;       // value V_DLONG = long code, V_DLONG | 30/31 = reserved symbol (Open.java:546-551),
                                           //       0xFFFF = the block has no distance code (Open.java:398-401)
 constexpr u32 V_EOB = 0, V_LONG = 1, V_NODIST = 0xFFFF, V_DLONG = 0xFF00;
+// Every lit/len entry that is neither a literal nor a resolved length carries V_NOPAIR in its value: taken for a length
+// by the symbol loop, it is longer than the tile and leaves through the exit of the pairs that need care, so the loop
+// does not test the kind of a non-literal entry at all.
+constexpr u32 V_NOPAIR = 0x8000;
+__device__ __forceinline__ u32 ll_value(u32 e) { return e & 0x7FFF; }
 
 __constant__ u8 CL_ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
@@ -188,17 +193,17 @@ __device__ __forceinline__ int getbits(BitIn &b, int n, int &avail, int &err) {
 // bits when the whole symbol fits the index); TB = index bits, or 0 for an entry made outside the LUT
 __device__ __forceinline__ u32 ll_entry(int sym, int l, u32 idx_hi, int tb) {
 	if (sym < 256) return (u32)l << 27 | K_LIT | (u32)sym;
-	if (sym == 256) return (u32)l << 27 | K_OTHER | V_EOB;
-	if (sym > 285) return (u32)l << 27 | K_OTHER | (u32)sym;
+	if (sym == 256) return (u32)l << 27 | K_OTHER | V_NOPAIR | V_EOB;
+	if (sym > 285) return (u32)l << 27 | K_OTHER | V_NOPAIR | (u32)sym;
 	int base, eb;
 	length_sym_info(sym, base, eb);
 	if (l + eb <= tb) return (u32)(l + eb) << 27 | K_LEN | (u32)(base + (int)(idx_hi & ((1u << eb) - 1)));
-	return (u32)(l + eb) << 27 | (u32)l << 23 | (u32)eb << 20 | K_LENX | (u32)base;
+	return (u32)(l + eb) << 27 | (u32)l << 23 | (u32)eb << 20 | K_LENX | V_NOPAIR | (u32)base;
 }
 // K_LENX -> K_LEN with the extra bits taken from the stream bits `lo` (code at bit 0)
 __device__ __forceinline__ u32 lenx_resolve(u32 e, u32 lo) {
 	const u32 eb = (e >> 20) & 7, cl = (e >> 23) & 15;
-	return (e & 0xF8000000u) | K_LEN | ((e & 0xFFFF) + ((lo >> cl) & ((1u << eb) - 1)));
+	return (e & 0xF8000000u) | K_LEN | (ll_value(e) + ((lo >> cl) & ((1u << eb) - 1)));
 }
 constexpr int POS_CLAMP = 1 << 15;        // (every valid distance is <= 32768)
 __device__ __forceinline__ u32 d_entry(int sym, int l) {
@@ -268,7 +273,7 @@ __device__ int build_code(const u8 *lens, int n, u32 *lut, u16 *sorted, Canon *c
 					for (u32 j = rev; j < (1u << TB); j += 1u << l) lut[j] = ll_entry(i, l, j >> l, TB);
 				}
 			} else {
-				lut[rev & ((1u << TB) - 1)] = IS_DIST ? (KD_SPECIAL | V_DLONG << 16 | 2u << 8) : ((u32)TB << 27 | K_OTHER | V_LONG);
+				lut[rev & ((1u << TB) - 1)] = IS_DIST ? (KD_SPECIAL | V_DLONG << 16 | 2u << 8) : ((u32)TB << 27 | K_OTHER | V_NOPAIR | V_LONG);
 			}
 		}
 	}
@@ -290,7 +295,7 @@ __device__ __noinline__ u32 slow_decode(u32 lo, const Canon *cn, const u16 *sort
 			return (e & K_LENX) ? lenx_resolve(e, lo) : e;
 		}
 	}
-	return IS_DIST ? d_entry(31, 15) : (15u << 27 | K_OTHER | 287u);   // unreachable for complete codes
+	return IS_DIST ? d_entry(31, 15) : (15u << 27 | K_OTHER | V_NOPAIR | 287u);   // unreachable for complete codes
 }
 
 // Per-member decoder state.  Output goes through a TILE-byte staging tile in shared memory: tile[i] holds the
@@ -634,9 +639,9 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 //    so the loop is the one with the fewest instructions;
 //  * ptxas "structures" a reducible loop even when every branch is .uni (a BSSY at the top of every trip, all ways back
 //    merged into one BSYNC + BRA): a second, never-taken way into the loop makes it irreducible and is left alone.
-// The block leaves with ev = EV_BOUNDARY (at a symbol boundary; the window may need a word), EV_SYMBOL (E is not a
-// literal or length entry: its bits are skipped, nothing else), EV_PAIR (a pair that needs care: E's and the distance
-// entry's bits are skipped and tp is advanced by the length) or EV_QFULL (the pair took the last slot of the queue).
+// The block leaves with ev = EV_BOUNDARY (at a symbol boundary; the window may need a word), EV_PAIR (a pair that
+// needs care, or an entry that is neither literal nor length: E's and the distance entry's bits are skipped and tp is
+// advanced by the length) or EV_QFULL (the pair took the last slot of the queue).
 #define A_CUR "%0"
 #define A_NXT "%1"
 #define A_PRE "%2"
@@ -664,7 +669,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
 		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                   \
-		".reg .pred p, pl, plt, p32, pk, pq, ptg;\n\t"                              \
+		".reg .pred p, pl, plt, p32, pq, ptg;\n\t"                              \
 		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
 		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
 		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
@@ -699,8 +704,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		   late, with independent work in between. */                                   \
 		"and.b32 t, " A_SH ", 32;\n\t"                                                  \
 		"setp.ne.u32 p32, t, 0;\n\t"                                                    \
-		"and.b32 t, " A_E ", 0x20000;\n\t"                                              \
-		"setp.eq.u32 pk, t, 0;\n\t"                    /* not a length entry */         \
 		/* queued form: tile address | length << 16 (the kind bits shift out) */        \
 		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
 		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
@@ -718,7 +721,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"setp.gt.s32 ptg, " A_TP ", " A_TGUARD ";\n\t"                                  \
 		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
 		"setp.eq.u32 pq, t, 0;\n\t"                                                     \
-		"@pk bra.uni L_X_SYMBOL;\n\t"                                                   \
 		"and.b32 t, " A_D ", 31;\n\t"                                                   \
 		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
 		"setp.lt.u32 plt, " A_SH ", 32;\n\t"                                            \
@@ -730,7 +732,8 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
 		"add.u32 dist, t, x;\n\t"                                                       \
 		/* the source must exist (Open.java:592-593); a special entry (long code, reserved symbol, no      \
-		   distance code) has a "distance" beyond every valid one */                    \
+		   distance code) has a "distance" beyond every valid one, and an entry that is no length at all   \
+		   (V_NOPAIR) a "length" beyond the tile */                                     \
 		"setp.gt.or.s32 ptg, dist, dmax, ptg;\n\t"                                      \
 		"@ptg bra.uni L_X_PAIR;\n\t"                                                    \
 		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t" /* same value from every lane: one broadcast write */ \
@@ -749,11 +752,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"L_X_BOUNDARY1:\n\t"                                                            \
 		"mov.u32 " A_EV ", 2;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_SYMBOL:\n\t"                              /* (from the literal path nothing is to be taken back) */ \
-		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
-		"sub.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
-		"mov.u32 " A_EV ", 3;\n\t"                                                      \
-		"bra.uni L_END;\n"                                                              \
 		"L_X_PAIR:\n\t"                                                                 \
 		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
 		"mov.u32 " A_LEN ", len;\n\t"                                                   \
@@ -766,7 +764,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
 		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(llb >> 2) \
 		: "memory")
-enum { EV_BOUNDARY = 2, EV_SYMBOL = 3, EV_PAIR = 4, EV_QFULL = 5 };
+enum { EV_BOUNDARY = 2, EV_PAIR = 4, EV_QFULL = 5 };
 
 __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32 lane) {
 	BitIn &b = m.in;
@@ -822,17 +820,19 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 #ifdef B2D_PROF
 		{ const long long t0 = clock64();
 		HOT_LOOP();
-		m.prof[5] += clock64() - t0; m.prof[1] += 1; if (ev == EV_SYMBOL) m.prof[4] += 1; }
+		m.prof[5] += clock64() - t0; m.prof[1] += 1; if (ev == EV_PAIR) m.prof[4] += 1; }
 #else
 		HOT_LOOP();
 #endif
-		if (ev == EV_SYMBOL) {                               // ---- a rare entry: decoded here
+		if (ev == EV_PAIR && !(e & K_LEN)) {                 // ---- not a pair at all but a rare entry: decoded here
+			sh -= d & 31;                                    // (what the loop did with the "distance" behind it)
+			tp -= len;
 			sh -= e >> 27;                                   // nothing of it is consumed yet
 			const u32 lo = __funnelshift_r(cur, nxt, sh) >> 2;
 			if (e & K_LENX) e = lenx_resolve(e, lo);
-			else if ((e & 0xFFFF) == V_LONG) e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
+			else if (ll_value(e) == V_LONG) e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted);
 			if (e & K_OTHER) {
-				if ((e & 0xFFFF) == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
+				if (ll_value(e) == V_EOB) { sh += e >> 27; SAVE_STATE(); return R_EOB; }
 				SAVE_STATE();
 				return B2D_RESERVED_LENGTH_SYMBOL;
 			}
@@ -1034,7 +1034,7 @@ __device__ __noinline__ int decode_block_careful(Member &m, const Sm &sm, const 
 		}
 		if (!(e & K_LEN)) {                                  // rare kinds
 			if (e & K_LENX) { e = lenx_resolve(e, lo); goto dispatch; }
-			const u32 v = e & 0xFFFF;
+			const u32 v = ll_value(e);
 			if (v == V_LONG) { e = slow_decode<LL_TB, false>(lo, &sm.side->ll_canon, sm->ll_sorted); goto dispatch; }
 			if (CAREFUL && (int)(e >> 27) > avail) { ret = B2D_UNEXPECTED_END_OF_STREAM; break; }
 			if (v == V_EOB) { sh += e >> 27; ret = R_EOB; break; }
