@@ -669,7 +669,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
 		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                   \
-		".reg .pred p, pl, plt, p32, pq, ptg;\n\t"                              \
+		".reg .pred p, pl, plt, p32, pok;\n\t"                              \
 		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
 		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
 		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
@@ -718,9 +718,9 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		   advanced: the handlers take it back), is this the last free slot of the queue */ \
 		"add.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
 		"add.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
-		"setp.gt.s32 ptg, " A_TP ", " A_TGUARD ";\n\t"                                  \
 		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
-		"setp.eq.u32 pq, t, 0;\n\t"                                                     \
+		"setp.ne.u32 pok, t, 0;\n\t"                                                    \
+		"setp.le.and.s32 pok, " A_TP ", " A_TGUARD ", pok;\n\t"                         \
 		"and.b32 t, " A_D ", 31;\n\t"                                                   \
 		"add.u32 " A_SH ", " A_SH ", t;\n\t"                                            \
 		"setp.lt.u32 plt, " A_SH ", 32;\n\t"                                            \
@@ -731,13 +731,13 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"shf.r.wrap.b32 x, x, 0, t;\n\t"                                                \
 		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
 		"add.u32 dist, t, x;\n\t"                                                       \
-		/* the source must exist (Open.java:592-593); a special entry (long code, reserved symbol, no      \
+		/* one exit for three reasons (the stub sorts them out).  The source must exist                  \
+		   (Open.java:592-593); a special entry (long code, reserved symbol, no      \
 		   distance code) has a "distance" beyond every valid one, and an entry that is no length at all   \
 		   (V_NOPAIR) a "length" beyond the tile */                                     \
-		"setp.gt.or.s32 ptg, dist, dmax, ptg;\n\t"                                      \
-		"@ptg bra.uni L_X_PAIR;\n\t"                                                    \
+		"setp.le.and.s32 pok, dist, dmax, pok;\n\t"                                     \
+		"@!pok bra.uni L_X_PAIR;\n\t"                                                   \
 		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t" /* same value from every lane: one broadcast write */ \
-		"@pq bra.uni L_X_QFULL;\n\t"                                                    \
 		"@plt bra.uni L_LOOKUP;\n"                                                      \
 		"L_REFILL2:\n\t"                               /* a pair can cross two words */ \
 		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
@@ -752,12 +752,16 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"L_X_BOUNDARY1:\n\t"                                                            \
 		"mov.u32 " A_EV ", 2;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_PAIR:\n\t"                                                                 \
+		"L_X_PAIR:\n\t"                                /* which of the three was it? */ \
+		"setp.le.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
+		"setp.le.and.s32 p, dist, dmax, p;\n\t"                                         \
+		"@p bra.uni L_X_QFULL;\n\t"                                                     \
 		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
 		"mov.u32 " A_LEN ", len;\n\t"                                                   \
 		"mov.u32 " A_EV ", 4;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_QFULL:\n\t"                                                                \
+		"L_X_QFULL:\n\t"                               /* only the queue: the pair is done, it took the last slot */ \
+		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t"                               \
 		"mov.u32 " A_EV ", 5;\n"                                                        \
 		"L_END:\n\t"                                                                    \
 		"}"                                                                             \

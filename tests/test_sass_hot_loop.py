@@ -40,7 +40,7 @@ def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
     start = hits[0] - 3
     # the loop and its exits end where the pairs that need care load their event code (EV_PAIR, 4)
     sts64 = next(i for i in range(start, len(sass)) if sass[i].startswith("STS.64"))
-    end = next(i for i in range(sts64, len(sass)) if re.match(r"(IMAD\.MOV\.U32|MOV) R\d+, (RZ, RZ, )?0x4$", sass[i]))
+    end = next(i for i in range(sts64, len(sass)) if re.match(r"(@!?P\d\s+)?(IMAD\.MOV\.U32|MOV) R\d+, (RZ, RZ, )?0x4$", sass[i]))
     body = sass[start:end]
     assert 60 < len(body) < 90, len(body)
     # the table lookups (lit/len, distance), the literal store, the queue store and the two refills from the lanes' line
