@@ -373,6 +373,7 @@ __device__ __forceinline__ u32 quarter(u32 a) {
 	asm volatile("shr.u32 %0, %1, 2;" : "=r"(r) : "r"(a));
 	return r;
 }
+__device__ __forceinline__ void sts_u32(u32 a, u32 v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_u8(u32 a, u32 v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts_v2(u32 a, u32 x, u32 y) {
 	asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(x), "r"(y) : "memory");
@@ -661,11 +662,11 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 #define A_LLB "%16"
 #define A_DLB "%17"
 #define A_REFILL_WORD                                                                   \
-	"add.u32 " A_W ", " A_W ", 1;\n\t"                                                  \
+	"add.u32 " A_W ", " A_W ", 4;\n\t"                                                  \
 	"sub.u32 " A_SH ", " A_SH ", 32;\n\t"                                               \
 	"mov.b32 " A_CUR ", " A_NXT ";\n\t"                                                 \
 	"mov.b32 " A_NXT ", " A_PRE ";\n\t"                                                 \
-	"shfl.sync.idx.b32 " A_PRE ", " A_BUF ", " A_W ", 31, 0xffffffff;\n\t"
+	"ld.shared.u32 " A_PRE ", [" A_W "];\n\t"
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
 		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                   \
@@ -765,8 +766,8 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"mov.u32 " A_EV ", 5;\n"                                                        \
 		"L_END:\n\t"                                                                    \
 		"}"                                                                             \
-		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(w), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
-		: "r"(buf), "r"(wstop - 1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(llb >> 2) \
+		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(wa), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
+		: "r"(0), "r"(line_s + (wstop - 1 - line_first) * 4), "r"(tguard), "r"(pos_off), "r"(llb), "r"(llb >> 2) \
 		: "memory")
 enum { EV_BOUNDARY = 2, EV_PAIR = 4, EV_QFULL = 5 };
 
@@ -791,27 +792,32 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 	int pos_off = m.pos_base - (int)tile_s;          // output position of the byte at tp = pos_off + tp
 	u32 qp = mq_s + m.nm * 8;                        // next free slot of the reference queue (256 B, 256-aligned:
 	                                                 // full when the next slot's address wraps to 0 mod 256)
-	// Input: the 32 lanes hold one 128-byte line of the member each way (buf = the line of the word in `pre`, bufn =
-	// the line behind it, loaded a whole line ahead with one coalesced request), and a refill takes its word from the
-	// lane that has it: no load instruction, no address arithmetic and no memory latency on the refill path.  b.words is
-	// 128-byte aligned (bitin_init), so word numbers are line-relative as they are; w = the number of the word in `pre`.
-	// The three buffered words must stay real input, so only full words (all of them staged) are ever fetched: wstop,
-	// the next number that needs a decision, is the nearer of the next line's first word and the first word that is
-	// not full; there the loop is left with the window untouched (the checked path advances by itself).
-	u32 w = b.widx + 2;
-	u32 wstop, buf, bufn;
+	// Input: the 128-byte line of the member that holds the word in `pre` sits, shifted, in shared memory (in the code
+	// lengths' place: they are dead once the tables are built), the line behind it is on its way in registers, loaded a
+	// whole line ahead with one coalesced request: a refill is one shared-memory load from an address that moves on by
+	// four -- no global load, no address arithmetic, no memory latency.  (A shuffle from a line held across the lanes
+	// costs two instructions more: ptxas guards it with UMOV + BRA.DIV.)  b.words is 128-byte aligned (bitin_init), so
+	// word numbers are line-relative as they are.  The three buffered words must stay real input, so only full words
+	// (all of them staged) are ever fetched: wstop, the next word number that needs a decision, is the nearer of the
+	// next line's first word and the first word that is not full; there the loop is left with the window untouched
+	// (the checked path advances by itself).
+	const u32 line_s = (u32)__cvta_generic_to_shared(sm->lens);
+	u32 line_first = (b.widx + 2) & ~31u;            // number of the line's first word
+	u32 wa = line_s + (b.widx + 2 - line_first) * 4;  // shared-window address of the word in `pre`
+	u32 wstop, bufn, bufn_lo;
 	// (the next line is kept as it was loaded, this lane's word and the one in front of it, and only shifted when its turn
 	// comes: shifting it at once would wait for the loads -- 6 % of the kernel when that was tried)
 #define LOAD_RAW(i) ((i) >= (b.lead8 >> 5) && (i) < b.n_full ? __ldg(b.words + (i)) : 0u)
 #define LOAD_NEXT(first) do { bufn_lo = (first) + lane ? LOAD_RAW((first) + lane - 1) : 0u; bufn = LOAD_RAW((first) + lane); } while (0)
-	u32 bufn_lo;
-	LOAD_NEXT(w & ~31u);
-	buf = __funnelshift_l(bufn_lo, bufn, 2);
-	LOAD_NEXT((w & ~31u) + 32);
-	wstop = min((w | 31u) + 1, b.n_full);
+#define NEXT_LINE() do { __syncwarp(); sts_u32(line_s + lane * 4, __funnelshift_l(bufn_lo, bufn, 2)); __syncwarp(); } while (0)
+#define WORD_NO() (line_first + ((wa - line_s) >> 2))
+	LOAD_NEXT(line_first);
+	NEXT_LINE();
+	LOAD_NEXT(line_first + 32);
+	wstop = min(line_first + 32, b.n_full);
 	// before resolve() / flush_tile(): the tile's state; before a return: the bit reader's as well (its own, unshifted words)
 #define SAVE_TILE() do { m.tpos = tp - tile_s; m.nm = (qp - mq_s) >> 3; } while (0)
-#define SAVE_STATE() do { b.widx = w - 2; b.sh = sh; b.cur = load_word(b, b.widx); b.nxt = load_word(b, b.widx + 1); \
+#define SAVE_STATE() do { b.widx = WORD_NO() - 2; b.sh = sh; b.cur = load_word(b, b.widx); b.nxt = load_word(b, b.widx + 1); \
                           b.pre = load_word(b, b.widx + 2); SAVE_TILE(); } while (0)
 #define LOAD_TILE() do { tp = tile_s + m.tpos; tend = tile_s + m.tlimit; qp = mq_s + m.nm * 8; \
                          pos_off = m.pos_base - (int)tile_s; tguard = (int)tend - (int)LIT_GUARD; } while (0)
@@ -901,15 +907,17 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 		}
 		// ---- back to a symbol boundary of the hot loop: window (with the change of line), literal guard
 		while (sh >= 32) {
-			if (w + 1 == wstop) {
+			if (WORD_NO() + 1 == wstop) {
 				if (wstop >= b.n_full) { SAVE_STATE(); return R_SWITCH; }
-				buf = __funnelshift_l(bufn_lo, bufn, 2);
-				LOAD_NEXT(wstop + 32);
-				wstop = min(wstop + 32, b.n_full);
+				NEXT_LINE();
+				line_first = wstop;
+				LOAD_NEXT(line_first + 32);
+				wstop = min(line_first + 32, b.n_full);
+				wa = line_s - 4;
 			}
-			w++;
+			wa += 4;
 			sh -= 32; cur = nxt; nxt = pre;
-			pre = __shfl_sync(FULL_MASK, buf, w);
+			pre = lds_u32(wa);
 		}
 		if ((int)tp > tguard) {
 			SAVE_TILE();
@@ -923,6 +931,8 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 #undef LOAD_RAW
 #undef LOAD_TILE
 #undef LOAD_NEXT
+#undef NEXT_LINE
+#undef WORD_NO
 }
 
 #ifdef B2D_LOOPBENCH
@@ -941,23 +951,31 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) loop_bench_ke
 	__syncwarp();
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile), mq_s = (u32)__cvta_generic_to_shared(sm.mq);
 	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);
-	u32 buf = (lane + 1) * 0x9E3779B9u, cur = 0x12345678u, nxt = 0x9ABCDEF1u, pre = 0x0F1E2D3Cu, sh = 0, w = 2, wstop = 0x7FFFFFF0u;
+	const u32 line_s = (u32)__cvta_generic_to_shared(sm->lens), line_first = 0, wstop = 32;
+	sts_u32(line_s + lane * 4, (lane + 1) * 0x9E3779B9u);
+	__syncwarp();
+	u32 cur = 0x12345678u, nxt = 0x9ABCDEF1u, pre = 0x0F1E2D3Cu, sh = 0, wa = line_s, words = 0;
 	u32 tp = tile_s + 100, qp = mq_s, e = 0;
 	const int tguard = (int)tile_s + 900, pos_off = 1 << 20;
 	long long bytes = 0, events = 0;
 	const long long t0 = clock64();
 	for (int r = 0; r < rounds; r++) {
 		u32 ev, d = 0, lo2 = 0, len = 0;
+		const u32 wa0 = wa;
 		HOT_LOOP();
+		words += (wa - wa0) >> 2;
 		events++;
 		if (ev == EV_QFULL) qp = mq_s;
 		else if (ev != EV_BOUNDARY && ev != EV_PAIR) break;  // (a pair leaving with EV_PAIR ran into the guard: counted as done)
-		while (sh >= 32) { w++; sh -= 32; cur = nxt; nxt = pre; pre = __shfl_sync(FULL_MASK, buf, w); }
+		while (sh >= 32) {                                   // (the same line over and over)
+			if (wa + 4 == line_s + 128) wa = line_s - 4;
+			wa += 4; words++; sh -= 32; cur = nxt; nxt = pre; pre = lds_u32(wa);
+		}
 		if ((int)tp > tguard) { bytes += tp - (tile_s + 100); tp = tile_s + 100; }
 	}
 	const long long t1 = clock64();
 	bytes += tp - (tile_s + 100);
-	const long long bits = (long long)(w - 2) * 32 + sh;
+	const long long bits = (long long)words * 32 + sh;
 	if (lane == 0) { out[0] = (u32)(t1 - t0); out[1] = (u32)bytes; out[2] = (u32)bits; out[3] = (u32)events; }
 }
 cudaError_t run_loop_bench(int mode, int rounds, uint32_t *out4) {
