@@ -661,45 +661,39 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 #define A_POSOFF "%15"
 #define A_LLB "%16"
 #define A_DLB "%17"
-#define A_REFILL_WORD                                                                   \
+// One word further: the new word goes into the register that held `cur` (dead now), and the loop goes on in the next
+// phase, where the three window registers have moved on by one role -- no register is moved on a refill.
+#define A_REFILL_INTO(R)                                                                \
 	"add.u32 " A_W ", " A_W ", 4;\n\t"                                                  \
 	"sub.u32 " A_SH ", " A_SH ", 32;\n\t"                                               \
-	"mov.b32 " A_CUR ", " A_NXT ";\n\t"                                                 \
-	"mov.b32 " A_NXT ", " A_PRE ";\n\t"                                                 \
-	"ld.shared.u32 " A_PRE ", [" A_W "];\n\t"
-#define HOT_LOOP()                                                                      \
-	asm volatile("{\n\t"                                                                \
-		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                   \
-		".reg .pred p, pl, plt, p32, pok;\n\t"                              \
-		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
-		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
-		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
-		"setp.eq.u32 p, " A_LLB ", 0;\n\t"                                              \
-		"@p bra.uni L_MID;\n"                                                           \
-		"L_LOOKUP:\n\t"                                                                 \
-		"shf.r.wrap.b32 t, " A_CUR ", " A_NXT ", " A_SH ";\n\t"                         \
+	"ld.shared.u32 " R ", [" A_W "];\n\t"
+// One phase of the loop: C, N, R = the registers that are cur, nxt, pre in it; P, P1, P2 = this phase's label suffix,
+// the next one's and the one after that
+#define HOT_PHASE(P, P1, P2, C, N, R)                                                   \
+		"L_LOOKUP" P ":\n\t"                                                            \
+		"shf.r.wrap.b32 t, " C ", " N ", " A_SH ";\n\t"                                 \
 		"lop3.b32 t, t, 0xFFC, " A_LLB ", 0xEA;\n\t"                                    \
 		"ld.shared.u32 " A_E ", [t];\n\t"                                               \
 		/* E = the entry of the symbol at SH (< 32) */                                  \
 		"shr.u32 t, " A_E ", 27;\n\t"                                                   \
 		"add.u32 " A_SH ", " A_SH ", t;\n"             /* behind the entry's bits (<= 51) */ \
-		"L_MID:\n\t"                                                                    \
+		"L_MID" P ":\n\t"                                                               \
 		"and.b32 t, " A_E ", 0x10000;\n\t"                                              \
 		"setp.ne.u32 pl, t, 0;\n\t"                                                     \
-		"@!pl bra.uni L_NOTLIT;\n\t"                                                    \
+		"@!pl bra.uni L_NOTLIT" P ";\n\t"                                               \
 		/* ---- literal: every lane stores the same byte (one broadcast write) */       \
 		"st.shared.u8 [" A_TP "], " A_E ";\n\t"                                         \
 		"add.u32 " A_TP ", " A_TP ", 1;\n\t"                                            \
 		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
-		"@p bra.uni L_LOOKUP;\n\t"                                                      \
+		"@p bra.uni L_LOOKUP" P ";\n\t"                                                 \
 		/* it ended in the next word (at most one) */                                   \
 		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
-		"@p bra.uni L_X_BOUNDARY1;\n\t"                                                 \
-		A_REFILL_WORD                                                                   \
+		"@p bra.uni L_XB" P ";\n\t"                                                     \
+		A_REFILL_INTO(C)                                                                \
 		"setp.gt.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
-		"@!p bra.uni L_LOOKUP;\n\t"                                                     \
-		"bra.uni L_X_BOUNDARY1;\n"                                                      \
-		"L_NOTLIT:\n\t"                                                                 \
+		"@!p bra.uni L_LOOKUP" P1 ";\n\t"                                               \
+		"bra.uni L_XB" P1 ";\n"                                                         \
+		"L_NOTLIT" P ":\n\t"                                                            \
 		/* ---- length/distance pair.  A test and the branch (or predicated instruction) that uses it are   \
 		   15 cycles apart for a lone warp: every test is issued as early as its inputs allow, its user     \
 		   late, with independent work in between. */                                   \
@@ -711,9 +705,9 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"add.s32 dmax, " A_POSOFF ", " A_TP ";\n\t"                                     \
 		"shr.u32 len, qx, 16;\n\t"                                                      \
 		/* the distance code, wherever it starts */                                     \
-		"@p32 shf.r.wrap.b32 " A_LO2 ", " A_NXT ", " A_PRE ", " A_SH ";\n\t"            \
-		"@!p32 shf.r.wrap.b32 " A_LO2 ", " A_CUR ", " A_NXT ", " A_SH ";\n\t"           \
-		"lop3.b32 t, " A_LO2 ", 0x3FC, " A_DLB ", 0xEA;\n\t"                                    \
+		"@p32 shf.r.wrap.b32 " A_LO2 ", " N ", " R ", " A_SH ";\n\t"                    \
+		"@!p32 shf.r.wrap.b32 " A_LO2 ", " C ", " N ", " A_SH ";\n\t"                   \
+		"lop3.b32 t, " A_LO2 ", 0x3FC, " A_DLB ", 0xEA;\n\t"                            \
 		"ld.shared.u32 " A_D ", [t];\n\t"                                               \
 		/* while it is on its way: does the reference fit the tile with the literal guard kept (tp is      \
 		   advanced: the handlers take it back), is this the last free slot of the queue */ \
@@ -733,27 +727,51 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"shr.u32 t, " A_D ", 16;\n\t"                                                   \
 		"add.u32 dist, t, x;\n\t"                                                       \
 		/* one exit for three reasons (the stub sorts them out).  The source must exist                  \
-		   (Open.java:592-593); a special entry (long code, reserved symbol, no      \
-		   distance code) has a "distance" beyond every valid one, and an entry that is no length at all   \
-		   (V_NOPAIR) a "length" beyond the tile */                                     \
+		   (Open.java:592-593); a special entry (long code, reserved symbol, no distance code) has a       \
+		   "distance" beyond every valid one, and an entry that is no length at all (V_NOPAIR) a "length"   \
+		   beyond the tile */                                                           \
 		"setp.le.and.s32 pok, dist, dmax, pok;\n\t"                                     \
-		"@!pok bra.uni L_X_PAIR;\n\t"                                                   \
+		"@!pok bra.uni L_XP" P ";\n\t"                                                  \
 		"st.shared.v2.u32 [" A_QP "+-8], {qx, dist};\n\t" /* same value from every lane: one broadcast write */ \
-		"@plt bra.uni L_LOOKUP;\n"                                                      \
-		"L_REFILL2:\n\t"                               /* a pair can cross two words */ \
+		"@plt bra.uni L_LOOKUP" P ";\n\t"                                               \
+		/* it ended in the next word, or in the one behind that (the pair has kept the literal guard itself) */ \
 		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
-		"@p bra.uni L_X_BOUNDARY;\n\t"                                                  \
-		A_REFILL_WORD                                                                   \
-		"setp.ge.u32 p, " A_SH ", 32;\n\t"                                              \
-		"@p bra.uni L_REFILL2;\n\t"                                                     \
-		"bra.uni L_LOOKUP;\n"                           /* (the pair has kept the literal guard itself) */ \
-		"L_X_BOUNDARY:\n\t"                                                             \
+		"@p bra.uni L_XB" P ";\n\t"                                                     \
+		A_REFILL_INTO(C)                                                                \
+		"setp.lt.u32 p, " A_SH ", 32;\n\t"                                              \
+		"@p bra.uni L_LOOKUP" P1 ";\n\t"                                                \
+		"setp.eq.u32 p, " A_W ", " A_WSTOP1 ";\n\t"                                     \
+		"@p bra.uni L_XB" P1 ";\n\t"                                                    \
+		A_REFILL_INTO(N)                                                                \
+		"bra.uni L_LOOKUP" P2 ";\n"
+#define HOT_LOOP()                                                                      \
+	asm volatile("{\n\t"                                                                \
+		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                      \
+		".reg .pred p, pl, plt, p32, pok;\n\t"                                          \
+		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
+		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
+		   BSYNC + BRA -- in spite of the .uni on every branch) */                      \
+		"setp.eq.u32 p, " A_LLB ", 0;\n\t"                                              \
+		"@p bra.uni L_MID_0;\n"                                                         \
+		/* three copies of the loop, the window registers one role further in each */   \
+		HOT_PHASE("_0", "_1", "_2", A_CUR, A_NXT, A_PRE)                                \
+		HOT_PHASE("_1", "_2", "_0", A_NXT, A_PRE, A_CUR)                                \
+		HOT_PHASE("_2", "_0", "_1", A_PRE, A_CUR, A_NXT)                                \
+		/* exits: the window back in the roles the caller knows */                      \
+		"L_XB_1:\n\t"                                                                   \
+		"mov.b32 t, " A_CUR ";\n\tmov.b32 " A_CUR ", " A_NXT ";\n\tmov.b32 " A_NXT ", " A_PRE ";\n\tmov.b32 " A_PRE ", t;\n\t" \
+		"bra.uni L_XB_0;\n"                                                             \
+		"L_XB_2:\n\t"                                                                   \
+		"mov.b32 t, " A_PRE ";\n\tmov.b32 " A_PRE ", " A_NXT ";\n\tmov.b32 " A_NXT ", " A_CUR ";\n\tmov.b32 " A_CUR ", t;\n" \
+		"L_XB_0:\n\t"                                                                   \
 		"mov.u32 " A_EV ", 2;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
-		"L_X_BOUNDARY1:\n\t"                                                            \
-		"mov.u32 " A_EV ", 2;\n\t"                                                      \
-		"bra.uni L_END;\n"                                                              \
-		"L_X_PAIR:\n\t"                                /* which of the three was it? */ \
+		"L_XP_1:\n\t"                                                                   \
+		"mov.b32 t, " A_CUR ";\n\tmov.b32 " A_CUR ", " A_NXT ";\n\tmov.b32 " A_NXT ", " A_PRE ";\n\tmov.b32 " A_PRE ", t;\n\t" \
+		"bra.uni L_XP_0;\n"                                                             \
+		"L_XP_2:\n\t"                                                                   \
+		"mov.b32 t, " A_PRE ";\n\tmov.b32 " A_PRE ", " A_NXT ";\n\tmov.b32 " A_NXT ", " A_CUR ";\n\tmov.b32 " A_CUR ", t;\n" \
+		"L_XP_0:\n\t"                                  /* which of the three was it? */ \
 		"setp.le.s32 p, " A_TP ", " A_TGUARD ";\n\t"                                    \
 		"setp.le.and.s32 p, dist, dmax, p;\n\t"                                         \
 		"@p bra.uni L_X_QFULL;\n\t"                                                     \

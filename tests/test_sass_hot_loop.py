@@ -38,15 +38,16 @@ def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
     hits = [i for i, ins in enumerate(sass) if re.match(r"LEA\.HI R\d+, R\d+(\.reuse)?, R\d+, RZ, 0x5$", ins)]
     assert hits, "symbol loop not found"
     start = hits[0] - 3
-    # the loop and its exits end where the pairs that need care load their event code (EV_PAIR, 4)
+    # the loop (three copies of it: the window registers change roles on a refill instead of being moved) and its exits end
+    # where the pairs that need care load their event code (EV_PAIR, 4)
     sts64 = next(i for i in range(start, len(sass)) if sass[i].startswith("STS.64"))
     end = next(i for i in range(sts64, len(sass)) if re.match(r"(@!?P\d\s+)?(IMAD\.MOV\.U32|MOV) R\d+, (RZ, RZ, )?0x4$", sass[i]))
     body = sass[start:end]
-    assert 60 < len(body) < 90, len(body)
-    # the table lookups (lit/len, distance), the two refills from the line of input in shared memory, the literal store
-    # and the queue store are there ...
-    assert sum("LDS R" in ins for ins in body) == 4 and sum("STS.U8" in ins for ins in body) == 1
-    assert sum(ins.startswith("STS.64") for ins in body) == 1
-    # ... and no local memory, no global load, no convergence barrier
+    assert 180 < len(body) < 270, len(body)
+    # per copy: the table lookups (lit/len, distance), three refills from the line of input in shared memory, the literal
+    # store and the queue store are there ...
+    assert sum("LDS R" in ins for ins in body) == 15 and sum("STS.U8" in ins for ins in body) == 3
+    assert sum(ins.startswith("STS.64") for ins in body) == 3
+    # ... and no local memory, no global load, no shuffle, no convergence barrier
     bad = [ins for ins in body if re.search(r"\b(LDL|STL|LDG|SHFL|BSSY|BSYNC|BREAK)\b", ins)]
     assert not bad, bad
