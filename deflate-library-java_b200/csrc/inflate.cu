@@ -784,8 +784,8 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"mov.u32 " A_EV ", 5;\n"                                                        \
 		"L_END:\n\t"                                                                    \
 		"}"                                                                             \
-		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(wa), "+r"(tp), "+r"(qp), "+r"(e), "+r"(len), "+r"(d), "+r"(lo2), "=r"(ev) \
-		: "r"(0), "r"(line_s + (wstop - 1 - line_first) * 4), "r"(tguard), "r"(pos_off), "r"(llb), "r"(llb >> 2) \
+		: "+r"(cur), "+r"(nxt), "+r"(pre), "+r"(sh), "+r"(wa), "+r"(tp), "+r"(qp), "+r"(e), "=r"(len), "=r"(d), "=r"(lo2), "=r"(ev) \
+		: "r"(0), "r"(wa_stop1), "r"(tguard), "r"(pos_off), "r"(llb), "r"(dlb)         \
 		: "memory")
 enum { EV_BOUNDARY = 2, EV_PAIR = 4, EV_QFULL = 5 };
 
@@ -833,6 +833,8 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 	NEXT_LINE();
 	LOAD_NEXT(line_first + 32);
 	wstop = min(line_first + 32, b.n_full);
+	u32 wa_stop1 = line_s + (wstop - 1 - line_first) * 4;    // address of the last word the loop may move on from
+	const u32 dlb = llb >> 2;
 	// before resolve() / flush_tile(): the tile's state; before a return: the bit reader's as well (its own, unshifted words)
 #define SAVE_TILE() do { m.tpos = tp - tile_s; m.nm = (qp - mq_s) >> 3; } while (0)
 #define SAVE_STATE() do { b.widx = WORD_NO() - 2; b.sh = sh; b.cur = load_word(b, b.widx); b.nxt = load_word(b, b.widx + 1); \
@@ -844,7 +846,7 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 		// ---- the hot loop: literals, and length/distance pairs whose reference exists and fits the tile.  Literals are
 		// stored without a capacity check: fewer than LIT_GUARD symbols can start before the next word boundary is
 		// crossed (<= 79 bits at >= 1 bit each), so room for that many is secured once per word (tp <= tguard).
-		u32 ev, d = 0, lo2 = 0, len = 0;
+		u32 ev, d, lo2, len;
 #ifdef B2D_PROF
 		{ const long long t0 = clock64();
 		HOT_LOOP();
@@ -925,12 +927,13 @@ __device__ __noinline__ int decode_block_fast(Member &m, const Sm &sm, const u32
 		}
 		// ---- back to a symbol boundary of the hot loop: window (with the change of line), literal guard
 		while (sh >= 32) {
-			if (WORD_NO() + 1 == wstop) {
+			if (wa == wa_stop1) {
 				if (wstop >= b.n_full) { SAVE_STATE(); return R_SWITCH; }
 				NEXT_LINE();
 				line_first = wstop;
 				LOAD_NEXT(line_first + 32);
 				wstop = min(line_first + 32, b.n_full);
+				wa_stop1 = line_s + (wstop - 1 - line_first) * 4;
 				wa = line_s - 4;
 			}
 			wa += 4;
@@ -969,7 +972,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) loop_bench_ke
 	__syncwarp();
 	const u32 tile_s = (u32)__cvta_generic_to_shared(sm->tile), mq_s = (u32)__cvta_generic_to_shared(sm.mq);
 	const u32 llb = (u32)__cvta_generic_to_shared(sm.ll);
-	const u32 line_s = (u32)__cvta_generic_to_shared(sm->lens), line_first = 0, wstop = 32;
+	const u32 line_s = (u32)__cvta_generic_to_shared(sm->lens), wa_stop1 = line_s + 31 * 4, dlb = llb >> 2;
 	sts_u32(line_s + lane * 4, (lane + 1) * 0x9E3779B9u);
 	__syncwarp();
 	u32 cur = 0x12345678u, nxt = 0x9ABCDEF1u, pre = 0x0F1E2D3Cu, sh = 0, wa = line_s, words = 0;
@@ -978,7 +981,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, CTAS_PER_SM) loop_bench_ke
 	long long bytes = 0, events = 0;
 	const long long t0 = clock64();
 	for (int r = 0; r < rounds; r++) {
-		u32 ev, d = 0, lo2 = 0, len = 0;
+		u32 ev, d, lo2, len;
 		const u32 wa0 = wa;
 		HOT_LOOP();
 		words += (wa - wa0) >> 2;
