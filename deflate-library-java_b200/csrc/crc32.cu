@@ -2,10 +2,11 @@
 //
 // Replaces java.util.zip.CRC32 at the reference's call sites GzipOutputStream.java:25,57,67 and
 // GzipInputStream.java:32,72,83 (the reference itself has no CRC code; it uses the JDK's).
-// One CTA per segment (a gzip member's output, or a 1 MiB chunk of deflate input).  Every thread folds
-// its own run of 16-byte vectors with slice-by-4 tables held in shared memory, then the per-thread CRCs
-// are combined in a log-depth tree with carry-less multiplications by x^(8*bytes) mod P -- the
-// crc32_combine identity crc(A||B) = crc(A)*x^(8|B|) + crc(B) -- so no byte is read twice.
+// One warp per segment (a gzip member's output, or a 1 MiB chunk of deflate input), in persistent CTAs.  Every lane
+// folds its own run of 16-byte vectors with slice-by-4 tables held in shared memory -- a copy per lane, so that no
+// lookup conflicts with another -- then the 32 lane CRCs are combined in a log-depth tree with carry-less
+// multiplications by x^(8*bytes) mod P -- the crc32_combine identity crc(A||B) = crc(A)*x^(8|B|) + crc(B) -- so no
+// byte is read twice.
 #include "common.cuh"
 #include "kernels.h"
 
@@ -70,81 +71,129 @@ __device__ inline u32 dev_x2nmodp(u64 n, unsigned k) {
 	return p;
 }
 
-__device__ __forceinline__ u32 crc_byte(const u32 *T0, u32 c, u32 byte) {
-	return T0[(c ^ byte) & 0xFF] ^ (c >> 8);
+// Slice-by-4 tables, one copy per LANE: TR[(k * 256 + v) * 32 + lane].  With one copy per CTA the 32 lanes of a warp hit
+// the 32 banks at random, 3.2 wavefronts per lookup (ncu: 67 % of the kernel's shared wavefronts were conflicts, stall
+// mio_throttle); here lane l only ever touches bank l.
+constexpr int CRC_WARPS = 32;
+constexpr int CRC_SMEM = 4 * 256 * 32 * 4;            // 128 KiB
+__device__ __forceinline__ u32 tr_at(u32 tr_lane, u32 k, u32 v) {   // tr_lane = shared address of TR + lane * 4
+	u32 r;
+	asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r) : "r"(tr_lane + ((k * 256 + v) << 7)));
+	return r;
 }
-__device__ __forceinline__ u32 crc_word(const u32 *T, u32 c, u32 w) {   // T[k*256 + v] = slice-by-4 tables
+__device__ __forceinline__ u32 crc_byte(u32 tr_lane, u32 c, u32 byte) {
+	return tr_at(tr_lane, 0, (c ^ byte) & 0xFF) ^ (c >> 8);
+}
+__device__ __forceinline__ u32 crc_word(u32 tr_lane, u32 c, u32 w) {
 	c ^= w;
-	return T[768 + (c & 0xFF)] ^ T[512 + ((c >> 8) & 0xFF)] ^ T[256 + ((c >> 16) & 0xFF)] ^ T[c >> 24];
+	return tr_at(tr_lane, 3, c & 0xFF) ^ tr_at(tr_lane, 2, (c >> 8) & 0xFF) ^ tr_at(tr_lane, 1, (c >> 16) & 0xFF) ^ tr_at(tr_lane, 0, c >> 24);
 }
 
-__global__ void __launch_bounds__(CRC_THREADS)
+// One CTA per SM, one WARP per part of a segment at a time (`sub` parts per segment, a power of two: few large
+// segments are shared by several warps so that the machine is full): every lane folds its own run of 16-byte vectors,
+// the 32 lane CRCs are combined in a five-step tree with multiplications by x^(8 * bytes) mod P, the parts' CRCs by
+// the first part's warp.
+__global__ void __launch_bounds__(CRC_WARPS * 32, 1)
 crc32_kernel(const u8 *__restrict__ data, const u64 *__restrict__ off, const u64 *__restrict__ len,
-             u64 total, u64 piece, u32 *__restrict__ crc_out) {
-	__shared__ u32 T[1024];
-	__shared__ u32 part[CRC_THREADS];
-	__shared__ u32 m0_sh;
-	const int t = threadIdx.x;
-	{   // slice-by-4 tables
-		u32 c = (u32)t;
-		for (int k = 0; k < 8; k++) c = (c >> 1) ^ (POLY & (0u - (c & 1u)));
-		T[t] = c;
-		__syncthreads();
-		u32 v = c;
-		for (int k = 1; k < 4; k++) { v = T[v & 0xFF] ^ (v >> 8); T[k * 256 + t] = v; }
-	}
-	u64 s_off, s_len;
-	if (off) { s_off = off[blockIdx.x]; s_len = len[blockIdx.x]; }
-	else { s_off = (u64)blockIdx.x * piece; s_len = total - s_off < piece ? total - s_off : piece; }
-	const u8 *s = data + s_off, *e = s + s_len;
-	const u8 *A = (const u8 *)(((uintptr_t)s + 15) & ~(uintptr_t)15);
-	const u8 *B = (const u8 *)((uintptr_t)e & ~(uintptr_t)15);
-	__syncthreads();
-	if (B <= A) {                                   // tiny segment: one thread, bytewise
-		if (t == 0) {
-			u32 c = 0xFFFFFFFFu;
-			for (const u8 *p = s; p < e; p++) c = crc_byte(T, c, *p);
-			crc_out[blockIdx.x] = ~c;
+             u64 total, u64 piece, u32 n_seg, u32 sub, u32 *__restrict__ crc_out) {
+	extern __shared__ __align__(16) u32 TR[];
+	__shared__ u32 T0[1024];
+	__shared__ u32 part_crc[CRC_WARPS];
+	__shared__ u64 part_len[CRC_WARPS];
+	const u32 t = threadIdx.x, lane = t & 31, warp = t >> 5;
+	{   // slice-by-4 tables, then a copy per lane (written bank by bank)
+		if (t < 256) {
+			u32 c = t;
+			for (int k = 0; k < 8; k++) c = (c >> 1) ^ (POLY & (0u - (c & 1u)));
+			T0[t] = c;
 		}
-		return;
-	}
-	const u64 nv = (u64)(B - A) >> 4;                // 16-byte vectors in the aligned middle
-	const u64 L = (nv + CRC_THREADS - 1) / CRC_THREADS;
-	// pieces are right-aligned: thread t owns vectors [nv - (T-t)L, nv - (T-1-t)L) clipped at 0, so every
-	// non-empty piece except the left-most is full and the combine multipliers are uniform per tree level
-	long long lo = (long long)nv - (long long)(CRC_THREADS - t) * (long long)L;
-	long long hi = lo + (long long)L;
-	const int t0 = CRC_THREADS - (int)((nv + L - 1) / L);   // left-most non-empty thread
-	if (lo < 0) lo = 0;
-	u32 c = 0xFFFFFFFFu;
-	if (t == t0) for (const u8 *p = s; p < A; p++) c = crc_byte(T, c, *p);   // unaligned head joins the first piece
-	if (hi > lo) {
-		const uint4 *v = (const uint4 *)A + lo;
-		for (long long k = 0; k < hi - lo; k++) {
-			uint4 w = __ldg(v + k);
-			c = crc_word(T, c, w.x);
-			c = crc_word(T, c, w.y);
-			c = crc_word(T, c, w.z);
-			c = crc_word(T, c, w.w);
+		__syncthreads();
+		if (t < 256) {
+			u32 v = T0[t];
+			for (u32 k = 1; k < 4; k++) { v = T0[v & 0xFF] ^ (v >> 8); T0[k * 256 + t] = v; }
 		}
-	}
-	part[t] = (t >= t0) ? ~c : 0u;                   // crc of an empty piece is 0
-	if (t == 0) m0_sh = dev_x2nmodp(L * 16, 3);      // x^(8 * bytes per piece)
-	__syncthreads();
-	u32 M = m0_sh;
-	for (int step = 1; step < CRC_THREADS; step <<= 1) {
-		u32 mine = 0;
-		bool act = (t & (2 * step - 1)) == (2 * step - 1);
-		if (act) mine = multmodp(M, part[t - step]) ^ part[t];
 		__syncthreads();
-		if (act) part[t] = mine;
-		M = multmodp(M, M);
+		for (u32 i = t; i < 32768; i += CRC_WARPS * 32) TR[i] = T0[i >> 5];
 		__syncthreads();
 	}
-	if (t == CRC_THREADS - 1) {
-		u32 cc = ~part[t];
-		for (const u8 *p = B; p < e; p++) cc = crc_byte(T, cc, *p);          // unaligned tail continues the state
-		crc_out[blockIdx.x] = ~cc;
+	const u32 tr_lane = (u32)__cvta_generic_to_shared(TR) + lane * 4;
+	u64 last_L = ~0ull;
+	u32 M0 = 0;
+	const u64 n_items = (u64)n_seg * sub;
+	for (u64 base = (u64)blockIdx.x * CRC_WARPS; base < n_items; base += (u64)gridDim.x * CRC_WARPS) {   // (uniform per CTA)
+		const u64 item = base + warp;
+		u32 crc = 0;
+		u64 my_len = 0;
+		const u32 seg = (u32)(item / sub), part_no = (u32)(item % sub);
+		if (item < n_items) {
+			u64 s_off, s_len;
+			if (off) { s_off = off[seg]; s_len = len[seg]; }
+			else { s_off = (u64)seg * piece; s_len = total - s_off < piece ? total - s_off : piece; }
+			const u64 plen = (((s_len + sub - 1) / sub) + 15) & ~(u64)15;          // bytes per part
+			const u64 pa = min(s_len, (u64)part_no * plen), pb = min(s_len, pa + plen);
+			my_len = pb - pa;
+			const u8 *s = data + s_off + pa, *e = data + s_off + pb;
+			const u8 *A = (const u8 *)(((uintptr_t)s + 15) & ~(uintptr_t)15);
+			const u8 *B = (const u8 *)((uintptr_t)e & ~(uintptr_t)15);
+			if (B <= A) {                                   // tiny: one lane, bytewise (every lane: the same result)
+				u32 c = 0xFFFFFFFFu;
+				for (const u8 *p = s; p < e; p++) c = crc_byte(tr_lane, c, *p);
+				crc = my_len ? ~c : 0u;
+			} else {
+				const u64 nv = (u64)(B - A) >> 4;                // 16-byte vectors in the aligned middle
+				const u64 L = (nv + 31) / 32;
+				// pieces are right-aligned: lane l owns vectors [nv - (32 - l) L, nv - (31 - l) L) clipped at 0, so every
+				// non-empty piece except the left-most is full and the combine multipliers are uniform per tree level
+				long long lo = (long long)nv - (long long)(32 - lane) * (long long)L;
+				const long long hi = lo + (long long)L;
+				const u32 l0 = 32 - (u32)((nv + L - 1) / L);     // left-most non-empty lane
+				if (lo < 0) lo = 0;
+				u32 c = 0xFFFFFFFFu;
+				if (lane == l0) for (const u8 *p = s; p < A; p++) c = crc_byte(tr_lane, c, *p);   // unaligned head joins the first piece
+				if (hi > lo) {
+					const uint4 *v = (const uint4 *)A + lo;
+					const long long n = hi - lo;
+					uint4 w0 = __ldg(v), w1 = n > 1 ? __ldg(v + 1) : make_uint4(0, 0, 0, 0);
+					long long k = 0;
+					for (; k + 2 <= n; k += 2) {                 // a whole 32-byte sector per trip, the next one on its way
+						const uint4 a0 = w0, a1 = w1;
+						if (k + 2 < n) w0 = __ldg(v + k + 2);
+						if (k + 3 < n) w1 = __ldg(v + k + 3);
+						c = crc_word(tr_lane, c, a0.x); c = crc_word(tr_lane, c, a0.y); c = crc_word(tr_lane, c, a0.z); c = crc_word(tr_lane, c, a0.w);
+						c = crc_word(tr_lane, c, a1.x); c = crc_word(tr_lane, c, a1.y); c = crc_word(tr_lane, c, a1.z); c = crc_word(tr_lane, c, a1.w);
+					}
+					if (k < n) {
+						c = crc_word(tr_lane, c, w0.x); c = crc_word(tr_lane, c, w0.y); c = crc_word(tr_lane, c, w0.z); c = crc_word(tr_lane, c, w0.w);
+					}
+				}
+				u32 part = (lane >= l0) ? ~c : 0u;              // crc of an empty piece is 0
+				if (L != last_L) { M0 = dev_x2nmodp(L * 16, 3); last_L = L; }   // x^(8 * bytes per piece)
+				u32 M = M0;
+#pragma unroll 1
+				for (u32 step = 1; step < 32; step <<= 1) {
+					const u32 left = __shfl_up_sync(0xFFFFFFFFu, part, step);
+					if ((lane & (2 * step - 1)) == (2 * step - 1)) part = multmodp(M, left) ^ part;
+					M = multmodp(M, M);
+				}
+				u32 cc = ~__shfl_sync(0xFFFFFFFFu, part, 31);
+				for (const u8 *p = B; p < e; p++) cc = crc_byte(tr_lane, cc, *p);      // unaligned tail continues the state
+				crc = ~cc;
+			}
+		}
+		if (sub == 1) {
+			if (item < n_items && lane == 0) crc_out[seg] = crc;
+			continue;
+		}
+		// the parts of a segment sit in neighbouring warps of this CTA: the first one's warp folds them left to right
+		if (lane == 0) { part_crc[warp] = crc; part_len[warp] = my_len; }
+		__syncthreads();
+		if (item < n_items && part_no == 0 && lane == 0) {
+			u32 acc = part_crc[warp];
+			for (u32 j = 1; j < sub; j++)
+				if (part_len[warp + j]) acc = multmodp(dev_x2nmodp(part_len[warp + j], 3), acc) ^ part_crc[warp + j];
+			crc_out[seg] = acc;
+		}
+		__syncthreads();
 	}
 }
 
@@ -172,12 +221,37 @@ static cudaError_t upload_tables() {
 	return e;
 }
 
+// one CTA per SM (fewer when there are fewer than 32 segments per SM); the kernel's 128 KiB of shared memory is opted
+// into once per device
+static cudaError_t crc32_grid(uint32_t n_seg, int *grid, uint32_t *sub) {
+	static int sms[MAX_DEVICES] = {};
+	const int slot = current_device_slot();
+	if (!sms[slot]) {
+		int dev = 0, n = 0;
+		cudaError_t e = cudaGetDevice(&dev);
+		if (e == cudaSuccess) e = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+		if (e == cudaSuccess) e = cudaFuncSetAttribute(crc32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CRC_SMEM);
+		if (e != cudaSuccess) return e;
+		sms[slot] = n > 0 ? n : 1;
+	}
+	// few segments are shared by several warps each (a power of two, so that a segment's parts sit in one CTA)
+	uint32_t s = 1;
+	while (s < 32 && (uint64_t)n_seg * s < (uint64_t)sms[slot] * CRC_WARPS / 2) s <<= 1;
+	*sub = s;
+	const uint64_t want = ((uint64_t)n_seg * s + CRC_WARPS - 1) / CRC_WARPS;
+	*grid = want < (uint64_t)sms[slot] ? (int)want : sms[slot];
+	return cudaSuccess;
+}
+
 cudaError_t launch_crc32_segments(const uint8_t *d_data, const uint64_t *d_off, const uint64_t *d_len,
                                   uint32_t n_seg, uint32_t *d_crc, cudaStream_t st) {
 	if (n_seg == 0) return cudaSuccess;
 	cudaError_t e = upload_tables();
 	if (e != cudaSuccess) return e;
-	B2D_LAUNCH(crc32_kernel, n_seg, CRC_THREADS, 0, st)(d_data, d_off, d_len, 0, 0, d_crc);
+	int grid = 0;
+	uint32_t sub = 1;
+	if ((e = crc32_grid(n_seg, &grid, &sub)) != cudaSuccess) return e;
+	B2D_LAUNCH(crc32_kernel, grid, CRC_WARPS * 32, CRC_SMEM, st)(d_data, d_off, d_len, 0, 0, n_seg, sub, d_crc);
 	return cudaGetLastError();
 }
 
@@ -186,7 +260,10 @@ cudaError_t launch_crc32_pieces(const uint8_t *d_data, uint64_t total, uint64_t 
 	if (n_pieces == 0) return cudaSuccess;
 	cudaError_t e = upload_tables();
 	if (e != cudaSuccess) return e;
-	B2D_LAUNCH(crc32_kernel, n_pieces, CRC_THREADS, 0, st)(d_data, nullptr, nullptr, total, piece, d_crc);
+	int grid = 0;
+	uint32_t sub = 1;
+	if ((e = crc32_grid(n_pieces, &grid, &sub)) != cudaSuccess) return e;
+	B2D_LAUNCH(crc32_kernel, grid, CRC_WARPS * 32, CRC_SMEM, st)(d_data, nullptr, nullptr, total, piece, n_pieces, sub, d_crc);
 	return cudaGetLastError();
 }
 
