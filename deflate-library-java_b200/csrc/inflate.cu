@@ -703,7 +703,6 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"shl.b32 t, " A_E ", 16;\n\t"                                                   \
 		"add.u32 qx, " A_TP ", t;\n\t"                                                  \
 		"add.s32 dmax, " A_POSOFF ", " A_TP ";\n\t"                                     \
-		"shr.u32 len, qx, 16;\n\t"                                                      \
 		/* the distance code, wherever it starts */                                     \
 		"@p32 shf.r.wrap.b32 " A_LO2 ", " N ", " R ", " A_SH ";\n\t"                    \
 		"@!p32 shf.r.wrap.b32 " A_LO2 ", " C ", " N ", " A_SH ";\n\t"                   \
@@ -711,7 +710,8 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"ld.shared.u32 " A_D ", [t];\n\t"                                               \
 		/* while it is on its way: does the reference fit the tile with the literal guard kept (tp is      \
 		   advanced: the handlers take it back), is this the last free slot of the queue */ \
-		"add.u32 " A_TP ", " A_TP ", len;\n\t"                                          \
+		"shr.u32 t, qx, 16;\n\t"                       /* (the length: one LEA.HI with the add) */ \
+		"add.u32 " A_TP ", " A_TP ", t;\n\t"                                            \
 		"add.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
 		"and.b32 t, " A_QP ", 0xFF;\n\t"                                                \
 		"setp.ne.u32 pok, t, 0;\n\t"                                                    \
@@ -746,7 +746,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"bra.uni L_LOOKUP" P2 ";\n"
 #define HOT_LOOP()                                                                      \
 	asm volatile("{\n\t"                                                                \
-		".reg .b32 t, x, dist, qx, len, dmax;\n\t"                                      \
+		".reg .b32 t, x, dist, qx, dmax;\n\t"                                      \
 		".reg .pred p, pl, plt, p32, pok;\n\t"                                          \
 		/* (never taken: a second way into the loop makes it irreducible, which keeps ptxas from        \
 		   "structuring" it -- a BSSY at the top of every trip and all ways back merged into one         \
@@ -776,7 +776,7 @@ __device__ __noinline__ void stage_input(Member &m, u64 upto, u32 lane) {
 		"setp.le.and.s32 p, dist, dmax, p;\n\t"                                         \
 		"@p bra.uni L_X_QFULL;\n\t"                                                     \
 		"sub.u32 " A_QP ", " A_QP ", 8;\n\t"                                            \
-		"mov.u32 " A_LEN ", len;\n\t"                                                   \
+		"shr.u32 " A_LEN ", qx, 16;\n\t"                                                \
 		"mov.u32 " A_EV ", 4;\n\t"                                                      \
 		"bra.uni L_END;\n"                                                              \
 		"L_X_QFULL:\n\t"                               /* only the queue: the pair is done, it took the last slot */ \
