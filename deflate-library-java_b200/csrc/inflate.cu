@@ -8,11 +8,11 @@
 //   decomp/Open.java:705-789  code tree + 9-bit LUT -> build_code(): canonical codes built by the whole warp
 //                                                      into a 10-bit (lit/len) / 8-bit (distance) LUT in shared
 //                                                      memory, longer codes resolved canonically (no tree walk)
-//   decomp/Open.java:438-620  symbol loop + copy    -> decode_block_fast() / decode_block_careful(): every lane decodes
-//                                                      the same symbol from shared tables (no divergence, no
-//                                                      broadcast needed); output is staged in a shared-memory tile,
-//                                                      back-references are queued and resolved 32 at a time by
-//                                                      resolve_pending()
+//   decomp/Open.java:438-620  symbol loop + copy    -> decode_block_fast() (its loop is the PTX block HOT_LOOP) /
+//                                                      decode_block_careful(): every lane decodes the same symbol
+//                                                      from shared tables (no divergence, no broadcast needed);
+//                                                      output is staged in a shared-memory tile, back-references
+//                                                      are queued and resolved 32 at a time by resolve_pending()
 // Results (bytes, out_len, consumed input, status) are identical to the reference's; the validation ORDER of
 // Open.java is kept (first failing check wins).  Not a translation: no dictionary ring (the output buffer plus
 // the staging tile are the window), no code tree, no per-block allocation.
@@ -73,7 +73,8 @@ struct __align__(16) WarpSmem {
 		u16 cl_lut[128];                  // build_code() fills ll_sorted
 		u16 ll_sorted[288];
 	};
-	u8 lens[320];
+	u8 lens[320];                         // code lengths while a block's tables are built; then (its first 128 bytes)
+	                                      // the current line of input of the symbol loop, see decode_block_fast
 	// host mirror (see mirror_progress): the member's output base and how many of its bytes are mirrored already.
 	// Kept here, reachable from the tile pointer, rather than in the Member.
 	u8 *m_out;
