@@ -22,7 +22,10 @@ inline int current_device_slot() {
 // runs a one-warp kernel with the decoder's static shared-memory declaration and reports where the segment starts in the
 // shared window; the decoder's LUT addressing (see inflate.cu) needs it at INFLATE_SMEM_WINDOW_BASE
 constexpr uint32_t INFLATE_SMEM_WINDOW_BASE = 0x400;
-constexpr uint32_t INFLATE_PROGRESS_SHIFT = 15;          // 32 KiB pieces
+#ifndef B2D_PROGRESS_SHIFT
+#define B2D_PROGRESS_SHIFT 15
+#endif
+constexpr uint32_t INFLATE_PROGRESS_SHIFT = B2D_PROGRESS_SHIFT;          // 32 KiB pieces
 cudaError_t probe_inflate_smem_base(uint32_t *base_out, cudaStream_t st);
 cudaError_t launch_inflate(const uint8_t *d_in, const uint64_t *d_in_off, uint32_t n, uint8_t *d_out,
                            const uint64_t *d_out_off, uint64_t *d_out_len, uint64_t *d_in_consumed,
