@@ -1534,8 +1534,8 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 		u8 *ubase = out + pos0;
 		const u64 *list = glist + (u64)u * gcap;
 		const u32 n = gcount[u];
+		u64 rec = lane < n ? list[lane] : 0;
 		for (u32 k = 0; k < n;) {
-			const u64 rec = k + lane < n ? list[k + lane] : 0;
 			const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF, dist = (u32)(rec >> 40);
 			const u32 first = __shfl_sync(FULL_MASK, pos, 0);
 			u8 *g0 = ubase + first;
@@ -1544,6 +1544,8 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 			const bool fits = k + lane < n && (pos + len - first) + mis <= (u32)UNIT_TILE;
 			const u32 okmask = __ballot_sync(FULL_MASK, fits);
 			const u32 cnt = okmask == 0xFFFFFFFFu ? 32u : (u32)(__ffs(~okmask) - 1);
+			// (the records of the next batch are on their way while this one is staged, resolved and stored)
+			const u64 rec_next = k + cnt + lane < n ? list[k + cnt + lane] : 0;
 			const u32 last_end = __shfl_sync(FULL_MASK, pos + len, cnt - 1);
 			const u32 hi = mis + (last_end - first);     // staged: tile[mis, hi) <-> g0 - mis + [mis, hi)
 			u8 *tile_g = g0 - mis;
@@ -1563,6 +1565,7 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 			resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane, 0);
 			store_tile(sm->tile, tile_g, mis, hi, lane, 0);
 			k += cnt;
+			rec = rec_next;
 		}
 	}
 	if (lane == 0) cstatus[c] = err;
