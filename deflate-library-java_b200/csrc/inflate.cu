@@ -1514,16 +1514,71 @@ struct ResolveSmem {
 	__align__(16) u8 tile[UNIT_TILE];
 	uint2 mq[32];
 };
+struct ReplaySmem {
+	__align__(16) u8 tile[2][UNIT_TILE];  // the region of the batch being resolved, and the next batch's on its way
+	uint2 mq[32];
+};
+// a batch of phase B: the references k .. k + cnt - 1 of a unit's list and the region of output they fall into
+struct ReplayBatch {
+	u32 first, mis, cnt, hi;              // staged: tile[mis, hi) <-> tile_g[mis, hi), tile_g 16-byte aligned
+	u8 *tile_g;
+	u32 head, tail;                       // this lane's byte of the region's unaligned ends (stored once the loads are back)
+};
+__device__ __forceinline__ ReplayBatch replay_batch(u64 rec, u32 k, u32 n, u8 *ubase, u32 lane) {
+	ReplayBatch r;
+	const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF;
+	r.first = __shfl_sync(FULL_MASK, pos, 0);
+	u8 *g0 = ubase + r.first;
+	r.mis = (u32)((uintptr_t)g0 & 15);
+	// as many references as fit the staged region (a single one always does: <= 258 bytes)
+	const bool fits = k + lane < n && (pos + len - r.first) + r.mis <= (u32)UNIT_TILE;
+	const u32 okmask = __ballot_sync(FULL_MASK, fits);
+	r.cnt = okmask == 0xFFFFFFFFu ? 32u : (u32)(__ffs(~okmask) - 1);
+	const u32 last_end = __shfl_sync(FULL_MASK, pos + len, r.cnt - 1);
+	r.hi = r.mis + (last_end - r.first);
+	r.tile_g = g0 - r.mis;
+	r.head = r.tail = 0;
+	return r;
+}
+// Stages a batch's region (literals are final, reference bytes are holes that get filled by the replay): the aligned
+// middle with asynchronous 16-byte copies (one commit group), the unaligned ends into registers.
+__device__ __forceinline__ void replay_stage(u8 *tile, ReplayBatch &r, u32 lane) {
+	const u32 a = (r.mis + 15) & ~15u, b = r.hi & ~15u;
+	if (a >= b) {                                   // fewer than 31 bytes: one per lane
+		if (r.mis + lane < r.hi) r.head = r.tile_g[r.mis + lane];
+	} else {
+		if (r.mis + lane < a) r.head = r.tile_g[r.mis + lane];
+		if (b + lane < r.hi) r.tail = r.tile_g[b + lane];
+		const u32 t_s = (u32)__cvta_generic_to_shared(tile);
+		for (u32 v = (a >> 4) + lane; v < (b >> 4); v += 32)
+			asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(t_s + v * 16), "l"(r.tile_g + (size_t)v * 16) : "memory");
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void replay_stage_ends(u8 *tile, const ReplayBatch &r, u32 lane) {
+	const u32 a = (r.mis + 15) & ~15u, b = r.hi & ~15u;
+	if (a >= b) {
+		if (r.mis + lane < r.hi) tile[r.mis + lane] = (u8)r.head;
+	} else {
+		if (r.mis + lane < a) tile[r.mis + lane] = (u8)r.head;
+		if (b + lane < r.hi) tile[b + lane] = (u8)r.tail;
+	}
+}
 
+// Phase B: the lists are replayed in stream order, a batch of up to 32 references and the region of output they fall
+// into at a time.  A batch costs dependent trips to global memory -- its records, its region, its far sources, the
+// store -- and a chunk has thousands of batches on one warp, so the next batch's records (two ahead) and region (one
+// ahead, into a second tile) are fetched while the current batch is resolved and stored.  Regions of consecutive
+// batches are disjoint: nothing the current batch writes is part of what is staged ahead.
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32 *__restrict__ gcount,
                      const int *__restrict__ ustatus, u32 n_chunks, u32 bpc, u32 chunk_bytes, u32 block_bytes, u64 out_total,
                      int *__restrict__ cstatus) {
-	__shared__ ResolveSmem smem[WARPS_PER_CTA];
+	__shared__ ReplaySmem smem[WARPS_PER_CTA];
 	const u32 lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 	const u32 c = blockIdx.x * WARPS_PER_CTA + warp;
 	if (c >= n_chunks) return;
-	ResolveSmem *sm = &smem[warp];
+	ReplaySmem *sm = &smem[warp];
 	int err = 0;
 	for (u32 bi = 0; bi < bpc && err == 0; bi++) {
 		const u32 u = c * bpc + bi;
@@ -1534,38 +1589,32 @@ resolve_units_kernel(u8 *out, const u64 *__restrict__ glist, u32 gcap, const u32
 		u8 *ubase = out + pos0;
 		const u64 *list = glist + (u64)u * gcap;
 		const u32 n = gcount[u];
+		if (n == 0) continue;
+		u32 k = 0, buf = 0;
 		u64 rec = lane < n ? list[lane] : 0;
-		for (u32 k = 0; k < n;) {
-			const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF, dist = (u32)(rec >> 40);
-			const u32 first = __shfl_sync(FULL_MASK, pos, 0);
-			u8 *g0 = ubase + first;
-			const u32 mis = (u32)((uintptr_t)g0 & 15);
-			// as many references as fit the staged region (a single one always does: <= 258 bytes)
-			const bool fits = k + lane < n && (pos + len - first) + mis <= (u32)UNIT_TILE;
-			const u32 okmask = __ballot_sync(FULL_MASK, fits);
-			const u32 cnt = okmask == 0xFFFFFFFFu ? 32u : (u32)(__ffs(~okmask) - 1);
-			// (the records of the next batch are on their way while this one is staged, resolved and stored)
-			const u64 rec_next = k + cnt + lane < n ? list[k + cnt + lane] : 0;
-			const u32 last_end = __shfl_sync(FULL_MASK, pos + len, cnt - 1);
-			const u32 hi = mis + (last_end - first);     // staged: tile[mis, hi) <-> g0 - mis + [mis, hi)
-			u8 *tile_g = g0 - mis;
-			// stage the region (literals are final, reference bytes are holes that get filled now)
-			__syncwarp();
-			{
-				const u32 a = (mis + 15) & ~15u, b = hi & ~15u;
-				if (a >= b) {
-					for (u32 i = mis + lane; i < hi; i += 32) sm->tile[i] = tile_g[i];
-				} else {
-					if (mis + lane < a) sm->tile[mis + lane] = tile_g[mis + lane];
-					for (u32 v = (a >> 4) + lane; v < (b >> 4); v += 32) ((uint4 *)sm->tile)[v] = ((const uint4 *)tile_g)[v];
-					if (b + lane < hi) sm->tile[b + lane] = tile_g[b + lane];
-				}
+		__syncwarp();                                    // (the previous block's last store has read its tile)
+		ReplayBatch cur = replay_batch(rec, 0, n, ubase, lane);
+		replay_stage(sm->tile[0], cur, lane);
+		u64 rec_n = cur.cnt + lane < n ? list[cur.cnt + lane] : 0;
+		while (k < n) {
+			const u32 kn = k + cur.cnt;
+			ReplayBatch nxt = cur;
+			u64 rec_nn = 0;
+			if (kn < n) {                                // the next batch: its region into the other tile, the records behind it
+				nxt = replay_batch(rec_n, kn, n, ubase, lane);
+				replay_stage(sm->tile[buf ^ 1], nxt, lane);
+				rec_nn = kn + nxt.cnt + lane < n ? list[kn + nxt.cnt + lane] : 0;
+				asm volatile("cp.async.wait_group 1;" ::: "memory");     // the current batch's region has landed
+			} else {
+				asm volatile("cp.async.wait_group 0;" ::: "memory");
 			}
-			sm->mq[lane] = make_uint2((mis + (pos - first)) | len << 16, dist);
-			resolve_pending(sm->tile, sm->mq, tile_g, (int)mis, cnt, lane, 0);
-			store_tile(sm->tile, tile_g, mis, hi, lane, 0);
-			k += cnt;
-			rec = rec_next;
+			replay_stage_ends(sm->tile[buf], cur, lane);
+			const u32 pos = (u32)(rec & 0xFFFFFF), len = (u32)(rec >> 24) & 0xFFFF, dist = (u32)(rec >> 40);
+			sm->mq[lane] = make_uint2((cur.mis + (pos - cur.first)) | len << 16, dist);
+			__syncwarp();
+			resolve_pending(sm->tile[buf], sm->mq, cur.tile_g, (int)cur.mis, cur.cnt, lane, 0);
+			store_tile(sm->tile[buf], cur.tile_g, cur.mis, cur.hi, lane, 0);
+			k = kn; rec = rec_n; rec_n = rec_nn; cur = nxt; buf ^= 1;
 		}
 	}
 	if (lane == 0) cstatus[c] = err;
