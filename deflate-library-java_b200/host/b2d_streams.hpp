@@ -255,6 +255,7 @@ public:
 	void close() override {                                                              // :173-179, idempotent
 		if (closed) return;
 		closed = true;
+		if (pending.valid()) pending.wait();            // (a batch on its way still reads the underlying stream)
 		input->close();
 	}
 
@@ -272,25 +273,38 @@ private:
 	uint32_t crc = 0;
 
 	// A stream with a block index is decoded in batches of batchChunks() chunks: while the caller consumes (writes out)
-	// batch k, a second thread already decodes batch k + 1 on the GPU -- the read side of the overlapped file pipeline
-	// (the write side is bin/gzip's).  The compressed input is still read in one go.
+	// batch k, a second thread already reads the compressed bytes of batch k + 1 (the index says how many there are) and
+	// decodes them on the GPU -- the read side of the overlapped file pipeline (the write side is bin/gzip's).
 	static uint32_t batchChunks() {                      // B2D_GUNZIP_BATCH=<chunks per batch> (default 256)
 		static const uint32_t n = getenv("B2D_GUNZIP_BATCH") ? std::max<uint32_t>(1, (uint32_t)strtoul(getenv("B2D_GUNZIP_BATCH"), nullptr, 10)) : 256u;
 		return n;
 	}
-	struct Batch { std::vector<uint8_t> bytes; std::vector<uint32_t> crcs; bool ok = false; std::string error; };
-	std::unique_ptr<PinnedBuffer> batchIn;               // the whole compressed input, kept while batches are pending
+	struct Batch { std::vector<uint8_t> bytes; std::vector<uint32_t> crcs; bool ok = false, truncated = false; std::string error; };
+	std::unique_ptr<PinnedBuffer> batchIn;               // the compressed input read so far, kept while batches are pending
 	std::vector<uint64_t> batchInOff;                    // chunk offsets in it
+	uint64_t batchInFilled = 0;                          // bytes of it that have been read from the underlying stream
 	uint32_t nextChunk = 0;                              // first chunk that is neither delivered nor being decoded
 	uint32_t pendingFirst = 0, pendingCount = 0;
 	std::future<Batch> pending;
 	size_t usableIn = 0;
 
 	bool moreBatches() const { return pending.valid(); }
+	// reads the underlying stream until the first `upTo` compressed bytes are in batchIn; false = the stream ended before
+	bool fillTo(uint64_t upTo) {
+		while (batchInFilled < upTo) {
+			long r = input->read(batchIn->p, (size_t)batchInFilled, (size_t)std::min<uint64_t>(upTo - batchInFilled, 8u << 20));
+			if (r <= 0) return false;
+			batchInFilled += (uint64_t)r;
+		}
+		return true;
+	}
 	Batch decodeBatch(uint32_t c0, uint32_t nb) {
 		Batch r;
 		const uint32_t n = (uint32_t)index.sizes.size();
 		const uint64_t bpc = index.chunk_bytes / index.block_bytes;
+		try {
+			if (!fillTo(batchInOff[c0 + nb])) { r.truncated = true; return r; }
+		} catch (const std::exception &e) { r.error = e.what(); return r; }
 		const uint64_t o0 = (uint64_t)c0 * index.chunk_bytes, o1 = std::min<uint64_t>(sizeHint, (uint64_t)(c0 + nb) * index.chunk_bytes);
 		PinnedBuffer pout;
 		pout.reserve(o1 - o0 + 64);
@@ -319,13 +333,25 @@ private:
 		Batch b = pending.get();
 		if (!b.error.empty()) throw IOException(b.error);
 		const uint32_t c0 = pendingFirst, nb = pendingCount;
+		if (b.truncated) {                              // the stream ends inside this batch: what was delivered stays, then the exception
+			if (!append) { out.clear(); pos = 0; }
+			status = B2D_UNEXPECTED_END_OF_STREAM;
+			consumed = batchInFilled;
+			batchIn.reset();
+			return;
+		}
 		if (!b.ok) {                                    // something unusual in this batch: the rest goes the careful way, chunk by chunk
 			std::vector<uint8_t> keep;
 			if (append) keep.assign(out.begin() + (long)pos, out.end());
 			PinnedBuffer pout;
+			usableIn = fillTo(batchInOff.back()) ? (size_t)batchInOff.back() : (size_t)batchInFilled;
 			decodeIndexedFrom(*batchIn, pout, usableIn, c0, keep);
 			pos = 0;
 			batchIn.reset();
+			if (endExactly && status == 0) {                // Open.finish, Open.java:113-124
+				input->reset();
+				input->skipNBytes(consumed);
+			}
 			return;
 		}
 		for (uint32_t i = 0; i < nb; i++) {
@@ -350,8 +376,9 @@ private:
 		decodeAll();
 		while (moreBatches()) adoptNextBatch(true);
 	}
-	// the batched path applies when the index has block offsets and the exact size is known (what bin/gzip writes)
-	bool startBatches(std::unique_ptr<PinnedBuffer> &pin, size_t in_len) {
+	// the batched path applies when the index has block offsets and the exact size is known (what bin/gzip writes);
+	// it reads the underlying stream itself, batch by batch
+	bool startBatches() {
 		const uint32_t n = (uint32_t)index.sizes.size();
 		if (n <= batchChunks() || index.block_bytes == 0 || sizeHint == 0 || index.chunk_bytes % index.block_bytes != 0) return false;
 		const uint64_t bpc = index.chunk_bytes / index.block_bytes;
@@ -359,9 +386,10 @@ private:
 		if ((uint64_t)n * index.chunk_bytes < sizeHint || (uint64_t)(n - 1) * index.chunk_bytes >= sizeHint) return false;
 		batchInOff.assign(n + 1, 0);
 		for (uint32_t i = 0; i < n; i++) batchInOff[i + 1] = batchInOff[i] + index.sizes[i];
-		if (batchInOff[n] > in_len) return false;
-		batchIn = std::move(pin);
-		usableIn = in_len;
+		batchIn.reset(new PinnedBuffer());
+		batchIn->reserve(batchInOff[n] + 64);
+		batchInFilled = 0;
+		usableIn = (size_t)batchInOff[n];
 		crc = adler ? 1 : 0;
 		nextChunk = 0;
 		launchBatch();
@@ -373,14 +401,14 @@ private:
 		if (decoded) return;
 		decoded = true;
 		requireDevice();
+		if (!index.empty() && startBatches()) return;     // batches deliver as they come
 		std::vector<uint8_t> raw = input->readAllBytes();
 		const size_t usable = raw.size() >= trailerBytes ? raw.size() - trailerBytes : raw.size();
 		std::unique_ptr<PinnedBuffer> pin(new PinnedBuffer());
 		PinnedBuffer pout;
 		pin->reserve(raw.size() + 64);
 		if (!raw.empty()) memcpy(pin->p, raw.data(), raw.size());
-		if (!index.empty() && startBatches(pin, usable)) { /* batches deliver as they come */ }
-		else if (!index.empty()) decodeIndexed(*pin, pout, usable);
+		if (!index.empty()) decodeIndexed(*pin, pout, usable);
 		else decodeSerial(*pin, pout, usable);
 		if (endExactly && status == 0 && !moreBatches()) {               // Open.finish, Open.java:113-124
 			input->reset();
@@ -786,7 +814,7 @@ public:
 		if ((uint32_t)length != el) throw DataFormatException(DataFormatException::Reason::DECOMPRESSED_SIZE_MISMATCH, "Decompressed size mismatch");
 		return -1;
 	}
-	void close() override { raw->close(); inflater.reset(); }
+	void close() override { inflater.reset(); raw->close(); }
 private:
 	InputStream *raw;
 	GzipMetadata metadata;

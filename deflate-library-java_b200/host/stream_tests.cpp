@@ -4,7 +4,8 @@
 //       underlying stream to stand exactly at its end (:557-558); failures must carry the expected Reason (:587-593).
 //   test/io/nayuki/deflate/DeflaterOutputStreamTest.java:24-115   five round-trip tests (empty, short random, mixed
 //       write(int) / write(b,off,len), byte runs, long random with mostly single-byte writes).
-//   plus the argument / state contract of InflaterInputStream.java:96-106,147-179 and DeflaterOutputStream.java:55-116.
+//   plus the argument / state contract of InflaterInputStream.java:96-106,147-179 and DeflaterOutputStream.java:55-116,
+//   and the GPU build's batched decode of indexed streams (input read batch by batch from the underlying stream).
 // Usage: stream_tests <vectors.txt>   (lines: name hexbytes ok|fail hexoutput|REASON ; "-" = empty)
 // Prints one line per failed check and "passed N checks" at the end; exit code 1 if any check failed.
 #include <fstream>
@@ -138,6 +139,92 @@ static void deflaterTests() {
 	}
 }
 
+// an InputStream that hands out a few hundred bytes per call (a pipe, a socket): the batched reader has to loop
+struct DribbleStream : ByteArrayInputStream {
+	using ByteArrayInputStream::ByteArrayInputStream;
+	long read(uint8_t *b, size_t off, size_t len) override { return ByteArrayInputStream::read(b, off, std::min<size_t>(len, 777)); }
+};
+
+// The GPU build's own extension: a stream with a chunk + block index and a known size is decoded in batches, and the
+// compressed bytes of batch k + 1 are READ from the underlying stream while batch k is consumed (B2D_GUNZIP_BATCH = 3
+// chunks here).  Same bytes, same checksum, same endExactly position as the one-shot decode; a stream that ends early
+// delivers what was whole and then throws UNEXPECTED_END_OF_STREAM.
+static void indexedBatchTests() {
+	std::vector<uint8_t> data;
+	for (int i = 0; i < 3000; i++) {                       // runs and noise: chunks of very different compressed sizes
+		if (rnd(3)) data.insert(data.end(), (size_t)rnd(400) + 1, (uint8_t)rng());
+		else { std::vector<uint8_t> r = randomBytes((size_t)rnd(300)); data.insert(data.end(), r.begin(), r.end()); }
+	}
+	DeflaterOptions o;
+	o.chunk_bytes = 1u << 16;
+	o.block_bytes = 1u << 14;
+	o.batch_bytes = 1u << 18;
+	ByteArrayOutputStream bout;
+	DeflaterOutputStream dout(bout, o);
+	dout.write(data.data(), 0, data.size());
+	dout.close();
+	const std::vector<uint8_t> comp = bout.toByteArray();
+	const ChunkIndex idx = dout.chunkIndex();
+	CHECK(idx.sizes.size() == (data.size() + o.chunk_bytes - 1) / o.chunk_bytes && idx.sizes.size() > 6, "indexed: chunk count");
+	uint32_t crcOneShot = 0;
+	{   // one-shot reference: no size hint -> not batched
+		ByteArrayInputStream bin(comp);
+		InflaterInputStream iin(bin, true);
+		iin.setChunkIndex(idx);
+		CHECK(iin.readAllBytes() == data, "indexed one-shot bytes");
+		crcOneShot = iin.crc32();
+	}
+	for (int variant = 0; variant < 2; variant++) {        // plain and dribbling underlying stream, 9 trailing bytes behind the data
+		std::vector<uint8_t> in = comp;
+		in.insert(in.end(), 9, (uint8_t)0xA5);
+		std::unique_ptr<ByteArrayInputStream> bin(variant ? new DribbleStream(in) : new ByteArrayInputStream(in));
+		InflaterInputStream iin(*bin, true);
+		iin.setChunkIndex(idx);
+		iin.setOutputSizeHint(data.size());
+		std::vector<uint8_t> back;
+		uint8_t buf[50000];
+		for (long r; (r = iin.read(buf, 0, (size_t)rnd(50000) + 1)) != -1;) back.insert(back.end(), buf, buf + r);
+		CHECK(back == data, "indexed batched bytes");
+		CHECK(iin.crc32() == crcOneShot, "indexed batched checksum");
+		CHECK(iin.consumedBytes() == comp.size(), "indexed batched consumed");
+		CHECK(bin->position() == comp.size(), "indexed batched endExactly position");
+	}
+	{   // checksum asked for before everything was read: the remaining batches are taken over, nothing is lost
+		ByteArrayInputStream bin(comp);
+		InflaterInputStream iin(bin, true);
+		iin.setChunkIndex(idx);
+		iin.setOutputSizeHint(data.size());
+		std::vector<uint8_t> back(1000);
+		CHECK(iin.read(back.data(), 0, 1000) == 1000, "indexed early checksum first read");
+		CHECK(iin.crc32() == crcOneShot, "indexed early checksum");
+		std::vector<uint8_t> rest = iin.readAllBytes();
+		back.insert(back.end(), rest.begin(), rest.end());
+		CHECK(back == data, "indexed early checksum bytes");
+	}
+	for (int variant = 0; variant < 2; variant++) {        // the stream ends inside chunk 5 (second batch) / inside chunk 1 (first batch)
+		uint64_t cut = 0;
+		const size_t cutChunk = variant ? 1 : 5;
+		for (size_t c = 0; c < cutChunk; c++) cut += idx.sizes[c];
+		cut += idx.sizes[cutChunk] / 2;
+		std::vector<uint8_t> in(comp.begin(), comp.begin() + (long)cut);
+		DribbleStream bin(in);
+		InflaterInputStream iin(bin, true);
+		iin.setChunkIndex(idx);
+		iin.setOutputSizeHint(data.size());
+		std::vector<uint8_t> back;
+		uint8_t buf[4096];
+		bool thrown = false;
+		try {
+			for (long r; (r = iin.read(buf, 0, sizeof buf)) != -1;) back.insert(back.end(), buf, buf + r);
+		} catch (const DataFormatException &e) {
+			thrown = e.getReason() == DataFormatException::Reason::UNEXPECTED_END_OF_STREAM;
+		}
+		CHECK(thrown, "indexed truncated: UNEXPECTED_END_OF_STREAM");
+		const size_t whole = (cutChunk / 3) * 3 * (size_t)o.chunk_bytes;         // the batches in front of the cut
+		CHECK(back.size() == whole && std::equal(back.begin(), back.end(), data.begin()), "indexed truncated: whole batches delivered first");
+	}
+}
+
 template <class E, class F> static bool throws(F f) {
 	try { f(); } catch (const E &) { return true; } catch (...) { return false; }
 	return false;
@@ -224,6 +311,7 @@ static void contractTests() {
 
 int main(int argc, char **argv) {
 	if (argc != 2) { fprintf(stderr, "Usage: stream_tests vectors.txt\n"); return 2; }
+	setenv("B2D_GUNZIP_BATCH", "3", 1);                       // indexedBatchTests: batches of three chunks
 	try {
 		std::ifstream f(argv[1]);
 		std::string line;
@@ -237,6 +325,7 @@ int main(int argc, char **argv) {
 		}
 		CHECK(nvec > 0, "vectors loaded");
 		deflaterTests();
+		indexedBatchTests();
 		contractTests();
 	} catch (const std::exception &e) {
 		fprintf(stderr, "FAIL unexpected exception: %s\n", e.what());
