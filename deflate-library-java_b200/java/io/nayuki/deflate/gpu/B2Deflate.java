@@ -32,10 +32,19 @@ public final class B2Deflate {
 	public static final int ERR_OUTPUT_OVERFLOW = -1;
 
 	private static final Linker LINKER = Linker.nativeLinker();
-	private static final SymbolLookup LIB = SymbolLookup.libraryLookup(
-		Path.of(System.getProperty("b2deflate.library", "libb2deflate.so")), Arena.global());
+	private static final SymbolLookup LIB = lookup();
+
+	/* null when the library is not there: available() then says no instead of the class failing to initialise */
+	private static SymbolLookup lookup() {
+		try {
+			return SymbolLookup.libraryLookup(Path.of(System.getProperty("b2deflate.library", "libb2deflate.so")), Arena.global());
+		} catch (IllegalArgumentException e) {
+			return null;
+		}
+	}
 
 	private static MethodHandle h(String name, FunctionDescriptor fd) {
+		if (LIB == null) return null;
 		return LINKER.downcallHandle(LIB.find(name).orElseThrow(() -> new UnsatisfiedLinkError(name)), fd);
 	}
 
@@ -62,6 +71,7 @@ public final class B2Deflate {
 		if (ready) return;
 		synchronized (B2Deflate.class) {
 			if (ready) return;
+			if (LIB == null) throw new IllegalStateException("libb2deflate.so not found (-Db2deflate.library=<path>)");
 			final int rc;
 			if ("all".equals(System.getProperty("b2deflate.devices"))) {
 				rc = call(() -> (int)INIT_DEVICES.invokeExact(MemorySegment.NULL, 0));
@@ -73,6 +83,17 @@ public final class B2Deflate {
 			}
 			if (rc != 0) throw new IllegalStateException(strerror(rc) + " [" + lastError() + "]");
 			ready = true;
+		}
+	}
+
+	/** What the patched constructors of InflaterInputStream / DeflaterOutputStream ask (INTEGRATION.md sections 2 and 3):
+	 *  true when the library loads and a GPU binds; the reference's own CPU classes stay in charge otherwise. */
+	public static boolean available() {
+		try {
+			requireDevice();
+			return true;
+		} catch (IllegalStateException e) {
+			return false;
 		}
 	}
 
