@@ -62,16 +62,14 @@ public final class GpuInflater {
 		MemorySegment in = B2Deflate.allocPinned(raw.length + 64L);
 		try (Arena a = Arena.ofConfined()) {
 			MemorySegment.copy(raw, 0, in, JAVA_BYTE, 0, raw.length);
-			MemorySegment inOff = a.allocate(JAVA_LONG, 2), outOff = a.allocate(JAVA_LONG, 2);
 			MemorySegment oLen = a.allocate(JAVA_LONG), cons = a.allocate(JAVA_LONG);
 			MemorySegment crc = a.allocate(JAVA_INT), st = a.allocate(JAVA_INT);
-			inOff.setAtIndex(JAVA_LONG, 1, raw.length);
 			long cap = Math.max(1 << 16, 6L * raw.length);
 			while (true) {                       // the decompressed size is unknown up front: grow and retry on overflow
 				out = B2Deflate.allocPinned(cap + 64);
-				outOff.setAtIndex(JAVA_LONG, 1, cap);
-				int rc = B2Deflate.inflateBatch(in, inOff, 1, out, outOff, oLen, cons, crc, st, B2Deflate.INFLATE_CRC32);
-				if (rc != 0) throw new IOException("b2d_inflate_batch: " + B2Deflate.strerror(rc) + " [" + B2Deflate.lastError() + "]");
+				// one stream nobody indexed: speculative parallel decode, the sequential decoder behind it (b2d_inflate_stream)
+				int rc = B2Deflate.inflateStream(in, raw.length, out, cap, oLen, cons, crc, st, B2Deflate.INFLATE_CRC32);
+				if (rc != 0) throw new IOException("b2d_inflate_stream: " + B2Deflate.strerror(rc) + " [" + B2Deflate.lastError() + "]");
 				if (st.get(JAVA_INT, 0) != B2Deflate.ERR_OUTPUT_OVERFLOW) break;
 				B2Deflate.freePinned(out);
 				cap = cap * 2 + (1 << 20);
