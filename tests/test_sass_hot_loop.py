@@ -51,3 +51,36 @@ def test_symbol_loop_of_the_member_decoder_has_no_local_memory_traffic(kernel):
     # ... and no local memory, no global load, no shuffle, no convergence barrier
     bad = [ins for ins in body if re.search(r"\b(LDL|STL|LDG|SHFL|BSSY|BSYNC|BREAK)\b", ins)]
     assert not bad, bad
+
+
+def _resources(obj):
+    out = subprocess.run(["cuobjdump", "--dump-resource-usage", obj], capture_output=True, text=True, check=True).stdout
+    res, name = {}, None
+    for ln in out.splitlines():
+        m = re.search(r"Function (\S+):", ln)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+) STACK:(\d+) SHARED:(\d+) LOCAL:(\d+)", ln)
+        if m and name:
+            res[name] = dict(zip(("reg", "stack", "shared", "local"), map(int, m.groups())))
+    return res
+
+
+@pytest.mark.skipif(shutil.which("cuobjdump") is None or not os.path.exists(OBJ), reason="needs the built objects and cuobjdump")
+def test_resident_warps_per_sm_of_the_decoders():
+    """the 4096 members of config 2 are ONE wave because 7 CTAs of 4 warps fit an SM -- 72 registers per
+    thread (7 x 128 x 72 <= 65536) and 33216 B of shared memory per CTA incl. the 1 KiB the driver reserves
+    (7 x 33216 <= 233472).  One more register or 200 more bytes and a quarter of the members wait for a second wave.
+    No kernel of the library may use local memory beyond its call stack."""
+    res = _resources(OBJ)
+    decoders = [k for k in res if re.search(r"(14inflate_kernel|20inflate_units_kernel|19stream_units_kernel)", k)]
+    assert len(decoders) == 4, sorted(res)
+    for k in decoders:
+        r = res[k]
+        assert r["reg"] * 128 * 7 <= 65536 and r["shared"] * 7 <= 233472, (k, r)
+    for name in ("deflate.cu.o", "crc32.cu.o"):
+        res.update(_resources(os.path.join(os.path.dirname(OBJ), name)))
+    assert len(res) >= 25 and all(r["local"] == 0 for r in res.values()), {k: r for k, r in res.items() if r["local"]}
+    # the search kernel owns its SM (one CTA of 1024 threads): 64 registers is the hard limit there
+    match = next(r for k, r in res.items() if "12match_kernel" in k)
+    assert match["reg"] <= 64, match
