@@ -151,3 +151,45 @@ def test_output_overflow_reports_prefix(oracle):
     comp = zlib_raw(data)
     st, out, _ = oracle.inflate(comp, out_cap=100)
     assert st == oracle.OUTPUT_OVERFLOW and out == data[:100]
+
+
+def test_mutated_streams_accept_reject_like_zlib(oracle):
+    """Differential check of the restatement against an independent decoder: 3000 zlib-made streams (levels 1/6/9,
+    default / fixed / Huffman-only / RLE strategies) with 1-3 mutations each (bit flip, byte overwrite, truncation).
+    zlib classifies errors more coarsely and later than Open.java, but the three verdicts line up: the oracle
+    accepts exactly what zlib accepts (same bytes, same consumed input), reports UNEXPECTED_END_OF_STREAM exactly where
+    zlib wants more input, and a format Reason exactly where zlib raises an error."""
+    rng = random.Random(99)
+    words = [bytes(rng.choices(b"etaoinshrdlu ,.\n", k=rng.randrange(1, 9))) for _ in range(300)]
+    verdicts = {}
+    for _ in range(3000):
+        n = rng.choice([50, 300, 2000, 9000])
+        text = bytearray()
+        while len(text) < n:
+            text += rng.choice(words)
+        base = bytearray(zlib_raw(bytes(text[:n]), rng.choice([1, 6, 9]),
+                                  rng.choice([zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE])))
+        for _ in range(rng.randrange(1, 4)):
+            if len(base) < 2:
+                break
+            m = rng.randrange(3)
+            if m == 0:
+                base[rng.randrange(len(base))] ^= 1 << rng.randrange(8)
+            elif m == 1 and len(base) > 4:
+                del base[rng.randrange(1, len(base)):]
+            else:
+                base[rng.randrange(len(base))] = rng.randrange(256)
+        data = bytes(base)
+        st, out, consumed = oracle.inflate(data, out_cap=1 << 20)
+        d = zlib.decompressobj(-15)
+        try:
+            zout = d.decompress(data)
+            z = "ok" if d.eof else "more"
+        except zlib.error:
+            z = "error"
+        mine = "ok" if st == 0 else "more" if oracle.status_name(st) == "UNEXPECTED_END_OF_STREAM" else "error"
+        assert mine == z, (oracle.status_name(st), z, data.hex()[:80])
+        if st == 0:
+            assert out == zout and consumed == len(data) - len(d.unused_data)
+        verdicts[mine] = verdicts.get(mine, 0) + 1
+    assert min(verdicts.get(k, 0) for k in ("ok", "more", "error")) > 300, verdicts
