@@ -193,3 +193,44 @@ def test_mutated_streams_accept_reject_like_zlib(oracle):
             assert out == zout and consumed == len(data) - len(d.unused_data)
         verdicts[mine] = verdicts.get(mine, 0) + 1
     assert min(verdicts.get(k, 0) for k in ("ok", "more", "error")) > 300, verdicts
+
+
+def test_mutated_gzip_and_zlib_members_accept_reject_like_python(oracle):
+    """The container restatements (GzipInputStream.java:66-90, ZlibInputStream.java:64-83: body, then CRC-32 + ISIZE /
+    Adler-32) against Python's gzip and zlib modules: 3000 members, most with 1-2 mutations behind the header (bit flip,
+    byte overwrite, truncation).  Accepted by one <=> accepted by the other, with the same bytes."""
+    import gzip
+    rng = random.Random(5)
+    words = [bytes(rng.choices(b"etaoinshrdlu ,.\n", k=rng.randrange(1, 9))) for _ in range(300)]
+    seen = set()
+    for _ in range(3000):
+        text = bytearray()
+        n = rng.choice([0, 1, 50, 300, 5000])
+        while len(text) < n:
+            text += rng.choice(words)
+        data = bytes(text[:n])
+        is_gzip = rng.random() < 0.5
+        base = bytearray(gzip.compress(data, rng.choice([1, 6, 9]), mtime=0) if is_gzip else zlib.compress(data, rng.choice([1, 6, 9])))
+        hdr = 10 if is_gzip else 2
+        if rng.random() < 0.85:
+            for _ in range(rng.randrange(1, 3)):
+                m = rng.randrange(3)
+                if m == 0:
+                    base[rng.randrange(hdr, len(base))] ^= 1 << rng.randrange(8)
+                elif m == 1 and len(base) > hdr + 2:
+                    del base[rng.randrange(hdr + 1, len(base)):]
+                else:
+                    base[rng.randrange(hdr, len(base))] = rng.randrange(256)
+        member = bytes(base)
+        st, out, _ = (oracle.gunzip if is_gzip else oracle.unzlib)(member, out_cap=1 << 16)
+        try:
+            ref = gzip.decompress(member) if is_gzip else zlib.decompress(member)
+        except Exception:
+            ref = None
+        assert (st == 0) == (ref is not None), (is_gzip, oracle.status_name(st), member.hex()[:80])
+        if st == 0:
+            assert out == ref
+        seen.add((is_gzip, oracle.status_name(st)))
+    for is_gzip in (True, False):
+        assert {(is_gzip, "OK"), (is_gzip, "DECOMPRESSED_CHECKSUM_MISMATCH"), (is_gzip, "UNEXPECTED_END_OF_STREAM")} <= seen
+    assert (True, "DECOMPRESSED_SIZE_MISMATCH") in seen
