@@ -152,3 +152,60 @@ def test_every_token_is_the_reference_rule_choice(oracle, name, lookahead, histo
                     assert t == (run, dist), (name, strat, pos, t, (run, dist))
                     pos += run
             assert pos == end
+
+
+@pytest.mark.parametrize("name", ["text", "runs", "mixed", "period3", "one", "two", "zeros", "empty", "bytes256"])
+@pytest.mark.parametrize("lookahead,history", [(1 << 16, 1 << 15), (700, 1 << 15), (512, 200)])
+def test_oracle_bytes_equal_the_python_restatement(oracle, name, lookahead, history):
+    """Byte equality of the two restatements of comp/Lz77Huffman.java + DeflaterOutputStream.java (tests/ref_model.py vs
+    oracle/oracle_deflate.c) for all six presets: search, symbolisation, histogram fix-ups, package-merge with the
+    reference's tie order, code-length run-length coding, header, canonical codes, bit order, block framing."""
+    import ref_model
+    inputs = dict(_inputs(), empty=b"", bytes256=bytes(range(256)) * 3)
+    data = inputs[name]
+    for preset in ref_model.PRESETS:
+        mine = ref_model.deflate(data, preset, lookahead, history)
+        theirs = oracle.deflate(data, (getattr(oracle, preset),), lookahead=lookahead, history=history)
+        assert mine == theirs, (name, preset, mine.hex()[:60], theirs.hex()[:60])
+
+
+@pytest.mark.parametrize("lookahead,history", [(1 << 16, 1 << 15), (700, 1 << 15), (512, 200)])
+def test_uncompressed_and_multistrategy_bytes_equal_the_python_restatement(oracle, lookahead, history):
+    """comp/Uncompressed.java:19-48 (cost per start bit, blocks of at most 65535 bytes) and comp/MultiStrategy.java:31-57
+    (cheapest substrategy for the bit position the block starts at) in both restatements: equal bytes."""
+    import ref_model
+    rng = random.Random(31)
+    inputs = dict(_inputs(), empty=b"", noise=rng.randbytes(2500), noise_then_text=rng.randbytes(1500) + _inputs()["text"][:1500],
+                  long_noise=rng.randbytes(66000 if lookahead > 65535 else 3000))
+    combos = [("UNCOMPRESSED",), ("UNCOMPRESSED", "FULL_STATIC", "FULL_DYNAMIC"), ("RLE_DYNAMIC", "UNCOMPRESSED"),
+              ("LITERAL_STATIC", "LITERAL_DYNAMIC", "UNCOMPRESSED")]
+    for name, data in inputs.items():
+        if len(data) > 4000 and lookahead > 65535:
+            use = [c for c in combos if all(x in ("UNCOMPRESSED", "RLE_DYNAMIC", "LITERAL_STATIC", "LITERAL_DYNAMIC") for x in c)]
+        else:
+            use = combos
+        for combo in use:
+            mine = ref_model.deflate(data, list(combo), lookahead, history)
+            theirs = oracle.deflate(data, tuple(getattr(oracle, x) for x in combo), lookahead=lookahead, history=history)
+            assert mine == theirs, (name, combo, len(mine), len(theirs), mine.hex()[:60], theirs.hex()[:60])
+
+
+@pytest.mark.parametrize("min_block", [100, 400])
+def test_binary_split_bytes_equal_the_python_restatement(oracle, min_block):
+    """comp/BinarySplit.java:30-98 in both restatements (recursive halving while a split is cheaper, kept per start bit
+    position, costs summed from position 0 as the reference does): equal bytes, on data whose statistics change."""
+    import ref_model
+    rng = random.Random(41)
+    inp = _inputs()
+    datas = {"mixed": inp["mixed"][600:2600], "noise_then_text": rng.randbytes(900) + inp["text"][:900],
+             "runs_noise_runs": inp["runs"][:700] + rng.randbytes(500) + inp["runs"][1200:1900]}
+    n_split = 0
+    for name, data in datas.items():
+        for combo in (("FULL_DYNAMIC",), ("RLE_DYNAMIC",), ("UNCOMPRESSED", "FULL_STATIC", "FULL_DYNAMIC")):
+            for lookahead in (1 << 16, 1100):
+                mine = ref_model.deflate(data, list(combo), lookahead, 1 << 15, split_min_block_len=min_block)
+                theirs, blocks = oracle.deflate_split(data, tuple(getattr(oracle, x) for x in combo), min_block_len=min_block,
+                                                      lookahead=lookahead)
+                assert mine == theirs, (name, combo, lookahead, len(mine), len(theirs))
+                n_split += blocks > -(-len(data) // lookahead)
+    assert n_split > 0                                     # (the splitter did cut somewhere)
