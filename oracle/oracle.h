@@ -16,7 +16,9 @@
  * (tests/golden/inflate_vectors.json, extracted from InflaterInputStreamTest.java:24-510) and
  * cross-checked against system zlib.  The encoder has NO golden bytes in the reference
  * (DeflaterOutputStreamTest.java only round-trips) and no JVM exists in this image, so encoder
- * byte-level parity is UNPINNED; it is pinned only by round-trips through oracle_inflate + zlib.
+ * byte-level parity is UNPINNED by the reference; what pins it here: round trips through oracle_inflate
+ * + zlib, the cross-check rows of SURVEY.md Appendix F, and byte equality with a second, independent
+ * restatement of the same Java in plain Python (tests/ref_model.py, tests/test_oracle_tokens.py).
  */
 #ifndef B2D_ORACLE_H
 #define B2D_ORACLE_H
@@ -94,7 +96,8 @@ size_t oracle_deflate(const uint8_t *in, size_t n, const int *strategies, int n_
  * substrategy = the single strategy or the MultiStrategy of `strategies`: every lookahead block is recursively cut in
  * halves while a cut makes it smaller, halves no shorter than min_block_len + 1.  *n_blocks (optional) = number of
  * blocks chosen, judged at bit position 0.  The reference never uses BinarySplit by default and has no test for it:
- * pinned by round trips and by never being larger than the unsplit stream. */
+ * pinned by round trips, by never being larger than the unsplit stream, and by byte equality with the Python
+ * restatement of tests/ref_model.py. */
 size_t oracle_deflate_split(const uint8_t *in, size_t n, const int *strategies, int n_strategies,
                             int lookahead, int history, int search, int min_block_len,
                             uint8_t *out, size_t cap, size_t *n_blocks);

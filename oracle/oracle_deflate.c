@@ -12,7 +12,8 @@
  *
  * Encoder byte-level parity is UNPINNED (the reference has no golden compressed bytes and no JVM exists
  * here); this restatement is validated by round trips through oracle_inflate and zlib and by the
- * cross-check rows of SURVEY.md Appendix F.
+ * cross-check rows of SURVEY.md Appendix F, and by byte equality with tests/ref_model.py (the same Java restated
+ * a second time, in plain Python, with none of this file's data structures).
  *
  * The match search is the reference's greedy "longest run, ties to the smallest distance" rule
  * (Lz77Huffman.java:68-84).  search=1 runs the literal brute-force scan; search=0 enumerates the same
