@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE.  The reference holds no golden compressed bytes and no JVM exists here, so the C
 oracle's encoder cannot be pinned against the real thing.  What can be done is to state the same Java twice, in two
-languages and two shapes, and demand equal bytes: this file follows comp/Lz77Huffman.java line by line in its simplest
+languages and two shapes, and demand equal bytes: this file restates comp/Lz77Huffman.java rule by rule in its simplest
 form (brute-force search, Python's stable sort standing in for Collections.sort, lists of symbols standing in for the node
 objects), where oracle/oracle_deflate.c uses hash chains, rank arithmetic and bit buffers.
 Paths relative to /root/reference/src/io/nayuki/deflate/.
